@@ -1,0 +1,5 @@
+"""`modules.pointnet` alias (reference: modules/pointnet.py)."""
+from pvcnn_b200.nn.pointnet import *  # noqa: F401,F403
+from pvcnn_b200.nn import pointnet as _impl
+
+__all__ = [n for n in dir(_impl) if not n.startswith("_") and isinstance(getattr(_impl, n), type)]

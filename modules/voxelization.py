@@ -1,0 +1,5 @@
+"""`modules.voxelization` alias (reference: modules/voxelization.py)."""
+from pvcnn_b200.nn.voxelization import *  # noqa: F401,F403
+from pvcnn_b200.nn import voxelization as _impl
+
+__all__ = [n for n in dir(_impl) if not n.startswith("_") and isinstance(getattr(_impl, n), type)]

@@ -1,0 +1,709 @@
+// point_ops.cu -- sm_100a kernels behind the reference's launcher-level interface
+// (mit-han-lab/pvcnn modules/functional/src/*/*.cuh), in the reference's own tensor layouts.
+//
+// Design differences from the reference kernels (which all launch <<<B, <=512>>>, i.e. use at most
+// B of the 148 SMs): every kernel here tiles (batch x points x channels) so that the
+// grid covers the whole chip, reads/writes are coalesced along the point dimension, scatter
+// reductions are warp-aggregated before they reach L2, zero-fills are issued by the callee, and
+// everything runs on the caller's stream.
+#include "common.cuh"
+
+namespace pvb {
+unsigned long long g_launches = 0;
+
+// =====================================================================================
+// Coordinate normalisation  (modules/voxelization.py:16-25)
+// One CTA per batch element: fp64 block reduction for the mean, NaN-propagating max-norm.
+// =====================================================================================
+template <typename T, typename Op>
+__device__ __forceinline__ T block_allreduce(T v, Op op, T *smem /* >= 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  T r = smem[0];
+  for (int w = 1; w < nwarp; ++w) r = op(r, smem[w]);
+  return r;
+}
+
+struct OpAddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct OpMaxNan {
+  __device__ float operator()(float a, float b) const { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+};
+
+__global__ void __launch_bounds__(512) voxelize_coords_kernel(int n, int r, int normalize, float eps,
+                                                              const float *__restrict__ coords,
+                                                              float *__restrict__ norm_coords,
+                                                              int *__restrict__ vox_coords) {
+  __shared__ double sd[32];
+  __shared__ float sf[32];
+  const int b = blockIdx.x;
+  const float *c = coords + (size_t)b * 3 * n;
+  float mean[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)c[a * n + i];
+    s = block_allreduce(s, OpAddD(), sd);
+    mean[a] = (float)(s / (double)n);
+  }
+  float denom = 1.0f;
+  if (normalize) {
+    float mx = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float x = __fsub_rn(c[i], mean[0]), y = __fsub_rn(c[n + i], mean[1]), z = __fsub_rn(c[2 * n + i], mean[2]);
+      float s = __fmul_rn(x, x);
+      s = __fadd_rn(s, __fmul_rn(y, y));
+      s = __fadd_rn(s, __fmul_rn(z, z));
+      mx = OpMaxNan()(__fsqrt_rn(s), mx);
+    }
+    mx = block_allreduce(mx, OpMaxNan(), sf);
+    denom = __fadd_rn(__fmul_rn(mx, 2.0f), eps);
+  }
+  const float rf = (float)r, hi = (float)(r - 1);
+  for (int idx = threadIdx.x; idx < 3 * n; idx += blockDim.x) {
+    const int a = idx / n;
+    float v = __fsub_rn(c[idx], a == 0 ? mean[0] : (a == 1 ? mean[1] : mean[2]));
+    if (normalize) v = __fadd_rn(__fdiv_rn(v, denom), 0.5f);
+    else v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    v = __fmul_rn(v, rf);
+    if (v < 0.0f) v = 0.0f;
+    if (v > hi) v = hi;
+    norm_coords[(size_t)b * 3 * n + idx] = v;
+    vox_coords[(size_t)b * 3 * n + idx] = __float2int_rn(v);
+  }
+}
+
+// =====================================================================================
+// avg_voxelize  (vox.cu:18-72).  K1: voxel index + count.  K2: scatter-mean.
+// =====================================================================================
+__global__ void __launch_bounds__(256) vox_index_count_kernel(int n, int r, int r2, int r3, long long total,
+                                                              const int *__restrict__ coords,
+                                                              int *__restrict__ ind, int *__restrict__ cnt) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(t / n), i = (int)(t % n);
+    const int *co = coords + (size_t)b * 3 * n;
+    const int v = co[i] * r2 + co[i + n] * r + co[i + 2 * n];
+    ind[t] = v;
+    atomicAdd(cnt + (size_t)b * r3 + v, 1);
+  }
+}
+
+// Sum of v over the lanes of `grp` in ascending lane order; every lane of the group gets the total.
+__device__ __forceinline__ float group_sum_ordered(unsigned grp, float v) {
+  float acc = 0.0f;
+  for (unsigned m = grp; m; m &= m - 1) acc = __fadd_rn(acc, __shfl_sync(grp, v, __ffs(m) - 1));
+  return acc;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) vox_scatter_kernel(int c, int n, int r3, const int *__restrict__ ind,
+                                                          const int *__restrict__ cnt,
+                                                          const float *__restrict__ feat,
+                                                          float *__restrict__ out) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  const int pos = valid ? ind[(size_t)b * n + i] : -1 - lane;
+  // lanes that hit the same voxel are pre-reduced in registers; one atomic per (voxel, channel)
+  const unsigned grp = __match_any_sync(0xffffffffu, pos);
+  const bool leader = (__ffs(grp) - 1) == lane;
+  const bool multi = __any_sync(0xffffffffu, grp != (1u << lane));
+  float inv = 0.0f;
+  if (valid) inv = (float)(1.0 / (double)(float)cnt[(size_t)b * r3 + pos]);  // vox.cu:66
+  const float *f = feat + ((size_t)b * c + c0) * n + i;
+  float *o = out + ((size_t)b * c + c0) * r3 + pos;
+  const int cmax = min(CT, c - c0);
+  for (int j = 0; j < cmax; ++j) {
+    float v = valid ? __fmul_rn(f[(size_t)j * n], inv) : 0.0f;
+    if (multi) v = group_sum_ordered(grp, v);
+    if (valid && leader) atomicAdd(o + (size_t)j * r3, v);
+  }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) vox_grad_kernel(int c, int n, int r3, const int *__restrict__ ind,
+                                                       const int *__restrict__ cnt,
+                                                       const float *__restrict__ grad_y,
+                                                       float *__restrict__ grad_x) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int pos = ind[(size_t)b * n + i];
+  const int cur = cnt[(size_t)b * r3 + pos];
+  const float inv = cur > 0 ? (float)(1.0 / (double)(float)cur) : 0.0f;
+  const float *gy = grad_y + ((size_t)b * c + c0) * r3 + pos;
+  float *gx = grad_x + ((size_t)b * c + c0) * n + i;
+  const int cmax = min(CT, c - c0);
+#pragma unroll 4
+  for (int j = 0; j < cmax; ++j) gx[(size_t)j * n] = cur > 0 ? __fmul_rn(__ldg(gy + (size_t)j * r3), inv) : 0.0f;
+}
+
+// =====================================================================================
+// trilinear_devoxelize  (trilinear_devox.cu:21-162)
+// =====================================================================================
+struct Corner8 {
+  float w[8];
+  int idx[8];
+};
+__device__ __forceinline__ void devox_setup(float x, float y, float z, int r, int r2, Corner8 &k) {
+  const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+  const float xd1 = __fsub_rn(x, xl), yd1 = __fsub_rn(y, yl), zd1 = __fsub_rn(z, zl);
+  const float xd0 = __fsub_rn(1.0f, xd1), yd0 = __fsub_rn(1.0f, yd1), zd0 = __fsub_rn(1.0f, zd1);
+  const float a00 = __fmul_rn(xd0, yd0), a01 = __fmul_rn(xd0, yd1), a10 = __fmul_rn(xd1, yd0),
+              a11 = __fmul_rn(xd1, yd1);
+  k.w[0] = __fmul_rn(a00, zd0); k.w[1] = __fmul_rn(a00, zd1);
+  k.w[2] = __fmul_rn(a01, zd0); k.w[3] = __fmul_rn(a01, zd1);
+  k.w[4] = __fmul_rn(a10, zd0); k.w[5] = __fmul_rn(a10, zd1);
+  k.w[6] = __fmul_rn(a11, zd0); k.w[7] = __fmul_rn(a11, zd1);
+  const int xlo = (int)xl, ylo = (int)yl, zlo = (int)zl;
+  const int dz = zd1 > 0 ? 1 : 0, dy = yd1 > 0 ? r : 0, dx = xd1 > 0 ? r2 : 0;  // trilinear_devox.cu:64-75
+  k.idx[0] = xlo * r2 + ylo * r + zlo;
+  k.idx[1] = k.idx[0] + dz;
+  k.idx[2] = k.idx[0] + dy;
+  k.idx[3] = k.idx[2] + dz;
+  k.idx[4] = k.idx[0] + dx;
+  k.idx[5] = k.idx[4] + dz;
+  k.idx[6] = k.idx[4] + dy;
+  k.idx[7] = k.idx[6] + dz;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) devox_kernel(int c, int n, int r, int r2, int r3, int training,
+                                                    const float *__restrict__ coords,
+                                                    const float *__restrict__ feat, int *__restrict__ inds,
+                                                    float *__restrict__ wgts, float *__restrict__ outs) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *co = coords + (size_t)b * 3 * n;
+  Corner8 k;
+  devox_setup(co[i], co[i + n], co[i + 2 * n], r, r2, k);
+  if (training && blockIdx.y == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      wgts[((size_t)b * 8 + q) * n + i] = k.w[q];
+      inds[((size_t)b * 8 + q) * n + i] = k.idx[q];
+    }
+  }
+  const float *f = feat + ((size_t)b * c + c0) * r3;
+  float *o = outs + ((size_t)b * c + c0) * n + i;
+  const int cmax = min(CT, c - c0);
+#pragma unroll 2
+  for (int j = 0; j < cmax; ++j) {
+    const float *fj = f + (size_t)j * r3;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldg(fj + k.idx[q]);
+    float acc = __fmul_rn(k.w[0], v[0]);
+#pragma unroll
+    for (int q = 1; q < 8; ++q) acc = __fmaf_rn(k.w[q], v[q], acc);
+    o[(size_t)j * n] = acc;
+  }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) devox_grad_kernel(int c, int n, int r3, const int *__restrict__ inds,
+                                                         const float *__restrict__ wgts,
+                                                         const float *__restrict__ grad_y,
+                                                         float *__restrict__ grad_x) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int idx[8];
+  float w[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    idx[q] = inds[((size_t)b * 8 + q) * n + i];
+    w[q] = wgts[((size_t)b * 8 + q) * n + i];
+  }
+  const float *gy = grad_y + ((size_t)b * c + c0) * n + i;
+  float *gx = grad_x + ((size_t)b * c + c0) * r3;
+  const int cmax = min(CT, c - c0);
+  for (int j = 0; j < cmax; ++j) {
+    const float g = gy[(size_t)j * n];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(gx + (size_t)j * r3 + idx[q], __fmul_rn(w[q], g));
+  }
+}
+
+// =====================================================================================
+// ball_query  (ball_query.cu:19-50): warp per query over a shared-memory point tile.
+// Ordered ballot compaction keeps the reference's "first U by index" semantics; the final
+// row is hits[0..cnt) followed by hits[0] repeated (or zeros when there is no hit).
+// =====================================================================================
+constexpr int BQ_WARPS = 8, BQ_QPW = 4, BQ_TILE = 2048;
+
+__global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(int n, int m, float r2, int u,
+                                                                   const float *__restrict__ centers,
+                                                                   const float *__restrict__ points,
+                                                                   int *__restrict__ out) {
+  __shared__ float sp[3][BQ_TILE];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *p = points + (size_t)b * 3 * n;
+  const float *ce = centers + (size_t)b * 3 * m;
+  const int q0 = (blockIdx.x * BQ_WARPS + warp) * BQ_QPW;
+  float cx[BQ_QPW], cy[BQ_QPW], cz[BQ_QPW];
+  int cnt[BQ_QPW], first[BQ_QPW];
+#pragma unroll
+  for (int q = 0; q < BQ_QPW; ++q) {
+    const int j = q0 + q;
+    cx[q] = j < m ? ce[j] : 0.f;
+    cy[q] = j < m ? ce[j + m] : 0.f;
+    cz[q] = j < m ? ce[j + 2 * m] : 0.f;
+    cnt[q] = j < m ? 0 : u;  // out-of-range queries are "done"
+    first[q] = 0;
+  }
+  for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
+    bool warp_done = true;
+#pragma unroll
+    for (int q = 0; q < BQ_QPW; ++q) warp_done = warp_done && (cnt[q] >= u);
+    if (__syncthreads_and(warp_done)) break;  // also fences the previous tile's readers
+    const int tn = min(BQ_TILE, n - t0);
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+      sp[0][k] = p[t0 + k];
+      sp[1][k] = p[t0 + k + n];
+      sp[2][k] = p[t0 + k + 2 * n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BQ_QPW; ++q) {
+      if (cnt[q] >= u) continue;  // warp-uniform
+      int *row = out + ((size_t)b * m + (q0 + q)) * u;
+      for (int base = 0; base < tn && cnt[q] < u; base += 32) {
+        const int k = base + lane;
+        bool hit = false;
+        if (k < tn) hit = sqdist(cx[q] - sp[0][k], cy[q] - sp[1][k], cz[q] - sp[2][k]) < r2;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+          if (cnt[q] == 0) first[q] = t0 + base + __ffs(bal) - 1;
+          const int slot = cnt[q] + __popc(bal & ((1u << lane) - 1));
+          if (hit && slot < u) row[slot] = t0 + k;
+          cnt[q] += __popc(bal);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < BQ_QPW; ++q) {
+    const int j = q0 + q;
+    if (j >= m) continue;
+    int *row = out + ((size_t)b * m + j) * u;
+    const int have = min(cnt[q], u);
+    for (int v = have + lane; v < u; v += 32) row[v] = first[q];  // first==0 when no hit at all
+  }
+}
+
+// =====================================================================================
+// grouping / gather  (grouping.cu:18-77, sampling.cu:17-66)
+// =====================================================================================
+template <int CT>
+__global__ void __launch_bounds__(256) grouping_kernel(int c, int n, int mu, const float *__restrict__ feat,
+                                                       const int *__restrict__ idx, float *__restrict__ out) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= mu) return;
+  const int src = idx[(size_t)b * mu + e];
+  const float *f = feat + ((size_t)b * c + c0) * n + src;
+  float *o = out + ((size_t)b * c + c0) * mu + e;
+  const int cmax = min(CT, c - c0);
+#pragma unroll 4
+  for (int j = 0; j < cmax; ++j) o[(size_t)j * mu] = __ldg(f + (size_t)j * n);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256) grouping_grad_kernel(int c, int n, int mu, const float *__restrict__ grad_y,
+                                                            const int *__restrict__ idx,
+                                                            float *__restrict__ grad_x) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e < mu;
+  const int dst = valid ? idx[(size_t)b * mu + e] : -1 - lane;
+  // ball_query pads rows with the first hit, so neighbouring lanes very often share dst
+  const unsigned grp = __match_any_sync(0xffffffffu, dst);
+  const bool leader = (__ffs(grp) - 1) == lane;
+  const bool multi = __any_sync(0xffffffffu, grp != (1u << lane));
+  const float *gy = grad_y + ((size_t)b * c + c0) * mu + e;
+  float *gx = grad_x + ((size_t)b * c + c0) * n + dst;
+  const int cmax = min(CT, c - c0);
+  for (int j = 0; j < cmax; ++j) {
+    float v = valid ? gy[(size_t)j * mu] : 0.0f;
+    if (multi) v = group_sum_ordered(grp, v);
+    if (valid && leader) atomicAdd(gx + (size_t)j * n, v);
+  }
+}
+
+// =====================================================================================
+// furthest point sampling  (sampling.cu:86-167)
+// One CTA of 1024 threads per batch element; points and running distances live in registers
+// (PPT points per thread), one __syncthreads per round, integer REDUX reductions.
+// Tie-break = the reference's: max distance, then smallest (k mod 512), then smallest k.
+// =====================================================================================
+constexpr int FPS_THREADS = 1024;
+
+__device__ __forceinline__ unsigned fps_tie_key(int k) { return ((unsigned)(k & 511) << 22) | ((unsigned)k >> 9); }
+__device__ __forceinline__ int fps_key_to_k(unsigned key) { return (int)(((key & 0x3FFFFFu) << 9) | (key >> 22)); }
+
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_kernel(int n, int m, int coords_in_smem,
+                                                             const float *__restrict__ coords,
+                                                             int *__restrict__ indices) {
+  extern __shared__ float s_xyz[];  // [3][n] when coords_in_smem
+  __shared__ unsigned s_d[2][32], s_k[2][32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *co = coords + (size_t)b * 3 * n;
+  int *out = indices + (size_t)b * m;
+  float px[PPT], py[PPT], pz[PPT], dist[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int k = tid + p * FPS_THREADS;
+    const bool v = k < n;
+    px[p] = v ? co[k] : 0.f;
+    py[p] = v ? co[k + n] : 0.f;
+    pz[p] = v ? co[k + 2 * n] : 0.f;
+    dist[p] = 1e38f;
+    if (coords_in_smem && v) {
+      s_xyz[k] = px[p];
+      s_xyz[n + k] = py[p];
+      s_xyz[2 * n + k] = pz[p];
+    }
+  }
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    float x1, y1, z1;
+    if (coords_in_smem) {
+      x1 = s_xyz[old]; y1 = s_xyz[n + old]; z1 = s_xyz[2 * n + old];
+    } else {
+      x1 = __ldg(co + old); y1 = __ldg(co + old + n); z1 = __ldg(co + old + 2 * n);
+    }
+    // per-thread best under (dist desc, tie key asc); threads without points contribute (0-bits, k=0)
+    unsigned bd = 0u, bk = fps_tie_key(0);
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+      const int k = tid + p * FPS_THREADS;
+      if (k < n) {
+        const float d = sqdist(px[p] - x1, py[p] - y1, pz[p] - z1);
+        const float d2 = fminf(d, dist[p]);
+        dist[p] = d2;
+        const unsigned db = __float_as_uint(d2);  // d2 >= 0 (or +0): monotone as unsigned
+        // within a thread k ascends with p, and all its k share (k mod 512) only if 1024 % 512 == 0:
+        // k mod 512 is identical for every p, so strict '>' keeps the smallest k  (sampling.cu:141-144)
+        if (!any || db > bd) { bd = db; bk = fps_tie_key(k); any = true; }
+      }
+    }
+    // warp argmax: max distance bits, then min tie key among the maxima
+    unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    unsigned wk = __reduce_min_sync(0xffffffffu, (bd == wd && any) ? bk : 0xffffffffu);
+    const int buf = j & 1;
+    if (lane == 0) { s_d[buf][warp] = wd; s_k[buf][warp] = wk; }
+    __syncthreads();
+    const unsigned d_l = s_d[buf][lane], k_l = s_k[buf][lane];
+    const unsigned gd = __reduce_max_sync(0xffffffffu, d_l);
+    const unsigned gk = __reduce_min_sync(0xffffffffu, d_l == gd ? k_l : 0xffffffffu);
+    old = (gk == 0xffffffffu) ? 0 : fps_key_to_k(gk);
+    if (tid == 0) out[j] = old;
+  }
+}
+
+// generic fallback for very large N: distances in global scratch
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_kernel_big(int n, int m, const float *__restrict__ coords,
+                                                                 float *__restrict__ distances,
+                                                                 int *__restrict__ indices) {
+  __shared__ unsigned s_d[2][32], s_k[2][32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *co = coords + (size_t)b * 3 * n;
+  float *dist = distances + (size_t)b * n;
+  int *out = indices + (size_t)b * m;
+  for (int k = tid; k < n; k += FPS_THREADS) dist[k] = 1e38f;
+  if (tid == 0) out[0] = 0;
+  __syncthreads();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = __ldg(co + old), y1 = __ldg(co + old + n), z1 = __ldg(co + old + 2 * n);
+    unsigned bd = 0u, bk = fps_tie_key(0);
+    bool any = false;
+    for (int k = tid; k < n; k += FPS_THREADS) {
+      const float d = sqdist(__ldg(co + k) - x1, __ldg(co + k + n) - y1, __ldg(co + k + 2 * n) - z1);
+      const float d2 = fminf(d, dist[k]);
+      dist[k] = d2;
+      const unsigned db = __float_as_uint(d2);
+      if (!any || db > bd) { bd = db; bk = fps_tie_key(k); any = true; }
+    }
+    unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    unsigned wk = __reduce_min_sync(0xffffffffu, (bd == wd && any) ? bk : 0xffffffffu);
+    const int buf = j & 1;
+    if (lane == 0) { s_d[buf][warp] = wd; s_k[buf][warp] = wk; }
+    __syncthreads();
+    const unsigned d_l = s_d[buf][lane], k_l = s_k[buf][lane];
+    const unsigned gd = __reduce_max_sync(0xffffffffu, d_l);
+    const unsigned gk = __reduce_min_sync(0xffffffffu, d_l == gd ? k_l : 0xffffffffu);
+    old = (gk == 0xffffffffu) ? 0 : fps_key_to_k(gk);
+    if (tid == 0) out[j] = old;
+  }
+}
+
+// =====================================================================================
+// three-NN search + interpolation  (neighbor_interpolate.cu:20-170)
+// =====================================================================================
+constexpr int NN_TILE = 2048;
+__global__ void __launch_bounds__(128) three_nn_kernel(int n, int m, const float *__restrict__ points,
+                                                       const float *__restrict__ centers,
+                                                       float *__restrict__ weights, int *__restrict__ indices) {
+  __shared__ float sc[3][NN_TILE];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *p = points + (size_t)b * 3 * n;
+  const float *ce = centers + (size_t)b * 3 * m;
+  const bool valid = j < n;
+  const float ux = valid ? p[j] : 0.f, uy = valid ? p[j + n] : 0.f, uz = valid ? p[j + 2 * n] : 0.f;
+  double best0 = 1e40, best1 = 1e40, best2 = 1e40;
+  int i0 = 0, i1 = 0, i2 = 0;
+  for (int t0 = 0; t0 < m; t0 += NN_TILE) {
+    const int tn = min(NN_TILE, m - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+      sc[0][k] = ce[t0 + k];
+      sc[1][k] = ce[t0 + k + m];
+      sc[2][k] = ce[t0 + k + 2 * m];
+    }
+    __syncthreads();
+    for (int k = 0; k < tn; ++k) {
+      const float d = sqdist(ux - sc[0][k], uy - sc[1][k], uz - sc[2][k]);
+      const double dd = (double)d;
+      if (dd < best2) {
+        best2 = dd; i2 = t0 + k;
+        if (dd < best1) {
+          best2 = best1; i2 = i1; best1 = dd; i1 = t0 + k;
+          if (dd < best0) { best1 = best0; i1 = i0; best0 = dd; i0 = t0 + k; }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  best0 = fmax(fmin((double)1e10f, best0), (double)1e-10f);
+  best1 = fmax(fmin((double)1e10f, best1), (double)1e-10f);
+  best2 = fmax(fmin((double)1e10f, best2), (double)1e-10f);
+  const float d0d1 = (float)(best0 * best1), d0d2 = (float)(best0 * best2), d1d2 = (float)(best1 * best2);
+  const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+  float *w = weights + (size_t)b * 3 * n;
+  int *id = indices + (size_t)b * 3 * n;
+  w[j] = __fmul_rn(d1d2, inv);          id[j] = i0;
+  w[j + n] = __fmul_rn(d0d2, inv);      id[j + n] = i1;
+  w[j + 2 * n] = __fmul_rn(d0d1, inv);  id[j + 2 * n] = i2;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) three_nn_interp_kernel(int c, int m, int n, const float *__restrict__ cfeat,
+                                                              const int *__restrict__ indices,
+                                                              const float *__restrict__ weights,
+                                                              float *__restrict__ out) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int *id = indices + (size_t)b * 3 * n;
+  const float *w = weights + (size_t)b * 3 * n;
+  const int i1 = id[j], i2 = id[j + n], i3 = id[j + 2 * n];
+  const float w1 = w[j], w2 = w[j + n], w3 = w[j + 2 * n];
+  const float *f = cfeat + ((size_t)b * c + c0) * m;
+  float *o = out + ((size_t)b * c + c0) * n + j;
+  const int cmax = min(CT, c - c0);
+#pragma unroll 4
+  for (int l = 0; l < cmax; ++l) {
+    const float *fl = f + (size_t)l * m;
+    o[(size_t)l * n] = __fmaf_rn(__ldg(fl + i3), w3, __fmaf_rn(__ldg(fl + i2), w2, __fmul_rn(__ldg(fl + i1), w1)));
+  }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128) three_nn_interp_grad_kernel(int c, int n, int m,
+                                                                   const float *__restrict__ grad_y,
+                                                                   const int *__restrict__ indices,
+                                                                   const float *__restrict__ weights,
+                                                                   float *__restrict__ grad_x) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int *id = indices + (size_t)b * 3 * n;
+  const float *w = weights + (size_t)b * 3 * n;
+  const int i1 = id[j], i2 = id[j + n], i3 = id[j + 2 * n];
+  const float w1 = w[j], w2 = w[j + n], w3 = w[j + 2 * n];
+  const float *gy = grad_y + ((size_t)b * c + c0) * n + j;
+  float *gx = grad_x + ((size_t)b * c + c0) * m;
+  const int cmax = min(CT, c - c0);
+  for (int l = 0; l < cmax; ++l) {
+    const float g = gy[(size_t)l * n];
+    float *gl = gx + (size_t)l * m;
+    atomicAdd(gl + i1, __fmul_rn(g, w1));
+    atomicAdd(gl + i2, __fmul_rn(g, w2));
+    atomicAdd(gl + i3, __fmul_rn(g, w3));
+  }
+}
+
+}  // namespace pvb
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+using namespace pvb;
+
+template <int PPT>
+static int launch_fps(int b, int n, int m, const float *coords, int *indices, cudaStream_t s) {
+  size_t smem = sizeof(float) * 3 * (size_t)n;
+  int in_smem = smem <= 200 * 1024;
+  if (!in_smem) smem = 0;
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(fps_kernel<PPT>, b, FPS_THREADS, smem, s, n, m, in_smem, coords, indices);
+  return 0;
+}
+
+extern "C" {
+
+int pvcnn_abi_version(void) { return PVCNN_B200_ABI_VERSION; }
+const char *pvcnn_build_info(void) {
+  return "pvcnn_b200 sm_100a (nvcc " __DATE__ " " __TIME__ ")";
+}
+unsigned long long pvcnn_launch_count(void) { return pvb::g_launches; }
+
+int pvcnn_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords, float *norm_coords,
+                          int *vox_coords, void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && r > 0 && coords && norm_coords && vox_coords);
+  PVB_LAUNCH(voxelize_coords_kernel, b, 512, 0, stream, n, r, normalize, eps, coords, norm_coords, vox_coords);
+  return 0;
+}
+
+int pvcnn_avg_voxelize(int b, int c, int n, int r, int r2, int r3, const int *coords, const float *feat, int *ind,
+                       int *cnt, float *out, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && r > 0 && r2 == r * r && r3 == r2 * r);
+  PVB_CHECK_ARG(coords && feat && ind && cnt && out);
+  cudaStream_t s = (cudaStream_t)stream;
+  PVB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * r3, s));
+  PVB_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, s));
+  const long long total = (long long)b * n;
+  PVB_LAUNCH(vox_index_count_kernel, min(ceil_div(total, 256), kNumSMs * 8), 256, 0, s, n, r, r2, r3, total, coords,
+             ind, cnt);
+  constexpr int CT = 16;
+  PVB_LAUNCH(vox_scatter_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, s, c, n, r3, ind, cnt, feat,
+             out);
+  return 0;
+}
+
+int pvcnn_avg_voxelize_grad(int b, int c, int n, int s_, const int *ind, const int *cnt, const float *grad_y,
+                            float *grad_x, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && s_ > 0 && ind && cnt && grad_y && grad_x);
+  constexpr int CT = 16;
+  PVB_LAUNCH(vox_grad_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, stream, c, n, s_, ind, cnt,
+             grad_y, grad_x);
+  return 0;
+}
+
+int pvcnn_trilinear_devoxelize(int b, int c, int n, int r, int r2, int r3, int training, const float *coords,
+                               const float *feat, int *inds, float *wgts, float *outs, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && r > 0 && r2 == r * r && r3 == r2 * r && coords && feat && outs);
+  PVB_CHECK_ARG(!training || (inds && wgts));
+  constexpr int CT = 16;
+  PVB_LAUNCH(devox_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, stream, c, n, r, r2, r3, training,
+             coords, feat, inds, wgts, outs);
+  return 0;
+}
+
+int pvcnn_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
+                                    const float *grad_y, float *grad_x, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && r3 > 0 && inds && wgts && grad_y && grad_x);
+  cudaStream_t s = (cudaStream_t)stream;
+  PVB_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)b * c * r3, s));
+  constexpr int CT = 16;
+  PVB_LAUNCH(devox_grad_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, s, c, n, r3, inds, wgts,
+             grad_y, grad_x);
+  return 0;
+}
+
+int pvcnn_ball_query(int b, int n, int m, float r2, int u, const float *centers_coords, const float *points_coords,
+                     int *neighbors_indices, void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && m > 0 && u > 0 && centers_coords && points_coords && neighbors_indices);
+  PVB_LAUNCH(ball_query_kernel, dim3(ceil_div(m, BQ_WARPS * BQ_QPW), b), BQ_WARPS * 32, 0, stream, n, m, r2, u,
+             centers_coords, points_coords, neighbors_indices);
+  return 0;
+}
+
+int pvcnn_grouping(int b, int c, int n, int m, int u, const float *features, const int *indices, float *out,
+                   void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && m > 0 && u > 0 && features && indices && out);
+  constexpr int CT = 8;
+  PVB_LAUNCH(grouping_kernel<CT>, dim3(ceil_div((long long)m * u, 256), ceil_div(c, CT), b), 256, 0, stream, c, n,
+             m * u, features, indices, out);
+  return 0;
+}
+
+int pvcnn_grouping_grad(int b, int c, int n, int m, int u, const float *grad_y, const int *indices, float *grad_x,
+                        void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && m > 0 && u > 0 && grad_y && indices && grad_x);
+  cudaStream_t s = (cudaStream_t)stream;
+  PVB_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)b * c * n, s));
+  constexpr int CT = 8;
+  PVB_LAUNCH(grouping_grad_kernel<CT>, dim3(ceil_div((long long)m * u, 256), ceil_div(c, CT), b), 256, 0, s, c, n,
+             m * u, grad_y, indices, grad_x);
+  return 0;
+}
+
+int pvcnn_gather_features(int b, int c, int n, int m, const float *features, const int *indices, float *out,
+                          void *stream) {
+  return pvcnn_grouping(b, c, n, m, 1, features, indices, out, stream);
+}
+
+int pvcnn_gather_features_grad(int b, int c, int n, int m, const float *grad_y, const int *indices, float *grad_x,
+                               void *stream) {
+  return pvcnn_grouping_grad(b, c, n, m, 1, grad_y, indices, grad_x, stream);
+}
+
+int pvcnn_furthest_point_sampling(int b, int n, int m, const float *coords, float *distances, int *indices,
+                                  void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && coords && indices);
+  if (m <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ppt = ceil_div(n, FPS_THREADS);
+  if (ppt <= 1) return launch_fps<1>(b, n, m, coords, indices, s);
+  if (ppt <= 2) return launch_fps<2>(b, n, m, coords, indices, s);
+  if (ppt <= 4) return launch_fps<4>(b, n, m, coords, indices, s);
+  if (ppt <= 8) return launch_fps<8>(b, n, m, coords, indices, s);
+  if (ppt <= 16) return launch_fps<16>(b, n, m, coords, indices, s);
+  if (ppt <= 32) return launch_fps<32>(b, n, m, coords, indices, s);
+  float *scratch = distances;
+  if (!scratch) PVB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(float) * (size_t)b * n, s));
+  PVB_LAUNCH(fps_kernel_big, b, FPS_THREADS, 0, s, n, m, coords, scratch, indices);
+  if (!distances) PVB_CUDA(cudaFreeAsync(scratch, s));
+  return 0;
+}
+
+int pvcnn_three_nearest_neighbors_interpolate(int b, int c, int m, int n, const float *points_coords,
+                                              const float *centers_coords, const float *centers_features,
+                                              int *indices, float *weights, float *out, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && m > 0 && n > 0 && points_coords && centers_coords && centers_features);
+  PVB_CHECK_ARG(indices && weights && out);
+  PVB_LAUNCH(three_nn_kernel, dim3(ceil_div(n, 128), b), 128, 0, stream, n, m, points_coords, centers_coords, weights,
+             indices);
+  constexpr int CT = 16;
+  PVB_LAUNCH(three_nn_interp_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, stream, c, m, n,
+             centers_features, indices, weights, out);
+  return 0;
+}
+
+int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n, int m, const float *grad_y,
+                                                   const int *indices, const float *weights, float *grad_x,
+                                                   void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && m > 0 && n > 0 && grad_y && indices && weights && grad_x);
+  cudaStream_t s = (cudaStream_t)stream;
+  PVB_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)b * c * m, s));
+  constexpr int CT = 16;
+  PVB_LAUNCH(three_nn_interp_grad_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, s, c, n, m, grad_y,
+             indices, weights, grad_x);
+  return 0;
+}
+
+}  // extern "C"

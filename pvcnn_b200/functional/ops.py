@@ -1,0 +1,171 @@
+"""autograd.Function wrappers -- same contracts as the reference's
+modules/functional/{voxelization,devoxelization,ball_query,grouping,sampling,interpolatation}.py."""
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import backend as _backend
+from .. import _lib
+
+
+class _AvgVoxelize(Function):
+    """modules/functional/voxelization.py:8-37: features [B,C,N], integer coords [B,3,N] ->
+    [B,C,R,R,R]; saves (ind, cnt); gradient flows to features only."""
+
+    @staticmethod
+    def forward(ctx, features, coords, resolution):
+        features = features.contiguous()
+        coords = coords.int().contiguous()
+        b, c, _ = features.shape
+        out, ind, cnt = _backend.avg_voxelize_forward(features, coords, resolution)
+        ctx.save_for_backward(ind, cnt)
+        return out.view(b, c, resolution, resolution, resolution)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        ind, cnt = ctx.saved_tensors
+        b, c = grad_output.shape[:2]
+        g = _backend.avg_voxelize_backward(grad_output.contiguous().view(b, c, -1), ind, cnt)
+        return g, None, None
+
+
+avg_voxelize = _AvgVoxelize.apply
+
+
+class _TrilinearDevoxelize(Function):
+    """modules/functional/devoxelization.py:8-39: grid [B,C,R,R,R] sampled at float coords
+    [B,3,N] -> [B,C,N]; (inds, wgts) are kept only in training mode."""
+
+    @staticmethod
+    def forward(ctx, features, coords, resolution, is_training=True):
+        b, c = features.shape[:2]
+        features = features.contiguous().view(b, c, -1)
+        coords = coords.contiguous()
+        outs, inds, wgts = _backend.trilinear_devoxelize_forward(resolution, is_training, coords, features)
+        if is_training:
+            ctx.save_for_backward(inds, wgts)
+            ctx.r = resolution
+        return outs
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        inds, wgts = ctx.saved_tensors
+        g = _backend.trilinear_devoxelize_backward(grad_output.contiguous(), inds, wgts, ctx.r)
+        return g.view(grad_output.size(0), grad_output.size(1), ctx.r, ctx.r, ctx.r), None, None, None
+
+
+trilinear_devoxelize = _TrilinearDevoxelize.apply
+
+
+def ball_query(centers_coords, points_coords, radius, num_neighbors):
+    """modules/functional/ball_query.py:8-19: int32 [B,M,U], not differentiable."""
+    return _backend.ball_query(centers_coords.contiguous(), points_coords.contiguous(), radius, num_neighbors)
+
+
+class _Grouping(Function):
+    """modules/functional/grouping.py:8-28"""
+
+    @staticmethod
+    def forward(ctx, features, indices):
+        features = features.contiguous()
+        indices = indices.contiguous()
+        ctx.save_for_backward(indices)
+        ctx.num_points = features.size(-1)
+        return _backend.grouping_forward(features, indices)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (indices,) = ctx.saved_tensors
+        return _backend.grouping_backward(grad_output.contiguous(), indices, ctx.num_points), None
+
+
+grouping = _Grouping.apply
+
+
+class _Gather(Function):
+    """modules/functional/sampling.py:10-32"""
+
+    @staticmethod
+    def forward(ctx, features, indices):
+        features = features.contiguous()
+        indices = indices.int().contiguous()
+        ctx.save_for_backward(indices)
+        ctx.num_points = features.size(-1)
+        return _backend.gather_features_forward(features, indices)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (indices,) = ctx.saved_tensors
+        return _backend.gather_features_backward(grad_output.contiguous(), indices, ctx.num_points), None
+
+
+gather = _Gather.apply
+
+
+def furthest_point_sample(coords, num_samples):
+    """modules/functional/sampling.py:37-48: returns the sampled *coordinates* [B,3,M]
+    (differentiable through gather)."""
+    coords = coords.contiguous()
+    return gather(coords, _backend.furthest_point_sampling(coords, num_samples))
+
+
+def logits_mask(coords, logits, num_points_per_object):
+    """modules/functional/sampling.py:51-84: foreground mask from 2-way logits, masked mean, and a
+    fixed-size resampling of the foreground points.  The resampling keeps the reference's
+    numpy RNG call sequence (choice / choice+shuffle per sample) so that results are
+    reproducible against it under the same np.random seed."""
+    bsz, _, npts = coords.shape
+    k = int(num_points_per_object)
+    mask = logits[:, 0, :] < logits[:, 1, :]
+    count = mask.sum(dim=-1, keepdim=True)
+    masked = coords * mask.view(bsz, 1, npts)
+    mean = masked.sum(dim=-1) / torch.max(count, torch.ones_like(count)).float()
+    picks = torch.zeros((bsz, k), device=coords.device, dtype=torch.int32)
+    for i in range(bsz):
+        cand = mask[i].nonzero().view(-1)
+        nc = cand.numel()
+        if nc >= k:
+            sel = np.random.choice(nc, k, replace=False)
+        elif nc > 0:
+            sel = np.concatenate([np.arange(nc).repeat(k // nc), np.random.choice(nc, k % nc, replace=False)])
+            np.random.shuffle(sel)
+        else:
+            continue
+        picks[i] = cand[sel]
+    return gather(masked - mean.view(bsz, -1, 1), picks), mean, mask
+
+
+class _NeighborInterpolate(Function):
+    """modules/functional/interpolatation.py:8-35: gradient only w.r.t. centers_features."""
+
+    @staticmethod
+    def forward(ctx, points_coords, centers_coords, centers_features):
+        centers_coords = centers_coords.contiguous()
+        points_coords = points_coords.contiguous()
+        centers_features = centers_features.contiguous()
+        out, indices, weights = _backend.three_nearest_neighbors_interpolate_forward(
+            points_coords, centers_coords, centers_features)
+        ctx.save_for_backward(indices, weights)
+        ctx.num_centers = centers_coords.size(-1)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        indices, weights = ctx.saved_tensors
+        g = _backend.three_nearest_neighbors_interpolate_backward(grad_output.contiguous(), indices, weights,
+                                                                  ctx.num_centers)
+        return None, None, g
+
+
+nearest_neighbor_interpolate = _NeighborInterpolate.apply
+
+
+def voxelize_coords(coords, resolution, normalize=True, eps=0.0):
+    """Fused replacement for the tensor ops of modules/voxelization.py:17-24: returns
+    (norm_coords float [B,3,N] clamped to [0,r-1], vox_coords int32 [B,3,N])."""
+    coords = coords.detach().contiguous().float()
+    b, _, n = coords.shape
+    nc = torch.empty_like(coords)
+    vc = torch.empty(coords.shape, dtype=torch.int32, device=coords.device)
+    _lib.call("pvcnn_voxelize_coords", b, n, int(resolution), bool(normalize), float(eps), coords, nc, vc)
+    return nc, vc

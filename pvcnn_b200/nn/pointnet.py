@@ -1,0 +1,84 @@
+import torch
+import torch.nn as nn
+
+from .. import functional as F
+from .ball_query import BallQuery
+from .shared_mlp import SharedMLP
+
+
+def _as_nested(widths, count):
+    """Normalise `out_channels` to one list of widths per branch (modules/pointnet.py:14-17, :56-60)."""
+    if not isinstance(widths, (list, tuple)):
+        return [[widths]] * count
+    if not isinstance(widths[0], (list, tuple)):
+        return [widths] * count
+    return widths
+
+
+class PointNetAModule(nn.Module):
+    """Global ("all points") abstraction (reference: modules/pointnet.py:11-46): per-branch
+    SharedMLP followed by a max over points; returns a single zero centre."""
+
+    def __init__(self, in_channels, out_channels, include_coordinates=True):
+        super().__init__()
+        branches = _as_nested(out_channels, 1)
+        cin = in_channels + (3 if include_coordinates else 0)
+        self.mlps = nn.ModuleList([SharedMLP(in_channels=cin, out_channels=w, dim=1) for w in branches])
+        self.include_coordinates = include_coordinates
+        self.out_channels = sum(w[-1] for w in branches)
+
+    def forward(self, inputs):
+        features, coords = inputs
+        if self.include_coordinates:
+            features = torch.cat([features, coords], dim=1)
+        origin = torch.zeros((coords.size(0), 3, 1), device=coords.device)
+        pooled = [mlp(features).max(dim=-1, keepdim=True).values for mlp in self.mlps]
+        return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), origin
+
+    def extra_repr(self):
+        return f"out_channels={self.out_channels}, include_coordinates={self.include_coordinates}"
+
+
+class PointNetSAModule(nn.Module):
+    """Set abstraction (reference: modules/pointnet.py:49-92): FPS centres, one
+    (BallQuery -> SharedMLP(dim=2) -> max over neighbours) branch per radius."""
+
+    def __init__(self, num_centers, radius, num_neighbors, in_channels, out_channels, include_coordinates=True):
+        super().__init__()
+        radii = list(radius) if isinstance(radius, (list, tuple)) else [radius]
+        ks = list(num_neighbors) if isinstance(num_neighbors, (list, tuple)) else [num_neighbors] * len(radii)
+        assert len(radii) == len(ks)
+        branches = _as_nested(out_channels, len(radii))
+        assert len(radii) == len(branches)
+        cin = in_channels + (3 if include_coordinates else 0)
+        self.groupers = nn.ModuleList(
+            [BallQuery(radius=r, num_neighbors=k, include_coordinates=include_coordinates) for r, k in zip(radii, ks)])
+        self.mlps = nn.ModuleList([SharedMLP(in_channels=cin, out_channels=w, dim=2) for w in branches])
+        self.num_centers = num_centers
+        self.out_channels = sum(w[-1] for w in branches)
+
+    def forward(self, inputs):
+        features, coords = inputs
+        centers = F.furthest_point_sample(coords, self.num_centers)
+        pooled = [mlp(g(coords, centers, features)).max(dim=-1).values for g, mlp in zip(self.groupers, self.mlps)]
+        return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), centers
+
+    def extra_repr(self):
+        return f"num_centers={self.num_centers}, out_channels={self.out_channels}"
+
+
+class PointNetFPModule(nn.Module):
+    """Feature propagation (reference: modules/pointnet.py:95-111): 3-NN inverse-distance
+    interpolation of the centres' features onto the points, optional skip concat, SharedMLP."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.mlp = SharedMLP(in_channels=in_channels, out_channels=out_channels, dim=1)
+
+    def forward(self, inputs):
+        points_coords, centers_coords, centers_features = inputs[:3]
+        skip = inputs[3] if len(inputs) > 3 else None
+        x = F.nearest_neighbor_interpolate(points_coords, centers_coords, centers_features)
+        if skip is not None:
+            x = torch.cat([x, skip], dim=1)
+        return self.mlp(x), points_coords

@@ -1,0 +1,53 @@
+import importlib.util
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+_REF = None
+
+
+def load_ref_backend():
+    """The UNMODIFIED reference extension built by oracle/build_ref.py (checker only)."""
+    global _REF
+    if _REF is None:
+        import torch  # noqa: F401  (libtorch symbols must be loaded first)
+        path = os.path.join(ROOT, "oracle", "_ref", "_pvcnn_backend.so")
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref/_pvcnn_backend.so not built (run python oracle/build_ref.py)")
+        spec = importlib.util.spec_from_file_location("_pvcnn_backend", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _REF = mod
+    return _REF
+
+
+@pytest.fixture(scope="session")
+def ref_backend():
+    return load_ref_backend()

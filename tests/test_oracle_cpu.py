@@ -1,0 +1,173 @@
+"""CPU tests: the oracle against brute-force numpy restatements and its own invariants."""
+import numpy as np
+import pytest
+
+import oracle
+from util import rng, s3dis_like_coords, degenerate_coords
+
+
+def test_voxelize_coords_matches_torch_ops():
+    """modules/voxelization.py:16-25 expressed with the reference's own torch calls (CPU)."""
+    import torch
+    g = rng(1)
+    for normalize, eps, r in [(True, 0.0, 8), (True, 1e-15, 32), (False, 0.0, 16)]:
+        c = s3dis_like_coords(g, 3, 777) - 0.3
+        nc, vc = oracle.voxelize_coords(c, r, normalize, eps)
+        t = torch.from_numpy(c)
+        n0 = t - t.mean(2, keepdim=True)
+        if normalize:
+            n0 = n0 / (n0.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps) + 0.5
+        else:
+            n0 = (n0 + 1) / 2.0
+        n0 = torch.clamp(n0 * r, 0, r - 1)
+        v0 = torch.round(n0).to(torch.int32)
+        assert np.abs(nc - n0.numpy()).max() < 1e-4
+        # identical voxel except where the reduction-order ulp flips a .5 boundary
+        assert (vc != v0.numpy()).mean() < 1e-3
+        assert vc.min() >= 0 and vc.max() <= r - 1
+
+
+def test_avg_voxelize_bruteforce():
+    g = rng(2)
+    b, c, n, r = 2, 5, 300, 4
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    vc = g.integers(0, r, size=(b, 3, n)).astype(np.int32)
+    out, ind, cnt = oracle.avg_voxelize(f, vc, r)
+    ind0 = vc[:, 0] * r * r + vc[:, 1] * r + vc[:, 2]
+    assert (ind == ind0).all()
+    for bi in range(b):
+        cnt0 = np.bincount(ind0[bi], minlength=r ** 3)
+        assert (cnt[bi] == cnt0).all()
+        ref = np.zeros((c, r ** 3))
+        for i in range(n):
+            ref[:, ind0[bi, i]] += f[bi, :, i].astype(np.float64) / cnt0[ind0[bi, i]]
+        assert np.abs(out[bi] - ref).max() < 1e-5
+    gy = g.standard_normal((b, c, r ** 3), dtype=np.float32)
+    gx = oracle.avg_voxelize_grad(gy, ind, cnt)
+    # adjoint identity <voxelize(f), gy> == <f, voxelize_grad(gy)>
+    assert abs((out.astype(np.float64) * gy).sum() - (f.astype(np.float64) * gx).sum()) < 1e-3
+
+
+def test_trilinear_devox_properties():
+    g = rng(3)
+    b, c, n, r = 2, 4, 500, 6
+    grid = g.standard_normal((b, c, r, r, r), dtype=np.float32)
+    co = (g.random((b, 3, n), dtype=np.float32) * (r - 1)).astype(np.float32)
+    co[:, :, :10] = np.float32(r - 1)      # clamp value: must not read out of bounds
+    co[:, :, 10:20] = np.floor(co[:, :, 10:20])  # exact integers
+    outs, inds, wgts = oracle.trilinear_devoxelize(grid, co, r, True)
+    assert inds.min() >= 0 and inds.max() < r ** 3
+    assert np.abs(wgts.sum(1) - 1).max() < 1e-5
+    # a linear field is reproduced exactly by trilinear interpolation
+    zz, yy, xx = np.meshgrid(np.arange(r), np.arange(r), np.arange(r), indexing="ij")
+    # grid index = x*r^2 + y*r + z  -> array axes are (x, y, z)
+    lin = (2.0 * zz + 3.0 * yy - 1.5 * xx + 0.25).astype(np.float32)  # axes (x,y,z) = (zz,yy,xx) names aside
+    lin_grid = np.broadcast_to(lin, (b, 1, r, r, r)).copy()
+    o2, _, _ = oracle.trilinear_devoxelize(lin_grid, co, r, False)
+    expect = 2.0 * co[:, 0] + 3.0 * co[:, 1] - 1.5 * co[:, 2] + 0.25
+    assert np.abs(o2[:, 0] - expect).max() < 1e-4
+    # adjoint
+    gy = g.standard_normal((b, c, n), dtype=np.float32)
+    gx = oracle.trilinear_devoxelize_grad(gy, inds, wgts, r)
+    lhs = (outs.astype(np.float64) * gy).sum()
+    rhs = (grid.reshape(b, c, -1).astype(np.float64) * gx).sum()
+    assert abs(lhs - rhs) < 1e-2
+    # eval mode leaves inds/wgts untouched
+    _, i2, w2 = oracle.trilinear_devoxelize(grid, co, r, False)
+    assert (i2 == 0).all() and (w2 == 0).all()
+
+
+def test_ball_query_bruteforce():
+    g = rng(4)
+    b, n, m, u = 2, 400, 37, 8
+    p = g.random((b, 3, n), dtype=np.float32)
+    ce = p[:, :, :m].copy()
+    ce[:, :, -1] = 50.0  # a centre with no neighbour -> row of zeros
+    radius = 0.2
+    out = oracle.ball_query(ce, p, radius, u)
+    r2 = np.float32(radius) * np.float32(radius)
+    for bi in range(b):
+        for j in range(m):
+            d = ce[bi, :, j:j + 1] - p[bi]
+            d2 = (d[2] * d[2]).astype(np.float64) + (d[0] * d[0] + d[1] * d[1])
+            hits = np.nonzero(d2 < r2 - 1e-6)[0][:u]
+            row = out[bi, j]
+            if len(hits) == 0:
+                assert (row == 0).all()
+            else:
+                k = min(len(hits), u)
+                # boundary-insensitive check: prefix equals hits, padding equals first hit
+                assert row[0] == hits[0] or abs(d2[row[0]] - r2) < 1e-5
+                assert (row[k:] == row[0]).all() or len(hits) >= u
+    assert (out[:, -1] == 0).all()
+
+
+def test_grouping_gather_adjoint():
+    g = rng(5)
+    b, c, n, m, u = 2, 6, 50, 11, 4
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    idx = g.integers(0, n, size=(b, m, u)).astype(np.int32)
+    out = oracle.grouping(f, idx)
+    for bi in range(b):
+        assert (out[bi] == f[bi][:, idx[bi]]).all()
+    gy = g.standard_normal((b, c, m, u), dtype=np.float32)
+    gx = oracle.grouping_grad(gy, idx, n)
+    assert abs((out.astype(np.float64) * gy).sum() - (f.astype(np.float64) * gx).sum()) < 1e-3
+    idx1 = idx[:, :, 0].copy()
+    o1 = oracle.gather(f, idx1)
+    assert (o1 == out[:, :, :, 0]).all()
+    g1 = oracle.gather_grad(gy[:, :, :, 0].copy(), idx1, n)
+    assert g1.shape == (b, c, n)
+
+
+def test_fps_semantics():
+    g = rng(6)
+    b, n, m = 2, 700, 40
+    co = g.random((b, 3, n), dtype=np.float32)
+    idx = oracle.furthest_point_sampling(co, m)
+    assert (idx[:, 0] == 0).all()
+    for bi in range(b):
+        assert len(set(idx[bi].tolist())) == m
+        # greedy property: each pick maximises the distance to the set so far
+        dist = np.full(n, 1e38, np.float32)
+        for j in range(1, m):
+            d = ((co[bi] - co[bi][:, idx[bi, j - 1]:idx[bi, j - 1] + 1]) ** 2).sum(0)
+            dist = np.minimum(dist, d)
+            assert dist[idx[bi, j]] >= dist.max() * (1 - 1e-5)
+    # tie-break: all-identical points -> always index 0
+    same = np.ones((1, 3, 600), np.float32)
+    assert (oracle.furthest_point_sampling(same, 5) == 0).all()
+    # two equidistant candidates: smallest (k mod 512), then smallest k
+    pts = np.zeros((1, 3, 1030), np.float32)
+    pts[0, 0, 5] = 1.0
+    pts[0, 0, 517] = 1.0      # 517 % 512 == 5 -> same slot, larger k loses
+    pts[0, 0, 3 + 512] = 1.0  # slot 3 beats slot 5
+    assert oracle.furthest_point_sampling(pts, 2)[0, 1] == 515
+
+
+def test_three_nn_bruteforce():
+    g = rng(7)
+    b, n, m, c = 2, 90, 33, 5
+    p = g.random((b, 3, n), dtype=np.float32)
+    ce = g.random((b, 3, m), dtype=np.float32)
+    idx, w = oracle.three_nn(p, ce)
+    for bi in range(b):
+        d = ((p[bi][:, :, None] - ce[bi][:, None, :]) ** 2).sum(0)
+        order = np.argsort(d, axis=1, kind="stable")[:, :3]
+        assert (np.sort(idx[bi].T, axis=1) == np.sort(order, axis=1)).mean() > 0.99
+    assert np.abs(w.sum(1) - 1).max() < 1e-5
+    f = g.standard_normal((b, c, m), dtype=np.float32)
+    out = oracle.three_nn_interpolate(f, idx, w)
+    gy = g.standard_normal((b, c, n), dtype=np.float32)
+    gx = oracle.three_nn_interpolate_grad(gy, idx, w, m)
+    assert abs((out.astype(np.float64) * gy).sum() - (f.astype(np.float64) * gx).sum()) < 1e-3
+
+
+def test_degenerate_voxelization():
+    g = rng(8)
+    c = degenerate_coords(g, 2, 256)
+    nc, vc = oracle.voxelize_coords(c, 8)
+    f = g.standard_normal((2, 3, 256), dtype=np.float32)
+    out, ind, cnt = oracle.avg_voxelize(f, vc, 8)
+    assert (cnt > 0).sum() <= 2 * 27
+    assert cnt.sum() == 2 * 256
