@@ -29,71 +29,77 @@ extern "C" {
 
 #define PVCNN_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define PVCNN_API __attribute__((visibility("default")))
+#else
+#define PVCNN_API
+#endif
+
 #define PVCNN_E_BADARG 100001   /* invalid size / null pointer                              */
 #define PVCNN_E_UNSUPPORTED 100002 /* shape outside what the sm_100a kernels were built for */
 
 /* ABI version + human-readable build string ("sm_100a, nvcc 12.9, ...") */
-int pvcnn_abi_version(void);
-const char *pvcnn_build_info(void);
+PVCNN_API int pvcnn_abi_version(void);
+PVCNN_API const char *pvcnn_build_info(void);
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
-unsigned long long pvcnn_launch_count(void);
+PVCNN_API unsigned long long pvcnn_launch_count(void);
 
 /* ---- coordinate normalisation: modules/voxelization.py:16-25 (the reference runs ~9 ATen
  *      kernels here; we fuse them).  coords [B,3,N] -> norm_coords [B,3,N] fp32 (clamped to
  *      [0,r-1], NOT rounded; this is what devoxelize consumes) and vox_coords [B,3,N] int32
  *      (round-half-even).  The mean is the fp64 sum rounded once (oracle/pvcnn_oracle.c). */
-int pvcnn_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords,
+PVCNN_API int pvcnn_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords,
                           float *norm_coords, int *vox_coords, void *stream);
 
 /* ---- replaces avg_voxelize(...)       voxelization/vox.cuh:5-6  (kernels vox.cu:18-72) */
-int pvcnn_avg_voxelize(int b, int c, int n, int r, int r2, int r3, const int *coords,
+PVCNN_API int pvcnn_avg_voxelize(int b, int c, int n, int r, int r2, int r3, const int *coords,
                        const float *feat, int *ind, int *cnt, float *out, void *stream);
 /* ---- replaces avg_voxelize_grad(...)  voxelization/vox.cuh:7-8  (kernel vox.cu:86-110) */
-int pvcnn_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
+PVCNN_API int pvcnn_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
                             const float *grad_y, float *grad_x, void *stream);
 
 /* ---- replaces trilinear_devoxelize(...)       interpolate/trilinear_devox.cuh:5-8
  *      inds/wgts [B,8,N] are written only when training != 0 (trilinear_devox.cpp:45-53);
  *      they may be NULL otherwise. */
-int pvcnn_trilinear_devoxelize(int b, int c, int n, int r, int r2, int r3, int training,
+PVCNN_API int pvcnn_trilinear_devoxelize(int b, int c, int n, int r, int r2, int r3, int training,
                                const float *coords, const float *feat, int *inds, float *wgts,
                                float *outs, void *stream);
 /* ---- replaces trilinear_devoxelize_grad(...)  interpolate/trilinear_devox.cuh:9-11 */
-int pvcnn_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds,
+PVCNN_API int pvcnn_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds,
                                     const float *wgts, const float *grad_y, float *grad_x,
                                     void *stream);
 
 /* ---- replaces ball_query(...)  ball_query/ball_query.cuh:4-6; r2 = radius*radius in float
  *      (ball_query.cpp:24).  neighbors_indices [B,M,U]. */
-int pvcnn_ball_query(int b, int n, int m, float r2, int u, const float *centers_coords,
+PVCNN_API int pvcnn_ball_query(int b, int n, int m, float r2, int u, const float *centers_coords,
                      const float *points_coords, int *neighbors_indices, void *stream);
 
 /* ---- replaces grouping(...) / grouping_grad(...)  grouping/grouping.cuh:4-7 */
-int pvcnn_grouping(int b, int c, int n, int m, int u, const float *features, const int *indices,
+PVCNN_API int pvcnn_grouping(int b, int c, int n, int m, int u, const float *features, const int *indices,
                    float *out, void *stream);
-int pvcnn_grouping_grad(int b, int c, int n, int m, int u, const float *grad_y,
+PVCNN_API int pvcnn_grouping_grad(int b, int c, int n, int m, int u, const float *grad_y,
                         const int *indices, float *grad_x, void *stream);
 
 /* ---- replaces gather_features(...) / gather_features_grad(...)  sampling/sampling.cuh:4-7 */
-int pvcnn_gather_features(int b, int c, int n, int m, const float *features, const int *indices,
+PVCNN_API int pvcnn_gather_features(int b, int c, int n, int m, const float *features, const int *indices,
                           float *out, void *stream);
-int pvcnn_gather_features_grad(int b, int c, int n, int m, const float *grad_y,
+PVCNN_API int pvcnn_gather_features_grad(int b, int c, int n, int m, const float *grad_y,
                                const int *indices, float *grad_x, void *stream);
 
 /* ---- replaces furthest_point_sampling(...)  sampling/sampling.cuh:8-9.  `distances` is the
  *      reference's [B,N] scratch (sampling.cpp:53-54); it may be NULL -- we keep the running
  *      distances in registers and only use it when N exceeds the register-resident limit. */
-int pvcnn_furthest_point_sampling(int b, int n, int m, const float *coords, float *distances,
+PVCNN_API int pvcnn_furthest_point_sampling(int b, int n, int m, const float *coords, float *distances,
                                   int *indices, void *stream);
 
 /* ---- replaces three_nearest_neighbors_interpolate(...) / _grad(...)
  *      interpolate/neighbor_interpolate.cuh:4-14 */
-int pvcnn_three_nearest_neighbors_interpolate(int b, int c, int m, int n,
+PVCNN_API int pvcnn_three_nearest_neighbors_interpolate(int b, int c, int m, int n,
                                               const float *points_coords,
                                               const float *centers_coords,
                                               const float *centers_features, int *indices,
                                               float *weights, float *out, void *stream);
-int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n, int m,
+PVCNN_API int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n, int m,
                                                    const float *grad_y, const int *indices,
                                                    const float *weights, float *grad_x,
                                                    void *stream);

@@ -1,0 +1,389 @@
+// conv_igemm.cu -- im2col-free implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the reference's cuDNN calls: nn.Conv3d(k=3, pad=1) (modules/pvconv.py:21,24) and the
+// 1x1 nn.Conv1d of SharedMLP (modules/shared_mlp.py:10), forward and data-gradient.
+//
+//   out[v, n] = bias[n] + sum_{tap, c} A[v + off(tap), c] * W[tap][n][c]
+//
+//   * activations are channels-last ([B, X, Y, Z, C], C contiguous); one M-tile is a box of up to 128
+//     voxels fetched by ONE 5-D TMA load per (tap, 32-channel chunk).  The tap offset is added to the box
+//     coordinates and TMA's out-of-bounds zero fill implements the conv's zero padding -- no im2col
+//     buffer, no halo copies, no boundary branches.
+//   * operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes
+//     directly (kind::tf32, M=128, N=block_n, K=8 per instruction), accumulators live in TMEM,
+//     double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias -> global).
+//   * fp32 parity: tf32 has a 10-bit mantissa, the north-star tolerance is 1e-5.  npass=3 runs the
+//     error-compensated split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (hi/lo exactly
+//     representable in tf32, produced by split_tf32_kernel), accumulating all three in the same
+//     fp32 TMEM accumulator.  npass=1 is plain TF32 (what cuDNN does by default in the reference).
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pvb {
+using namespace umma;
+
+constexpr int IG_BLOCK_M = 128;
+constexpr int IG_KC = 32;  // channels per k-block = 128 bytes = one swizzle row
+constexpr int IG_THREADS = 256;
+constexpr int IG_MAX_STAGES = 8;
+constexpr uint32_t IG_A_TILE_BYTES = IG_BLOCK_M * IG_KC * 4;  // 16 KB
+
+struct IgemmParams {
+  int nb, sx, sy, sz;
+  int bx, by, bz;  // rows per tile = bx*by*bz <= 128
+  int tx, ty, tz;
+  int num_m_tiles, n_tiles;
+  int cin_chunks, ntaps;
+  int cout, block_n;
+  int npass, stages;
+  int ldo;
+  uint32_t stage_bytes, a_bytes, b_bytes, tx_bytes, tmem_cols;
+  const float *bias;
+  float *out;
+  int *err;
+};
+
+__global__ void __launch_bounds__(IG_THREADS, 1)
+    igemm_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                      const IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[IG_MAX_STAGES], empty_bar[IG_MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.n_tiles;
+  const int num_kb = p.ntaps * p.cin_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a_hi);
+    prefetch_tensormap(&map_w_hi);
+    if (p.npass > 1) {
+      prefetch_tensormap(&map_a_lo);
+      prefetch_tensormap(&map_w_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int z0 = (mt % p.tz) * p.bz; mt /= p.tz;
+        const int y0 = (mt % p.ty) * p.by; mt /= p.ty;
+        const int x0 = (mt % p.tx) * p.bx; mt /= p.tx;
+        const int b = mt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
+          int dx = 0, dy = 0, dz = 0;
+          if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
+          uint8_t *st = smem + (size_t)stage * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+          tma_load_5d(st, &map_a_hi, &full_bar[stage], cc * IG_KC, z0 + dz, y0 + dy, x0 + dx, b);
+          tma_load_3d(st + p.a_bytes, &map_w_hi, &full_bar[stage], cc * IG_KC, n_tile * p.block_n, tap);
+          if (p.npass > 1) {
+            tma_load_5d(st + IG_A_TILE_BYTES, &map_a_lo, &full_bar[stage], cc * IG_KC, z0 + dz, y0 + dy, x0 + dx, b);
+            tma_load_3d(st + p.a_bytes + p.b_bytes / 2, &map_w_lo, &full_bar[stage], cc * IG_KC, n_tile * p.block_n,
+                        tap);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(IG_BLOCK_M, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, p.err, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err, 3);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t a_lo = a_hi + IG_A_TILE_BYTES;
+          const uint32_t b_hi = a_hi + p.a_bytes;
+          const uint32_t b_lo = b_hi + p.b_bytes / 2;
+#pragma unroll
+          for (int k = 0; k < IG_KC / 8; ++k) {
+            const uint32_t koff = k * 8 * 4;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
+            const uint64_t da_hi = make_smem_desc(a_hi + koff, 0, 1024, kLayoutSW128);
+            const uint64_t db_hi = make_smem_desc(b_hi + koff, 0, 1024, kLayoutSW128);
+            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            if (p.npass > 1) {
+              const uint64_t da_lo = make_smem_desc(a_lo + koff, 0, 1024, kLayoutSW128);
+              const uint64_t db_lo = make_smem_desc(b_lo + koff, 0, 1024, kLayoutSW128);
+              mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
+              mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, 1);
+            }
+          }
+          mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int we = warp - 4;  // TMEM lane quarter this warp may access
+    const int m = we * 32 + lane;
+    const int lz = m % p.bz, ly = (m / p.bz) % p.by, lx = m / (p.bz * p.by);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int z = (mt % p.tz) * p.bz + lz; mt /= p.tz;
+      const int y = (mt % p.ty) * p.by + ly; mt /= p.ty;
+      const int x = (mt % p.tx) * p.bx + lx; mt /= p.tx;
+      const int b = mt;
+      const bool valid = (lx < p.bx) && x < p.sx && y < p.sy && z < p.sz;
+      float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + z) * p.ldo + (size_t)n_tile * p.block_n;
+      mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const int ncols = min(p.block_n, p.cout - n_tile * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (valid && c0 < ncols) {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < ncols) v[i] += __ldg(p.bias + n_tile * p.block_n + c0 + i);
+          }
+          if (c0 + 16 <= ncols) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4 *>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < 16 && c0 + i < ncols; ++i) orow[c0 + i] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operand preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);  // exact in tf32 (10-bit mantissa)
+  lo = __uint_as_float(__float_as_uint(__fsub_rn(x, hi)) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(long long n4, const float4 *__restrict__ x,
+                                                         float4 *__restrict__ hi, float4 *__restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// w [cout][cin][ntaps] (torch Conv3d / Conv1d weight, taps flattened kd*9+kh*3+kw) ->
+//   mode 0 (forward): wr[tap][cout][ld]          = w[co][ci][tap]
+//   mode 1 (dgrad)  : wr[tap][cin ][ld]  (K=cout) = w[co][ci][ntaps-1-tap]
+__global__ void __launch_bounds__(256) weight_prep_kernel(int cout, int cin, int ntaps, int mode, int ld,
+                                                          const float *__restrict__ w, float *__restrict__ hi,
+                                                          float *__restrict__ lo) {
+  const int rows = mode == 0 ? cout : cin;   // GEMM N
+  const int kdim = mode == 0 ? cin : cout;   // GEMM K
+  const long long total = (long long)ntaps * rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ld);
+    const int r = (int)((i / ld) % rows);
+    const int tap = (int)(i / ((long long)ld * rows));
+    float v = 0.0f;
+    if (k < kdim) {
+      if (mode == 0) v = w[((size_t)r * cin + k) * ntaps + tap];
+      else v = w[((size_t)k * cin + r) * ntaps + (ntaps - 1 - tap)];
+    }
+    float h, l;
+    split_tf32(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstride,
+                      const cuuint32_t *box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return PVCNN_E_UNSUPPORTED;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (200000 + (int)r);
+}
+
+static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps
+
+}  // namespace pvb
+
+using namespace pvb;
+
+extern "C" {
+
+int pvcnn_split_tf32(long long n, const float *x, float *hi, float *lo, void *stream) {
+  PVB_CHECK_ARG(n > 0 && (n % 4) == 0 && x && hi && lo);
+  const long long n4 = n / 4;
+  PVB_LAUNCH(split_tf32_kernel, min((long long)ceil_div(n4, 256), (long long)kNumSMs * 16), 256, 0, stream, n4,
+             reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo));
+  return 0;
+}
+
+int pvcnn_conv_weight_prep(int cout, int cin, int ntaps, int mode, int ld, const float *w, float *w_hi, float *w_lo,
+                           void *stream) {
+  PVB_CHECK_ARG(cout > 0 && cin > 0 && (ntaps == 1 || ntaps == 27) && (mode == 0 || mode == 1) && w && w_hi && w_lo);
+  PVB_CHECK_ARG(ld % 4 == 0 && ld >= (mode == 0 ? cin : cout));
+  const long long total = (long long)ntaps * (mode == 0 ? cout : cin) * ld;
+  PVB_LAUNCH(weight_prep_kernel, min((long long)ceil_div(total, 256), (long long)kNumSMs * 8), 256, 0, stream, cout,
+             cin, ntaps, mode, ld, w, w_hi, w_lo);
+  return 0;
+}
+
+int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi,
+                     const float *a_lo, int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias,
+                     float *out, int ldo, int npass, void *stream) {
+  PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && k > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
+  PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || (a_lo && w_lo)));
+  PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
+  if (!g_err_flag) {
+    PVB_CUDA(cudaMalloc((void **)&g_err_flag, sizeof(int)));
+    PVB_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+  }
+  IgemmParams p{};
+  p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
+  // tile box: up to 128 voxels, z fastest
+  p.bz = min(sz, IG_BLOCK_M);
+  p.by = min(sy, max(1, IG_BLOCK_M / p.bz));
+  p.bx = min(sx, max(1, IG_BLOCK_M / (p.bz * p.by)));
+  if (sz > IG_BLOCK_M) { p.bz = IG_BLOCK_M; p.by = 1; p.bx = 1; }
+  p.tz = ceil_div(sz, p.bz); p.ty = ceil_div(sy, p.by); p.tx = ceil_div(sx, p.bx);
+  p.num_m_tiles = nb * p.tx * p.ty * p.tz;
+  p.cin_chunks = ceil_div(k, IG_KC);
+  p.ntaps = ntaps;
+  p.cout = cout;
+  int bn = ((cout + 15) / 16) * 16;
+  if (bn > 128) bn = 128;
+  p.block_n = bn;
+  p.n_tiles = ceil_div(cout, bn);
+  p.npass = npass;
+  p.ldo = ldo;
+  p.a_bytes = IG_A_TILE_BYTES * (npass > 1 ? 2 : 1);
+  p.b_bytes = (uint32_t)bn * IG_KC * 4 * (npass > 1 ? 2 : 1);
+  p.stage_bytes = p.a_bytes + p.b_bytes;  // multiple of 1024 since bn % 16 == 0 -> bn*128 % 2048 == 0? ensured below
+  p.stage_bytes = (p.stage_bytes + 1023) & ~1023u;
+  const uint32_t rows = (uint32_t)(p.bx * p.by * p.bz);
+  p.tx_bytes = (rows * IG_KC * 4 + (uint32_t)bn * IG_KC * 4) * (npass > 1 ? 2 : 1);
+  const int smem_budget = 227 * 1024 - 2048;
+  p.stages = min(IG_MAX_STAGES, smem_budget / (int)p.stage_bytes);
+  PVB_CHECK_ARG(p.stages >= 2);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.bias = bias; p.out = out; p.err = g_err_flag;
+  // B tiles must start 1024-aligned inside the stage: a_bytes is a multiple of 16 KB, b_hi = bn*128 bytes;
+  // b_lo starts at b_bytes/2 = bn*128 which is a multiple of 1024 only when bn % 8 == 0 (true: bn % 16 == 0).
+
+  CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+  {
+    cuuint64_t gdim[5] = {(cuuint64_t)k, (cuuint64_t)sz, (cuuint64_t)sy, (cuuint64_t)sx, (cuuint64_t)nb};
+    cuuint64_t gstr[4] = {(cuuint64_t)lda * 4, (cuuint64_t)sz * lda * 4, (cuuint64_t)sy * sz * lda * 4,
+                          (cuuint64_t)sx * sy * sz * lda * 4};
+    cuuint32_t box[5] = {(cuuint32_t)IG_KC, (cuuint32_t)p.bz, (cuuint32_t)p.by, (cuuint32_t)p.bx, 1};
+    int rc = encode_map(&ma_hi, a_hi, 5, gdim, gstr, box);
+    if (rc) return rc;
+    rc = encode_map(&ma_lo, npass > 1 ? a_lo : a_hi, 5, gdim, gstr, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)k, (cuuint64_t)cout, (cuuint64_t)ntaps};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)cout * ldw * 4};
+    cuuint32_t box[3] = {(cuuint32_t)IG_KC, (cuuint32_t)bn, 1};
+    int rc = encode_map(&mw_hi, w_hi, 3, gdim, gstr, box);
+    if (rc) return rc;
+    rc = encode_map(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  PVB_CUDA(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(kNumSMs, p.num_m_tiles * p.n_tiles);
+  PVB_LAUNCH(igemm_conv_kernel, grid, IG_THREADS, smem, stream, ma_hi, ma_lo, mw_hi, mw_lo, p);
+  return 0;
+}
+
+/* Diagnostic: code of the mbarrier wait that starved (0 = none); readable after a trapped launch only
+ * through a fresh context, so mainly useful under compute-sanitizer / in bring-up tests. */
+int pvcnn_igemm_last_error(int *host_code) {
+  if (!g_err_flag) { *host_code = 0; return 0; }
+  return (int)cudaMemcpy(host_code, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol the header
+declares; the drop-in `modules` package exposes the reference's names; the reference's own
+models build on top of it (when /root/reference is present)."""
+import ctypes
+import os
+import sys
+
+import pytest
+
+from pvcnn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _lib.header_symbols()
+    assert len(syms) >= 16
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+    assert lib.pvcnn_abi_version() == 1
+
+
+def test_modules_surface():
+    import modules
+    import modules.functional as F
+    from modules.frustum import get_box_corners_3d, FrustumPointNetLoss  # noqa: F401
+    for name in ["BallQuery", "FrustumPointNetLoss", "KLLoss", "PointNetAModule", "PointNetSAModule",
+                 "PointNetFPModule", "PVConv", "SE3d", "SharedMLP", "Voxelization"]:
+        assert hasattr(modules, name)
+    for name in ["ball_query", "trilinear_devoxelize", "grouping", "nearest_neighbor_interpolate", "kl_loss",
+                 "huber_loss", "gather", "furthest_point_sample", "logits_mask", "avg_voxelize"]:
+        assert hasattr(F, name)
+
+
+def test_pvconv_state_dict_matches_reference_layout():
+    import modules
+    m = modules.PVConv(64, 64, 3, 32, with_se=True)
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd["voxel_layers.0.weight"] == (64, 64, 3, 3, 3)
+    assert sd["voxel_layers.3.weight"] == (64, 64, 3, 3, 3)
+    assert sd["voxel_layers.1.running_var"] == (64,)
+    assert sd["voxel_layers.6.fc.0.weight"] == (8, 64) and sd["voxel_layers.6.fc.2.weight"] == (64, 8)
+    assert sd["point_features.layers.0.weight"] == (64, 64, 1)
+    assert "point_features.layers.1.num_batches_tracked" in sd
+
+
+def test_cpu_tensors_fail_loudly():
+    import torch
+    import modules.functional as F
+    with pytest.raises(RuntimeError):
+        F.avg_voxelize(torch.zeros(1, 2, 8), torch.zeros(1, 3, 8, dtype=torch.int32), 2)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_reference_models_build_on_our_modules():
+    """The reference's models/ (unmodified, imported from /root/reference) must compose our
+    `modules` package: same constructor signatures and state_dict layout."""
+    import importlib
+    import torch
+    added = "/root/reference"
+    # our repo root must win for `modules`; the reference only supplies `models`
+    sys.path.append(added)
+    try:
+        for mod in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[mod]
+        import modules
+        assert os.path.dirname(modules.__file__).startswith(ROOT)
+        s3dis = importlib.import_module("models.s3dis")
+        shapenet = importlib.import_module("models.shapenet")
+        kitti = importlib.import_module("models.kitti.frustum")
+        net = s3dis.PVCNN(num_classes=13, extra_feature_channels=6)
+        assert sum(p.numel() for p in net.parameters()) == 2572493
+        net2 = s3dis.PVCNN2(num_classes=13, extra_feature_channels=6)
+        assert sum(p.numel() for p in net2.parameters()) == 13709837
+        net3 = shapenet.PVCNN(num_classes=50, num_shapes=16, extra_feature_channels=3, width_multiplier=0.25)
+        assert sum(p.numel() for p in net3.parameters()) == 268898
+        assert kitti.FrustumPVCNNE is not None
+        assert isinstance(net.point_features[0], modules.PVConv)
+    finally:
+        sys.path.remove(added)

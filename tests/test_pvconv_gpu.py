@@ -1,0 +1,55 @@
+"""PVConv block parity on the GPU against the CPU oracle (fp32 restatement + fp64 truth)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from util import rng, s3dis_like_coords, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_block(cin, cout, r, with_se=False, normalize=True, eps=0.0, seed=0):
+    import modules
+    torch.manual_seed(seed)
+    m = modules.PVConv(cin, cout, 3, r, with_se=with_se, normalize=normalize, eps=eps)
+    # non-trivial BN affine parameters
+    with torch.no_grad():
+        for bn in (m.voxel_layers[1], m.voxel_layers[4], m.point_features.layers[1]):
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.uniform_(-0.3, 0.3)
+    return m
+
+
+def run_oracle(m, f, co, go, r, training=True, dtype="float32", **kw):
+    params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()
+              if "running" not in k and "num_batches" not in k}
+    buffers = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items() if "running" in k}
+    return oracle.pvconv_forward_backward(params, f, co, go, r, training=training, dtype=dtype,
+                                          buffers=None if training else buffers, **kw)
+
+
+@pytest.mark.parametrize("mode", ["composed", "fused"])
+@pytest.mark.parametrize("b,n,c,r", [(2, 1024, 16, 8), (2, 2048, 32, 16)])
+def test_pvconv_train_step(mode, b, n, c, r, monkeypatch):
+    if mode == "fused" and not os.path.exists(os.path.join(os.path.dirname(oracle.__file__), "..", "pvcnn_b200", "fused.py")):
+        pytest.skip("fused path not built yet")
+    monkeypatch.setenv("PVCNN_B200_PVCONV", mode)
+    if mode == "composed":
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    g = rng(30)
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n)
+    go = g.standard_normal((b, c, n), dtype=np.float32)
+    m = make_block(c, c, r).cuda().train()
+    ref = run_oracle(m, f, co, go, r, dtype="float64")
+    ft = torch.from_numpy(f).cuda().requires_grad_(True)
+    out, _ = m((ft, torch.from_numpy(co).cuda()))
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) < 1e-5
+    assert rel_err(ft.grad.cpu().numpy(), ref["grad_features"]) < 2e-5
+    for name, p in m.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), ref["grads"][name]) < 5e-5, name
