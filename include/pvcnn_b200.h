@@ -104,6 +104,36 @@ PVCNN_API int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n
                                                    const float *weights, float *grad_x,
                                                    void *stream);
 
+
+/* =====================================================================================
+ * Dense tcgen05 primitives (channels-last).  These replace the reference's cuDNN/cuBLAS calls:
+ * nn.Conv3d(k=3,pad=1) of modules/pvconv.py:21,24 and the 1x1 nn.Conv1d of
+ * modules/shared_mlp.py:10 (forward and data gradient); there is no reference launcher to cite
+ * because the reference delegates them to torch.
+ * ===================================================================================== */
+
+/* x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exact in tf32), lo = tf32(x - hi).
+ * n must be a multiple of 4. */
+PVCNN_API int pvcnn_split_tf32(long long n, const float *x, float *hi, float *lo, void *stream);
+
+/* Conv weight [cout][cin][ntaps] (torch layout, taps flattened kd*9+kh*3+kw; ntaps 1 or 27) ->
+ * GEMM "B" operand [ntaps][rows][ld], split into hi/lo.
+ *   mode 0 (forward):       rows = cout, K = cin,  wr[t][co][ci] = w[co][ci][t]
+ *   mode 1 (data gradient): rows = cin,  K = cout, wr[t][ci][co] = w[co][ci][ntaps-1-t]   */
+PVCNN_API int pvcnn_conv_weight_prep(int cout, int cin, int ntaps, int mode, int ld, const float *w,
+                                     float *w_hi, float *w_lo, void *stream);
+
+/* out[b,x,y,z,n] = bias[n] + sum_{tap,c} a[b, (x,y,z)+off(tap), c] * w[tap][n][c]   (zero padding)
+ *   a_hi/a_lo : [nb,sx,sy,sz,lda] channels-last, k valid channels (lda % 4 == 0)
+ *   w_hi/w_lo : [ntaps][cout][ldw] from pvcnn_conv_weight_prep;  out: [nb,sx,sy,sz,ldo]
+ *   npass = 3: error-compensated 3xTF32 (fp32-faithful, ~1e-6 rel);  npass = 1: plain TF32 (lo unused)
+ * A plain GEMM [M,K]x[N,K]^T is nb=sx=sy=1, sz=M, ntaps=1. */
+PVCNN_API int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, int ntaps,
+                               const float *a_hi, const float *a_lo, int lda, const float *w_hi,
+                               const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                               int npass, void *stream);
+PVCNN_API int pvcnn_igemm_last_error(int *host_code);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,63 @@
+"""Pins the CPU oracle to REAL reference outputs: tests/golden/ref_ops_golden.npz was produced on a
+B200 by the reference's own unmodified CUDA kernels (tests/golden/make_golden.py).  Integer / index
+outputs must match bit-exactly, fp32 outputs within 1e-5 relative (atomics make the reference's own
+summation order nondeterministic)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import rel_err
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ops_golden.npz")
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(G)
+
+
+def test_voxelize_coords_vs_reference_torch_ops(gold):
+    """The reference computed these with torch ops on the GPU (modules/voxelization.py:17-24)."""
+    nc, vc = oracle.voxelize_coords(gold["vox_coords_in"], 8, True, 0.0)
+    assert np.abs(nc - gold["vox_norm"]).max() < 2e-6
+    assert (vc != gold["vox_vc"]).mean() < 1e-3  # ulp-level reduction-order differences may flip a .5 tie
+
+
+def test_avg_voxelize(gold):
+    out, ind, cnt = oracle.avg_voxelize(gold["vox_feat"], gold["vox_vc"], 8)
+    assert np.array_equal(ind, gold["vox_ind"]) and np.array_equal(cnt, gold["vox_cnt"])
+    assert rel_err(out, gold["vox_out"]) < TOL
+    gx = oracle.avg_voxelize_grad(gold["vox_gy"], gold["vox_ind"], gold["vox_cnt"])
+    assert rel_err(gx, gold["vox_gx"]) < TOL
+
+
+def test_trilinear_devoxelize(gold):
+    out, inds, wgts = oracle.trilinear_devoxelize(gold["devox_grid"], gold["vox_norm"], 8, True)
+    assert np.array_equal(inds, gold["devox_inds"])
+    assert np.array_equal(wgts, gold["devox_wgts"])  # same left-to-right products -> identical floats
+    assert rel_err(out, gold["devox_out"]) < TOL
+    gx = oracle.trilinear_devoxelize_grad(gold["devox_gy"], gold["devox_inds"], gold["devox_wgts"], 8)
+    assert rel_err(gx, gold["devox_gx"]) < TOL
+
+
+def test_fps_ballquery_grouping(gold):
+    p = gold["pn_points"]
+    fps = oracle.furthest_point_sampling(p, 96)
+    assert np.array_equal(fps, gold["pn_fps"])          # incl. the quantised (tie-heavy) sample
+    centers = oracle.gather(p, fps)
+    assert np.array_equal(centers, gold["pn_centers"])
+    bq = oracle.ball_query(centers, p, 0.25, 16)
+    assert np.array_equal(bq, gold["pn_bq"])
+    assert np.array_equal(oracle.grouping(gold["pn_feat"], bq), gold["pn_group"])
+    assert rel_err(oracle.grouping_grad(gold["pn_ggy"], bq, 600), gold["pn_ggx"]) < TOL
+
+
+def test_three_nn(gold):
+    idx, w = oracle.three_nn(gold["pn_points"], gold["pn_centers"])
+    assert np.array_equal(idx, gold["pn_iidx"])
+    assert rel_err(w, gold["pn_iw"]) < TOL
+    assert rel_err(oracle.three_nn_interpolate(gold["pn_cf"], idx, w), gold["pn_interp"]) < TOL
+    assert rel_err(oracle.three_nn_interpolate_grad(gold["pn_igy"], idx, w, 96), gold["pn_igx"]) < TOL

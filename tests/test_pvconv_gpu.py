@@ -52,4 +52,11 @@ def test_pvconv_train_step(mode, b, n, c, r, monkeypatch):
     assert rel_err(out.detach().cpu().numpy(), ref["out"]) < 1e-5
     assert rel_err(ft.grad.cpu().numpy(), ref["grad_features"]) < 2e-5
     for name, p in m.named_parameters():
-        assert rel_err(p.grad.cpu().numpy(), ref["grads"][name]) < 5e-5, name
+        got, want = p.grad.cpu().numpy(), ref["grads"][name]
+        if name in ("voxel_layers.0.bias", "voxel_layers.3.bias", "point_features.layers.0.bias"):
+            # a bias in front of a train-mode BatchNorm has an exactly-zero gradient; both sides
+            # only hold summation noise, so compare on the scale of the layer's weight gradient
+            scale = np.abs(ref["grads"][name.replace("bias", "weight")]).max()
+            assert np.abs(got - want).max() < 1e-4 * scale, name
+        else:
+            assert rel_err(got, want) < 5e-5, name
