@@ -113,7 +113,8 @@ PVCNN_API int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n
  * ===================================================================================== */
 
 /* x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exact in tf32), lo = tf32(x - hi).
- * n must be a multiple of 4. */
+ * n must be a multiple of 4.  hi may be NULL: kind::tf32 truncates its fp32 operands (measured),
+ * so x itself can be passed wherever an a_hi / w_hi operand is expected. */
 PVCNN_API int pvcnn_split_tf32(long long n, const float *x, float *hi, float *lo, void *stream);
 
 /* Conv weight [cout][cin][ntaps] (torch layout, taps flattened kd*9+kh*3+kw; ntaps 1 or 27) ->

@@ -15,9 +15,14 @@
 //   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
 //     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias -> global).
 //   * fp32 parity: tf32 has a 10-bit mantissa, the north-star tolerance is 1e-5.  npass=3 runs the
-//     error-compensated split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (hi/lo exactly
-//     representable in tf32, produced by split_tf32_kernel), accumulating all three in the same
-//     fp32 TMEM accumulator.  npass=1 is plain TF32 (what cuDNN does by default in the reference).
+//     error-compensated split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  Measured on B200
+//     (tests/test_igemm_gpu.py::test_hw_rounding_probe): kind::tf32 TRUNCATES fp32 operands, so the
+//     raw fp32 tensor serves as a_hi and only a_lo = x - trunc(x) is materialised.  The tensor core
+//     also truncates when it accumulates (~2^-24 relative bias per MMA), which over a 27-tap, K=1728
+//     chain reaches ~1.5e-5; therefore (1) the tiny correction terms get their own TMEM
+//     accumulator and (2) the main chain is split over up to 3 accumulators of <= 72 MMAs each;
+//     the epilogue adds the partial sums in round-to-nearest fp32.
+//     npass=1 is plain TF32 (what cuDNN does by default in the reference).
 #include <mutex>
 #include <unordered_map>
 
@@ -31,6 +36,7 @@ constexpr int IG_BLOCK_M = 128;
 constexpr int IG_KC = 32;  // channels per k-block = 128 bytes = one swizzle row
 constexpr int IG_THREADS = 256;
 constexpr int IG_MAX_STAGES = 8;
+constexpr int IG_MAX_CHAIN = 72;  // MMAs accumulated into one TMEM accumulator
 constexpr uint32_t IG_A_TILE_BYTES = IG_BLOCK_M * IG_KC * 4;  // 16 KB
 
 struct IgemmParams {
@@ -41,6 +47,9 @@ struct IgemmParams {
   int cin_chunks, ntaps;
   int cout, block_n;
   int npass, stages;
+  int acc_split;      // main accumulators per tile (bounds the RZ-rounded tensor-core accumulation chain)
+  int acc_slots;      // acc_split + (npass > 1): the correction terms get their own accumulator
+  int acc_bufs;       // 2 when two tiles' accumulators fit in TMEM (512 columns), else 1
   int ldo;
   uint32_t stage_bytes, a_bytes, b_bytes, tx_bytes, tmem_cols;
   const float *bias;
@@ -125,14 +134,21 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
       uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it % p.acc_bufs;
+        const uint32_t acc_phase = (it / p.acc_bufs) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, p.err, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        const uint32_t tile_tmem = tmem_base + (uint32_t)(acc * p.acc_slots * p.block_n);
+        const uint32_t corr_tmem = tile_tmem + (uint32_t)(p.acc_split * p.block_n);
+        int prev_slot = -1;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, p.err, 3);
           tc_fence_after();
+          // k-blocks are dealt to the main accumulators in contiguous ranges
+          const int slot = (int)(((long long)kb * p.acc_split) / num_kb);
+          const uint32_t d_tmem = tile_tmem + (uint32_t)(slot * p.block_n);
+          const bool fresh = slot != prev_slot;
+          prev_slot = slot;
           const uint32_t a_hi = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t a_lo = a_hi + IG_A_TILE_BYTES;
           const uint32_t b_hi = a_hi + p.a_bytes;
@@ -142,12 +158,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
             const uint32_t koff = k * 8 * 4;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
             const uint64_t da_hi = make_smem_desc(a_hi + koff, 0, 1024, kLayoutSW128);
             const uint64_t db_hi = make_smem_desc(b_hi + koff, 0, 1024, kLayoutSW128);
-            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, (kb | k) != 0);
+            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, !(fresh && k == 0));
             if (p.npass > 1) {
               const uint64_t da_lo = make_smem_desc(a_lo + koff, 0, 1024, kLayoutSW128);
               const uint64_t db_lo = make_smem_desc(b_lo + koff, 0, 1024, kLayoutSW128);
-              mma_tf32_ss(d_tmem, da_hi, db_lo, idesc, 1);
-              mma_tf32_ss(d_tmem, da_lo, db_hi, idesc, 1);
+              mma_tf32_ss(corr_tmem, da_hi, db_lo, idesc, (kb | k) != 0);
+              mma_tf32_ss(corr_tmem, da_lo, db_hi, idesc, 1);
             }
           }
           mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
@@ -163,8 +179,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
     const int lz = m % p.bz, ly = (m / p.bz) % p.by, lx = m / (p.bz * p.by);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % p.acc_bufs;
+      const uint32_t acc_phase = (it / p.acc_bufs) & 1;
       const int n_tile = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int z = (mt % p.tz) * p.bz + lz; mt /= p.tz;
@@ -175,11 +191,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
       float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + z) * p.ldo + (size_t)n_tile * p.block_n;
       mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(acc * p.acc_slots * p.block_n);
       const int ncols = min(p.block_n, p.cout - n_tile * p.block_n);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
+        // partial accumulators are combined here in round-to-nearest fp32 (the tensor core's own
+        // accumulation truncates, so its chains are kept short; see DESIGN.md "accumulation")
+        for (int sl = 1; sl < p.acc_slots; ++sl) {
+          float t[16];
+          tmem_ld16(taddr + sl * p.block_n + c0, t);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += t[i];
+        }
         if (valid && c0 < ncols) {
           if (p.bias) {
 #pragma unroll
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(long long n4, const flo
     const float4 v = x[i];
     float4 h, l;
     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    hi[i] = h;
+    if (hi) hi[i] = h;
     lo[i] = l;
   }
 }
@@ -291,7 +315,7 @@ using namespace pvb;
 extern "C" {
 
 int pvcnn_split_tf32(long long n, const float *x, float *hi, float *lo, void *stream) {
-  PVB_CHECK_ARG(n > 0 && (n % 4) == 0 && x && hi && lo);
+  PVB_CHECK_ARG(n > 0 && (n % 4) == 0 && x && lo);
   const long long n4 = n / 4;
   PVB_LAUNCH(split_tf32_kernel, min((long long)ceil_div(n4, 256), (long long)kNumSMs * 16), 256, 0, stream, n4,
              reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo));
@@ -345,8 +369,17 @@ int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, int ntaps,
   const int smem_budget = 227 * 1024 - 2048;
   p.stages = min(IG_MAX_STAGES, smem_budget / (int)p.stage_bytes);
   PVB_CHECK_ARG(p.stages >= 2);
+  // the tensor core accumulates with truncation (measured: ~2^-24 relative bias per accumulate), so
+  // one accumulator sees at most ~IG_MAX_CHAIN MMAs; partial sums are combined in the epilogue
+  const int chain = ntaps * p.cin_chunks * (IG_KC / 8);
+  int split = ceil_div(chain, IG_MAX_CHAIN);
+  const int corr = npass > 1 ? 1 : 0;
+  while (split > 1 && (split + corr) * bn > 512) --split;
+  p.acc_split = split;
+  p.acc_slots = split + corr;
+  p.acc_bufs = (2 * p.acc_slots * bn <= 512) ? 2 : 1;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * bn)) cols <<= 1;
+  while (cols < (uint32_t)(p.acc_bufs * p.acc_slots * bn)) cols <<= 1;
   p.tmem_cols = cols;
   p.bias = bias; p.out = out; p.err = g_err_flag;
   // B tiles must start 1024-aligned inside the stage: a_bytes is a multiple of 16 KB, b_hi = bn*128 bytes;

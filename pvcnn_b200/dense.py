@@ -5,11 +5,13 @@ import torch
 from . import _lib
 
 
-def split_tf32(x):
+def split_tf32(x, want_hi=True):
+    """(hi, lo) with hi = trunc_tf32(x) (or x itself when want_hi=False: the tensor core truncates)."""
     x = x.contiguous()
-    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    lo = torch.empty_like(x)
+    hi = torch.empty_like(x) if want_hi else None
     _lib.call("pvcnn_split_tf32", _LL(x.numel()), x, hi, lo)
-    return hi, lo
+    return (hi if want_hi else x), lo
 
 
 def _LL(v):
