@@ -135,6 +135,75 @@ PVCNN_API int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, 
                                int npass, void *stream);
 PVCNN_API int pvcnn_igemm_last_error(int *host_code);
 
+/* dW[co][ci][tap] = sum_v g[v][co] * x[v+off(tap)][ci]   (weight gradient of pvcnn_igemm_conv; torch
+ * weight layout).  x: layer input [nb,sx,sy,sz,ldx], g: output gradient [nb,sx,sy,sz,ldg]; lo
+ * operands as for pvcnn_igemm_conv.  dw is overwritten.  cout <= 128 in this version. */
+PVCNN_API int pvcnn_conv_wgrad(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps,
+                               const float *x_hi, const float *x_lo, int ldx, const float *g_hi,
+                               const float *g_lo, int ldg, float *dw, int npass, void *stream);
+
+/* =====================================================================================
+ * Fused PVConv block: replaces modules.PVConv.forward (modules/pvconv.py:33-39) and its autograd
+ * backward, i.e. Voxelization (modules/voxelization.py:16-25) -> Conv3d/BN3d/LeakyReLU x2
+ * (modules/pvconv.py:20-27) -> trilinear_devoxelize, plus SharedMLP (modules/shared_mlp.py:29-33)
+ * and the residual add, as ONE call each way.  with_se is not part of this entry point yet.
+ *
+ * Sizes below use  Mv = b*r^3, Mp = b*n, ci = pad4(cin), co = pad4(cout), ld(x) = roundup(x,32).
+ * ===================================================================================== */
+typedef struct {
+  int b, n, cin, cout, r;
+  int normalize;      /* Voxelization(normalize=...)                       */
+  float eps;          /* Voxelization eps                                  */
+  int training;       /* BN batch statistics + running-stat update         */
+  int npass;          /* 3 = fp32-faithful 3xTF32, 1 = plain TF32          */
+  float bn_eps_vox;   /* 1e-4 (modules/pvconv.py:22)                       */
+  float bn_eps_pt;    /* 1e-5 (nn.BatchNorm1d default)                     */
+  float momentum;     /* 0.1                                               */
+  float slope;        /* LeakyReLU 0.1                                     */
+} pvcnn_pvconv_desc;
+
+typedef struct { /* parameters in torch layouts; running stats are updated in training mode */
+  const float *w1, *b1, *g1, *be1; float *rm1, *rv1;   /* voxel_layers.0 / .1 */
+  const float *w2, *b2, *g2, *be2; float *rm2, *rv2;   /* voxel_layers.3 / .4 */
+  const float *wp, *bp, *gp, *bep; float *rmp, *rvp;   /* point_features.layers.0 / .1 */
+} pvcnn_pvconv_params;
+
+typedef struct { /* parameter gradients (same shapes as the parameters) */
+  float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *wp, *bp, *gp, *bep;
+} pvcnn_pvconv_grads;
+
+typedef struct { /* caller-allocated device buffers (element counts in comments) */
+  float *nc;        /* b*3*n   normalised coords (also an output of the forward pass)   */
+  int *vc;          /* b*3*n   */
+  int *ind;         /* b*n     */
+  int *cnt;         /* b*r^3   */
+  float *fcl, *fcl_lo;      /* Mp*ci */
+  float *g0, *g0_lo;        /* Mv*ci */
+  float *y1, *z1, *z1_lo;   /* Mv*co */
+  float *y2;                /* Mv*co */
+  float *p;                 /* Mp*co */
+  float *coef;              /* 12*co  BN coefficients (mean, invstd, scale, shift) x 3 */
+  float *wprep;             /* pvcnn_pvconv_wprep_floats()    */
+  float *partials;          /* pvcnn_pvconv_partials_floats() */
+  float *sums;              /* 16*co  */
+  /* backward-only scratch */
+  float *ga, *gpp, *gpp_lo; /* Mp*co */
+  float *gfpt;              /* Mp*ci */
+  float *d2;                /* Mv*max(ci,co) */
+  float *gy2, *gy2_lo, *gy1, *gy1_lo; /* Mv*co */
+} pvcnn_pvconv_ws;
+
+PVCNN_API long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d);
+PVCNN_API long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d);
+/* features [b,cin,n], coords [b,3,n] -> out [b,cout,n] */
+PVCNN_API int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, const float *coords,
+                                   const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws, float *out,
+                                   void *stream);
+/* grad_out [b,cout,n] -> grad_features [b,cin,n] + parameter gradients; needs the ws of the forward */
+PVCNN_API int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out,
+                                    const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws,
+                                    float *grad_features, const pvcnn_pvconv_grads *grads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

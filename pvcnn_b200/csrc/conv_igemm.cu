@@ -306,10 +306,25 @@ static int encode_map(CUtensorMap *map, const void *ptr, int rank, const cuuint6
   return r == CUDA_SUCCESS ? 0 : (200000 + (int)r);
 }
 
+// 5-D map over a channels-last tensor [nb,sx,sy,sz,ld] with k valid channels and a {32, bz, by, bx, 1} box
+int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, int sx, int sy, int sz, int bz, int by,
+                     int bx) {
+  cuuint64_t gdim[5] = {(cuuint64_t)k, (cuuint64_t)sz, (cuuint64_t)sy, (cuuint64_t)sx, (cuuint64_t)nb};
+  cuuint64_t gstr[4] = {(cuuint64_t)ld * 4, (cuuint64_t)sz * ld * 4, (cuuint64_t)sy * sz * ld * 4,
+                        (cuuint64_t)sx * sy * sz * ld * 4};
+  cuuint32_t box[5] = {(cuuint32_t)IG_KC, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
+  return encode_map(map, ptr, 5, gdim, gstr, box);
+}
+
 static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps
 
 }  // namespace pvb
 
+namespace pvb {
+int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                 int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                 int npass, cudaStream_t stream);
+}
 using namespace pvb;
 
 extern "C" {
@@ -335,6 +350,15 @@ int pvcnn_conv_weight_prep(int cout, int cin, int ntaps, int mode, int ld, const
 int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi,
                      const float *a_lo, int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias,
                      float *out, int ldo, int npass, void *stream) {
+  return pvb::igemm_launch(nb, sx, sy, sz, k, cout, ntaps, a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, out, ldo, npass,
+                           (cudaStream_t)stream);
+}
+}  // extern "C"
+
+namespace pvb {
+int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                 int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                 int npass, cudaStream_t stream) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && k > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
   PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || (a_lo && w_lo)));
   PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
@@ -412,6 +436,9 @@ int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, int ntaps,
   return 0;
 }
 
+}  // namespace pvb
+
+extern "C" {
 /* Diagnostic: code of the mbarrier wait that starved (0 = none); readable after a trapped launch only
  * through a fresh context, so mainly useful under compute-sanitizer / in bring-up tests. */
 int pvcnn_igemm_last_error(int *host_code) {

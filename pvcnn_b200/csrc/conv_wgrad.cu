@@ -1,0 +1,302 @@
+// conv_wgrad.cu -- weight gradient of the 3x3x3 / 1x1 convolutions on tcgen05 tensor cores (sm_100a).
+//
+//   dW[co][ci][tap] = sum_v  gY[v][co] * X[v + off(tap)][ci]            (reduction over ALL voxels / points)
+//
+// Replaces cuDNN's wgrad for nn.Conv3d (modules/pvconv.py:21,24) and nn.Conv1d (modules/shared_mlp.py:10).
+//
+//   * Both operands are read straight from the channels-last activations, i.e. with the reduction
+//     index (voxel) as the ROW of the shared-memory tile and 32 channels per 128-byte row: that is the
+//     MN-major operand layout of tcgen05.mma (kind::tf32 supports it), so no transposed copies exist.
+//   * A = X tiles, shifted per tap by the TMA box coordinates (OOB zero fill = padding).  Four
+//     (tap, 32-channel) blocks form one M=128 operand; B = the gY tile (N = cout).
+//   * The tensor core truncates when it accumulates (see conv_igemm.cu), and this reduction is 524 288
+//     long at the metric shape.  So TMEM only holds SHORT chains (<= 64 MMAs): the epilogue
+//     warps drain each finished chain into fp32 REGISTER accumulators (round-to-nearest adds) while the
+//     MMA warp fills the other TMEM buffer.  The 3xTF32 correction terms use their own accumulators.
+//   * split-K over the SMs; partial results are combined with fp32 reductions into the zeroed dW.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pvb {
+using namespace umma;
+
+constexpr int WG_THREADS = 384;       // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 drain
+constexpr int WG_ROWS = 32;           // voxels per k-tile (box rows), 4 MMA K-steps
+constexpr uint32_t WG_BLK = WG_ROWS * 128;  // bytes of one [32 rows x 32 channels] block
+constexpr int WG_STAGES = 2;
+constexpr int WG_DRAIN_TILES = 16;    // k-tiles per TMEM chain: 16 * 4 = 64 MMAs
+
+struct WgradParams {
+  int nb, sx, sy, sz;
+  int bz, by;               // k-tile box (bz * by = rows <= 32, multiple of 8)
+  int tz, ty;               // k-tiles per dim (x is walked one slice at a time)
+  long long num_ktiles;
+  int cin, cout, ntaps;
+  int chunks_in, chunks_out;
+  int n_ablocks;            // ntaps * chunks_in
+  int groups_per_cta;       // G: M=128 operand groups handled by one CTA
+  int num_sets;             // ceil(ceil(n_ablocks/4) / G)
+  int ksplit;               // CTAs per set
+  int block_n;              // cout padded to 16 (<= 128)
+  int npass;
+  int ksteps;               // rows / 8
+  uint32_t stage_bytes, g_bytes;  // g_bytes: bytes of the gY part of a stage (hi [+lo])
+  uint32_t box_bytes;             // bytes one TMA box really delivers (rows * 128)
+  float *dw;                // [cout][cin][ntaps], zero-initialised by the launcher
+  int *err;
+};
+
+template <int G>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                      const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                      const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int set = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
+  const int ab0 = set * G * 4;                                  // first A-block of this CTA
+  const int nab = min(G * 4, p.n_ablocks - ab0);                // A-blocks that really exist
+  const int ngroups = (nab + 3) / 4;
+  const uint32_t passes = p.npass > 1 ? 2u : 1u;                // hi [+ lo] copies of each operand
+  const uint32_t tmem_cols_per_buf = (uint32_t)(G * p.block_n * (p.npass > 1 ? 2 : 1));
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2 * tmem_cols_per_buf) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_x_hi);
+    prefetch_tensormap(&map_g_hi);
+    if (p.npass > 1) { prefetch_tensormap(&map_x_lo); prefetch_tensormap(&map_g_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // number of k-tiles this CTA walks
+  const long long my_tiles = p.num_ktiles > split ? (p.num_ktiles - split + p.ksplit - 1) / p.ksplit : 0;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      const uint32_t tx_bytes = p.box_bytes * passes * (uint32_t)(p.chunks_out + nab);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = 0; t < my_tiles; ++t) {
+        long long kt = split + t * p.ksplit;
+        const int z0 = (int)(kt % p.tz) * p.bz; kt /= p.tz;
+        const int y0 = (int)(kt % p.ty) * p.by; kt /= p.ty;
+        const int x0 = (int)(kt % p.sx); kt /= p.sx;
+        const int b = (int)kt;
+        mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
+        uint8_t *st = smem + (size_t)stage * p.stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        for (int cc = 0; cc < p.chunks_out; ++cc) {
+          tma_load_5d(st + (size_t)cc * WG_BLK, &map_g_hi, &full_bar[stage], cc * 32, z0, y0, x0, b);
+          if (p.npass > 1)
+            tma_load_5d(st + (size_t)(p.chunks_out + cc) * WG_BLK, &map_g_lo, &full_bar[stage], cc * 32, z0, y0, x0, b);
+        }
+        uint8_t *sa = st + p.g_bytes;
+        for (int a = 0; a < nab; ++a) {
+          const int ab = ab0 + a;
+          const int tap = ab / p.chunks_in, cc = ab - tap * p.chunks_in;
+          int dx = 0, dy = 0, dz = 0;
+          if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
+          tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], cc * 32, z0 + dz, y0 + dy, x0 + dx, b);
+          if (p.npass > 1)
+            tma_load_5d(sa + (size_t)(G * 4 + a) * WG_BLK, &map_x_lo, &full_bar[stage], cc * 32, z0 + dz, y0 + dy,
+                        x0 + dx, b);
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(128, p.block_n, /*a MN-major*/ 1, /*b MN-major*/ 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int chain = 0;  // index of the current TMEM chain
+      for (long long t = 0; t < my_tiles; ++t) {
+        const int pos_in_chain = (int)(t % WG_DRAIN_TILES);
+        const int buf = chain & 1;
+        if (pos_in_chain == 0) {
+          mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1, p.err, 12);
+          tc_fence_after();
+        }
+        mbar_wait(&full_bar[stage], phase, p.err, 13);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t g_hi = st, g_lo = st + (uint32_t)p.chunks_out * WG_BLK;
+        const uint32_t a_base = st + p.g_bytes;
+        for (int g = 0; g < ngroups; ++g) {
+          const uint32_t a_hi = a_base + (uint32_t)(g * 4) * WG_BLK;
+          const uint32_t a_lo = a_base + (uint32_t)(G * 4 + g * 4) * WG_BLK;
+          const uint32_t d_main = tmem_base + (uint32_t)buf * tmem_cols_per_buf + (uint32_t)(g * p.block_n);
+          const uint32_t d_corr = d_main + (uint32_t)(G * p.block_n);
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const uint32_t koff = (uint32_t)ks * 1024u;  // 8 voxel rows = one 1024-byte swizzle atom
+            // MN-major SW128: LBO = stride between 32-channel blocks, SBO = stride between 8-row K groups
+            const uint64_t da_hi = make_smem_desc(a_hi + koff, WG_BLK, 1024, kLayoutSW128);
+            const uint64_t db_hi = make_smem_desc(g_hi + koff, WG_BLK, 1024, kLayoutSW128);
+            const uint32_t accum = (pos_in_chain | ks) != 0;
+            mma_tf32_ss(d_main, da_hi, db_hi, idesc, accum);
+            if (p.npass > 1) {
+              const uint64_t da_lo = make_smem_desc(a_lo + koff, WG_BLK, 1024, kLayoutSW128);
+              const uint64_t db_lo = make_smem_desc(g_lo + koff, WG_BLK, 1024, kLayoutSW128);
+              mma_tf32_ss(d_corr, da_hi, db_lo, idesc, accum);
+              mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
+            }
+          }
+        }
+        mma_commit(&empty_bar[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        if (pos_in_chain == WG_DRAIN_TILES - 1 || t == my_tiles - 1) {
+          mma_commit(&tmem_full_bar[buf]);
+          ++chain;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ drain / epilogue ================================
+    const int e = warp - 4;
+    const int q = e & 3;   // TMEM lane quarter
+    const int h = e >> 2;  // column half
+    const int cols = p.block_n / 2;            // columns owned per accumulator
+    constexpr int CMAX = 64 / G;               // register columns per group (G=2: 32, G=1: 64)
+    float acc[G][CMAX];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int i = 0; i < CMAX; ++i) acc[g][i] = 0.0f;
+    const long long nchains = (my_tiles + WG_DRAIN_TILES - 1) / WG_DRAIN_TILES;
+    for (long long ch = 0; ch < nchains; ++ch) {
+      const int buf = (int)(ch & 1);
+      mbar_wait(&tmem_full_bar[buf], (uint32_t)((ch >> 1) & 1), p.err, 14);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * tmem_cols_per_buf;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int c0 = 0; c0 < CMAX; c0 += 16) {
+          if (g < ngroups && c0 < cols) {  // warp-uniform
+            float v[16];
+            tmem_ld16(tb + (uint32_t)(g * p.block_n + h * cols + c0), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[g][c0 + i] += v[i];
+            if (p.npass > 1) {
+              tmem_ld16(tb + (uint32_t)(G * p.block_n + g * p.block_n + h * cols + c0), v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[g][c0 + i] += v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    // scatter-add this CTA's partial dW:  D row m = (A-block m/32, channel m%32), column = cout index
+    const int m = q * 32 + lane;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int a = g * 4 + (m >> 5);
+      if (g < ngroups && a < nab) {
+        const int ab = ab0 + a;
+        const int tap = ab / p.chunks_in, cc = ab - tap * p.chunks_in;
+        const int ci = cc * 32 + (m & 31);
+        if (ci < p.cin) {
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c) {
+            const int co = h * cols + c;
+            if (c < cols && co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * p.ntaps + tap, acc[g][c]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, int sx, int sy, int sz, int bz, int by,
+                     int bx);  // conv_igemm.cu
+
+static int *g_wg_err = nullptr;
+
+// x: layer input [nb,sx,sy,sz,ldx] (cin valid), g: output gradient [nb,sx,sy,sz,ldg] (cout valid)
+int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
+                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s) {
+  PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
+  PVB_CHECK_ARG(x_hi && g_hi && dw && (npass == 1 || (x_lo && g_lo)) && ldx % 4 == 0 && ldg % 4 == 0);
+  if (cout > 128) return PVCNN_E_UNSUPPORTED;  // TODO(round 2): N tiling for wide SharedMLPs
+  if (!g_wg_err) {
+    PVB_CUDA(cudaMalloc((void **)&g_wg_err, sizeof(int)));
+    PVB_CUDA(cudaMemset(g_wg_err, 0, sizeof(int)));
+  }
+  WgradParams p{};
+  p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
+  p.bz = ((min(sz, WG_ROWS) + 7) / 8) * 8;
+  p.by = max(1, WG_ROWS / p.bz);
+  if (p.by > sy) p.by = sy;
+  const int rows = p.bz * p.by;
+  p.ksteps = rows / 8;
+  p.tz = ceil_div(sz, p.bz);
+  p.ty = ceil_div(sy, p.by);
+  p.num_ktiles = (long long)nb * sx * p.ty * p.tz;
+  p.cin = cin; p.cout = cout; p.ntaps = ntaps;
+  p.chunks_in = ceil_div(cin, 32);
+  p.chunks_out = ceil_div(cout, 32);
+  p.n_ablocks = ntaps * p.chunks_in;
+  p.block_n = max(16, ((cout + 15) / 16) * 16);
+  p.groups_per_cta = p.block_n <= 64 ? 2 : 1;
+  const int ngroups = ceil_div(p.n_ablocks, 4);
+  p.num_sets = ceil_div(ngroups, p.groups_per_cta);
+  p.ksplit = max(1, kNumSMs / p.num_sets);
+  if ((long long)p.ksplit > p.num_ktiles) p.ksplit = (int)p.num_ktiles;
+  p.npass = npass;
+  const uint32_t passes = npass > 1 ? 2 : 1;
+  p.g_bytes = (uint32_t)p.chunks_out * WG_BLK * passes;
+  p.stage_bytes = p.g_bytes + (uint32_t)(p.groups_per_cta * 4) * WG_BLK * passes;
+  p.box_bytes = (uint32_t)rows * 128u;
+  p.dw = dw;
+  p.err = g_wg_err;
+  PVB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * cin * ntaps, s));
+
+  CUtensorMap mx_hi, mx_lo, mg_hi, mg_lo;
+  int rc;
+  if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
+  if ((rc = encode_map_5d_cl(&mx_lo, npass > 1 ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_lo, npass > 1 ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
+  const size_t smem = (size_t)WG_STAGES * p.stage_bytes + 1024;
+  if (p.groups_per_cta == 2) {
+    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(conv_wgrad_kernel<2>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(conv_wgrad_kernel<1>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+  }
+  return 0;
+}
+
+}  // namespace pvb
+
+extern "C" int pvcnn_conv_wgrad(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi,
+                                const float *x_lo, int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw,
+                                int npass, void *stream) {
+  return pvb::wgrad_launch(nb, sx, sy, sz, cin, cout, ntaps, x_hi, x_lo, ldx, g_hi, g_lo, ldg, dw, npass,
+                           (cudaStream_t)stream);
+}

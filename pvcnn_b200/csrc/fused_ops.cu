@@ -1,0 +1,640 @@
+// fused_ops.cu -- channels-last HBM-bound kernels of the fused PVConv pipeline (see fused_ops.cuh).
+//
+// These replace, in one pass each, chains of separate kernels in the reference:
+//   voxelize_cl           <- avg_voxelize_kernel (vox.cu:48-72) but channels-last, warp-aggregated
+//   bn_stats/bn_apply     <- nn.BatchNorm3d + nn.LeakyReLU (modules/pvconv.py:22-26)
+//   devox_fused           <- BatchNorm3d-apply + LeakyReLU + trilinear_devoxelize_kernel
+//                            (trilinear_devox.cu:21-105) + BatchNorm1d-apply + ReLU + add
+//                            (modules/pvconv.py:36-38, modules/shared_mlp.py:11-12)
+//   bwd_points            <- add-backward, ReLU/BN1d backward reductions, trilinear_devoxelize_grad_kernel
+//                            (trilinear_devox.cu:119-162), LeakyReLU backward, BN3d backward reductions
+//   bn_bwd_apply          <- BatchNorm backward (input gradient) + conv-bias gradient
+//   bwd_final             <- avg_voxelize_grad_kernel (vox.cu:86-110) + add of the point-branch gradient
+// All of them stream rows of C contiguous floats with 128-bit accesses.
+#include "fused_ops.cuh"
+
+namespace pvb {
+
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __fsub_rn(x, hi);  // <= 13 significant bits; the tensor core truncates it to tf32 itself
+}
+__device__ __forceinline__ float4 tf32_lo4(float4 v) {
+  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
+__device__ __forceinline__ float leaky(float z, float slope) { return z > 0.0f ? z : z * slope; }
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+static inline int grid_for(long long work_items, int per_block, int max_blocks) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) points_to_cl_kernel(int c, int n, int cp, const float *__restrict__ x,
+                                                           float *__restrict__ xcl, float *__restrict__ xlo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = c0 + ty + 8 * j, i = n0 + tx;
+    tile[ty + 8 * j][tx] = (cc < c && i < n) ? x[((size_t)b * c + cc) * n + i] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = n0 + ty + 8 * j, cc = c0 + tx;
+    if (p < n && cc < cp) {
+      const float v = tile[tx][ty + 8 * j];
+      const size_t o = ((size_t)b * n + p) * cp + cc;
+      xcl[o] = v;
+      if (xlo) xlo[o] = tf32_lo(v);
+    }
+  }
+}
+
+int launch_points_to_cl(int b, int c, int n, int cp, const float *x, float *xcl, float *xcl_lo, cudaStream_t s) {
+  PVB_LAUNCH(points_to_cl_kernel, dim3(ceil_div(n, 32), ceil_div(cp, 32), b), 256, 0, s, c, n, cp, x, xcl, xcl_lo);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vox_index_count_cl_kernel(int n, int r, int r3, long long total,
+                                                                 const int *__restrict__ coords,
+                                                                 int *__restrict__ ind, int *__restrict__ cnt) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(t / n), i = (int)(t % n);
+    const int *co = coords + (size_t)b * 3 * n;
+    const int v = co[i] * r * r + co[i + n] * r + co[i + 2 * n];  // vox.cu:31
+    ind[t] = v;
+    atomicAdd(cnt + (size_t)b * r3 + v, 1);
+  }
+}
+
+int launch_vox_index_count(int b, int n, int r, const int *coords, int *ind, int *cnt, cudaStream_t s) {
+  const int r3 = r * r * r;
+  PVB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * r3, s));
+  const long long total = (long long)b * n;
+  PVB_LAUNCH(vox_index_count_cl_kernel, grid_for(total, 256, kNumSMs * 8), 256, 0, s, n, r, r3, total, coords, ind,
+             cnt);
+  return 0;
+}
+
+// One warp owns 32 consecutive points.  Points of the warp that fall into the same voxel form a
+// group (match.any); the warp walks the groups, sums each group's rows in registers (coalesced
+// 16-byte loads, ascending point order) and issues ONE vector reduction per (voxel, 4 channels).
+__global__ void __launch_bounds__(256) voxelize_cl_kernel(int n, int r3, int cp, const int *__restrict__ ind,
+                                                          const int *__restrict__ cnt,
+                                                          const float *__restrict__ xcl, float *__restrict__ grid) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = blockIdx.x * 256 + warp * 32;
+  if (base >= n) return;
+  const int i = base + lane;
+  const bool valid = i < n;
+  const int pos = valid ? ind[(size_t)b * n + i] : -1 - lane;
+  const unsigned grp = __match_any_sync(0xffffffffu, pos);
+  const bool leader = valid && ((__ffs(grp) - 1) == lane);
+  float inv = 0.0f;
+  if (valid) inv = (float)(1.0 / (double)(float)cnt[(size_t)b * r3 + pos]);  // vox.cu:66
+  const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+  const int cp4 = cp >> 2;
+  const float *rows = xcl + ((size_t)b * n + base) * cp;
+  for (unsigned lm = leaders; lm; lm &= lm - 1) {
+    const int L = __ffs(lm) - 1;
+    const unsigned gmask = __shfl_sync(0xffffffffu, grp, L);
+    const int gpos = __shfl_sync(0xffffffffu, pos, L);
+    const float ginv = __shfl_sync(0xffffffffu, inv, L);
+    float *dst = grid + ((size_t)b * r3 + gpos) * cp;
+    for (int c4 = lane; c4 < cp4; c4 += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (unsigned mm = gmask; mm; mm &= mm - 1) {
+        const int src = __ffs(mm) - 1;
+        const float4 v = ld4(rows + (size_t)src * cp + c4 * 4);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, ginv));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, ginv));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, ginv));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v.w, ginv));
+      }
+      red_add4(dst + c4 * 4, acc);
+    }
+  }
+}
+
+int launch_voxelize_cl(int b, int n, int r3, int cp, const int *ind, const int *cnt, const float *xcl, float *grid,
+                       cudaStream_t s) {
+  PVB_LAUNCH(voxelize_cl_kernel, dim3(ceil_div(n, 256), b), 256, 0, s, n, r3, cp, ind, cnt, xcl, grid);
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) grid_lo_at_points_kernel(int n, int r3, int cp, long long total,
+                                                                const int *__restrict__ ind,
+                                                                const float *__restrict__ grid,
+                                                                float *__restrict__ grid_lo) {
+  const int cp4 = cp >> 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long p = t / cp4;
+    const int c4 = (int)(t % cp4);
+    const int b = (int)(p / n);
+    const size_t o = ((size_t)b * r3 + ind[p]) * cp + c4 * 4;
+    st4(grid_lo + o, tf32_lo4(ld4(grid + o)));
+  }
+}
+
+int launch_grid_lo_at_points(int b, int n, int r3, int cp, const int *ind, const float *grid, float *grid_lo,
+                             cudaStream_t s) {
+  const long long total = (long long)b * n * (cp / 4);
+  PVB_LAUNCH(grid_lo_at_points_kernel, grid_for(total, 256, kNumSMs * 16), 256, 0, s, n, r3, cp, total, ind, grid,
+             grid_lo);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// Column reductions over [rows, cp]: thread -> (channel quad c4 = t % cp4, row lane = t / cp4).
+// --------------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = kNumSMs * 4;
+
+template <int NSETS, typename F>
+__device__ __forceinline__ void column_reduce(long long rows, int cp, float *partials, F &&body) {
+  __shared__ float4 red[NSETS][RED_THREADS];
+  const int cp4 = cp >> 2;
+  const int rl = RED_THREADS / cp4;  // row lanes (cp4 <= 256)
+  const int c4 = threadIdx.x % cp4, lane_r = threadIdx.x / cp4;
+  float4 acc[NSETS];
+#pragma unroll
+  for (int k = 0; k < NSETS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane_r < rl)
+    for (long long r = (long long)blockIdx.x * rl + lane_r; r < rows; r += (long long)gridDim.x * rl)
+      body(r, c4, acc);
+#pragma unroll
+  for (int k = 0; k < NSETS; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < cp4) {
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+      float4 s = red[k][threadIdx.x];
+      for (int j = 1; j < rl; ++j) {
+        const float4 v = red[k][threadIdx.x + j * cp4];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      st4(partials + ((size_t)blockIdx.x * NSETS + k) * cp + threadIdx.x * 4, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) bn_stats_kernel(long long rows, int cp, const float *__restrict__ y,
+                                                               float *__restrict__ partials) {
+  column_reduce<2>(rows, cp, partials, [&](long long r, int c4, float4 *acc) {
+    const float4 v = ld4(y + (size_t)r * cp + c4 * 4);
+    acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+    acc[1].x = fmaf(v.x, v.x, acc[1].x); acc[1].y = fmaf(v.y, v.y, acc[1].y);
+    acc[1].z = fmaf(v.z, v.z, acc[1].z); acc[1].w = fmaf(v.w, v.w, acc[1].w);
+  });
+}
+
+int launch_bn_stats(long long rows, int cp, const float *y, float *partials, int *nblocks, cudaStream_t s) {
+  PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
+  const int rl = RED_THREADS / (cp / 4);
+  const int g = grid_for(rows, rl * 8, RED_MAX_BLOCKS);
+  *nblocks = g;
+  PVB_LAUNCH(bn_stats_kernel, g, RED_THREADS, 0, s, rows, cp, y, partials);
+  return 0;
+}
+
+// sums[set][c] = sum over blocks (fp64) of partials[block][set][c]
+__global__ void __launch_bounds__(256) reduce_partials_kernel(int nblocks, int ncols, const float *__restrict__ partials,
+                                                              float *__restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int k = 0; k < nblocks; ++k) s += (double)partials[(size_t)k * ncols + c];
+  sums[c] = (float)s;
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, int cp, double rows, float eps,
+                                                          float momentum, const float *__restrict__ partials,
+                                                          const float *__restrict__ gamma,
+                                                          const float *__restrict__ beta, float *running_mean,
+                                                          float *running_var, BnCoef coef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cp) return;
+  if (ch >= c) {
+    coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f;
+    return;
+  }
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nblocks; ++k) {
+    s += (double)partials[((size_t)k * 2 + 0) * cp + ch];
+    ss += (double)partials[((size_t)k * 2 + 1) * cp + ch];
+  }
+  const double mean = s / rows;
+  double var = ss / rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float scale = gamma[ch] * invstd;
+  coef.mean[ch] = (float)mean;
+  coef.invstd[ch] = invstd;
+  coef.scale[ch] = scale;
+  coef.shift[ch] = beta[ch] - (float)mean * scale;
+  if (running_mean) {  // torch: running = (1-m)*running + m*batch, unbiased variance
+    running_mean[ch] = (1.0f - momentum) * running_mean[ch] + momentum * (float)mean;
+    const double unbiased = rows > 1.0 ? var * rows / (rows - 1.0) : var;
+    running_var[ch] = (1.0f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
+                       const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
+                       cudaStream_t s) {
+  PVB_LAUNCH(bn_finalize_kernel, ceil_div(cp, 256), 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
+             gamma, beta, running_mean, running_var, coef);
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) bn_coef_running_kernel(int c, int cp, float eps, const float *__restrict__ gamma,
+                                                              const float *__restrict__ beta,
+                                                              const float *__restrict__ rm,
+                                                              const float *__restrict__ rv, BnCoef coef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cp) return;
+  if (ch >= c) {
+    coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f;
+    return;
+  }
+  const float invstd = 1.0f / sqrtf(rv[ch] + eps);
+  const float scale = gamma[ch] * invstd;
+  coef.mean[ch] = rm[ch];
+  coef.invstd[ch] = invstd;
+  coef.scale[ch] = scale;
+  coef.shift[ch] = beta[ch] - rm[ch] * scale;
+}
+
+int launch_bn_coef_from_running(int c, float eps, const float *gamma, const float *beta, const float *running_mean,
+                                const float *running_var, BnCoef coef, cudaStream_t s) {
+  const int cp = (c + 3) / 4 * 4;
+  PVB_LAUNCH(bn_coef_running_kernel, ceil_div(cp, 256), 256, 0, s, c, cp, eps, gamma, beta, running_mean,
+             running_var, coef);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_apply_leaky_kernel(long long total4, int cp, float slope,
+                                                             const float *__restrict__ y, BnCoef coef,
+                                                             float *__restrict__ z, float *__restrict__ zlo) {
+  extern __shared__ float sco[];  // [2][cp]
+  for (int c = threadIdx.x; c < cp; c += blockDim.x) {
+    sco[c] = coef.scale[c];
+    sco[cp + c] = coef.shift[c];
+  }
+  __syncthreads();
+  const int cp4 = cp >> 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % cp4);
+    const float4 v = ldg_stream4(y + t * 4);
+    const float4 sc = ld4(sco + c4 * 4), sh = ld4(sco + cp + c4 * 4);
+    float4 o;
+    o.x = leaky(fmaf(v.x, sc.x, sh.x), slope);
+    o.y = leaky(fmaf(v.y, sc.y, sh.y), slope);
+    o.z = leaky(fmaf(v.z, sc.z, sh.z), slope);
+    o.w = leaky(fmaf(v.w, sc.w, sh.w), slope);
+    st4(z + t * 4, o);
+    if (zlo) st4(zlo + t * 4, tf32_lo4(o));
+  }
+}
+
+int launch_bn_apply_leaky(long long rows, int cp, float slope, const float *y, BnCoef coef, float *z, float *z_lo,
+                          cudaStream_t s) {
+  const long long total4 = rows * (cp / 4);
+  PVB_LAUNCH(bn_apply_leaky_kernel, grid_for(total4, 256 * 4, kNumSMs * 8), 256, 2 * cp * sizeof(float), s, total4,
+             cp, slope, y, coef, z, z_lo);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// trilinear corner setup, identical arithmetic to trilinear_devox.cu:36-75
+// --------------------------------------------------------------------------------------------
+struct Corners {
+  float w[8];
+  int idx[8];
+};
+__device__ __forceinline__ void corner_setup(float x, float y, float z, int r, Corners &k) {
+  const int r2 = r * r;
+  const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+  const float xd1 = __fsub_rn(x, xl), yd1 = __fsub_rn(y, yl), zd1 = __fsub_rn(z, zl);
+  const float xd0 = __fsub_rn(1.0f, xd1), yd0 = __fsub_rn(1.0f, yd1), zd0 = __fsub_rn(1.0f, zd1);
+  const float a00 = __fmul_rn(xd0, yd0), a01 = __fmul_rn(xd0, yd1), a10 = __fmul_rn(xd1, yd0),
+              a11 = __fmul_rn(xd1, yd1);
+  k.w[0] = __fmul_rn(a00, zd0); k.w[1] = __fmul_rn(a00, zd1);
+  k.w[2] = __fmul_rn(a01, zd0); k.w[3] = __fmul_rn(a01, zd1);
+  k.w[4] = __fmul_rn(a10, zd0); k.w[5] = __fmul_rn(a10, zd1);
+  k.w[6] = __fmul_rn(a11, zd0); k.w[7] = __fmul_rn(a11, zd1);
+  const int dz = zd1 > 0 ? 1 : 0, dy = yd1 > 0 ? r : 0, dx = xd1 > 0 ? r2 : 0;
+  k.idx[0] = (int)xl * r2 + (int)yl * r + (int)zl;
+  k.idx[1] = k.idx[0] + dz;
+  k.idx[2] = k.idx[0] + dy;
+  k.idx[3] = k.idx[2] + dz;
+  k.idx[4] = k.idx[0] + dx;
+  k.idx[5] = k.idx[4] + dz;
+  k.idx[6] = k.idx[4] + dy;
+  k.idx[7] = k.idx[6] + dz;
+}
+
+constexpr int PT_TILE = 32;   // points per CTA
+constexpr int PT_WARPS = 8;   // each warp walks PT_TILE / PT_WARPS points
+
+// smem: tile[cp][33] floats
+__global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, int r, float slope,
+                                                          const float *__restrict__ nc,
+                                                          const float *__restrict__ y2, BnCoef bn2,
+                                                          const float *__restrict__ p, BnCoef bnp,
+                                                          float *__restrict__ out) {
+  extern __shared__ float tile[];
+  const int b = blockIdx.y, i0 = blockIdx.x * PT_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r3 = r * r * r, cp4 = cp >> 2;
+  const float *co = nc + (size_t)b * 3 * n;
+  for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
+    const int pt = warp * (PT_TILE / PT_WARPS) + q;
+    const int i = i0 + pt;
+    if (i >= n) break;
+    Corners k;
+    corner_setup(co[i], co[i + n], co[i + 2 * n], r, k);
+    const float *prow = p + ((size_t)b * n + i) * cp;
+    for (int c4 = lane; c4 < cp4; c4 += 32) {
+      const float4 sc = ld4(bn2.scale + c4 * 4), sh = ld4(bn2.shift + c4 * 4);
+      float4 acc;
+      {
+        const float4 v = ld4(y2 + ((size_t)b * r3 + k.idx[0]) * cp + c4 * 4);
+        acc.x = __fmul_rn(k.w[0], leaky(fmaf(v.x, sc.x, sh.x), slope));
+        acc.y = __fmul_rn(k.w[0], leaky(fmaf(v.y, sc.y, sh.y), slope));
+        acc.z = __fmul_rn(k.w[0], leaky(fmaf(v.z, sc.z, sh.z), slope));
+        acc.w = __fmul_rn(k.w[0], leaky(fmaf(v.w, sc.w, sh.w), slope));
+      }
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        const float4 v = ld4(y2 + ((size_t)b * r3 + k.idx[j]) * cp + c4 * 4);
+        acc.x = fmaf(k.w[j], leaky(fmaf(v.x, sc.x, sh.x), slope), acc.x);
+        acc.y = fmaf(k.w[j], leaky(fmaf(v.y, sc.y, sh.y), slope), acc.y);
+        acc.z = fmaf(k.w[j], leaky(fmaf(v.z, sc.z, sh.z), slope), acc.z);
+        acc.w = fmaf(k.w[j], leaky(fmaf(v.w, sc.w, sh.w), slope), acc.w);
+      }
+      const float4 pv = ld4(prow + c4 * 4);
+      const float4 ps = ld4(bnp.scale + c4 * 4), ph = ld4(bnp.shift + c4 * 4);
+      tile[(c4 * 4 + 0) * 33 + pt] = acc.x + fmaxf(fmaf(pv.x, ps.x, ph.x), 0.0f);
+      tile[(c4 * 4 + 1) * 33 + pt] = acc.y + fmaxf(fmaf(pv.y, ps.y, ph.y), 0.0f);
+      tile[(c4 * 4 + 2) * 33 + pt] = acc.z + fmaxf(fmaf(pv.z, ps.z, ph.z), 0.0f);
+      tile[(c4 * 4 + 3) * 33 + pt] = acc.w + fmaxf(fmaf(pv.w, ps.w, ph.w), 0.0f);
+    }
+  }
+  __syncthreads();
+  const int i = i0 + lane;
+  if (i < n)
+    for (int ch = warp; ch < c; ch += PT_WARPS) out[((size_t)b * c + ch) * n + i] = tile[ch * 33 + lane];
+}
+
+int launch_devox_fused(int b, int n, int c, int cp, int r, float slope, const float *norm_coords, const float *y2,
+                       BnCoef bn2, const float *p, BnCoef bnp, float *out, cudaStream_t s) {
+  const size_t smem = (size_t)cp * 33 * sizeof(float);
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(devox_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(devox_fused_kernel, dim3(ceil_div(n, PT_TILE), b), 256, smem, s, n, c, cp, r, slope, norm_coords, y2, bn2,
+             p, bnp, out);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// backward stage 1 over points
+// smem: gtile[cp][33] + red[PT_WARPS][4][cp]
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, int r, float slope,
+                                                         const float *__restrict__ gout,
+                                                         const float *__restrict__ nc,
+                                                         const float *__restrict__ y2, BnCoef bn2,
+                                                         const float *__restrict__ p, BnCoef bnp,
+                                                         float *__restrict__ ga_cl, float *__restrict__ d2,
+                                                         float *__restrict__ partials) {
+  extern __shared__ float sm[];
+  float *gtile = sm;                 // [cp][33]
+  float *red = sm + (size_t)cp * 33;  // [PT_WARPS][4][cp]
+  const int b = blockIdx.y, i0 = blockIdx.x * PT_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r3 = r * r * r, cp4 = cp >> 2;
+  {
+    const int i = i0 + lane;
+    for (int ch = warp; ch < cp; ch += PT_WARPS)
+      gtile[ch * 33 + lane] = (ch < c && i < n) ? gout[((size_t)b * c + ch) * n + i] : 0.0f;
+  }
+  __syncthreads();
+  const float *co = nc + (size_t)b * 3 * n;
+  for (int c4 = lane; c4 < cp4; c4 += 32) {
+    const float4 sc2 = ld4(bn2.scale + c4 * 4), sh2 = ld4(bn2.shift + c4 * 4);
+    const float4 mu2 = ld4(bn2.mean + c4 * 4), is2 = ld4(bn2.invstd + c4 * 4);
+    const float4 scp = ld4(bnp.scale + c4 * 4), shp = ld4(bnp.shift + c4 * 4);
+    const float4 mup = ld4(bnp.mean + c4 * 4), isp = ld4(bnp.invstd + c4 * 4);
+    float4 S1 = make_float4(0.f, 0.f, 0.f, 0.f), S2 = S1, T1 = S1, T2 = S1;
+    for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
+      const int pt = warp * (PT_TILE / PT_WARPS) + q;
+      const int i = i0 + pt;
+      if (i >= n) break;
+      const float4 g = make_float4(gtile[(c4 * 4 + 0) * 33 + pt], gtile[(c4 * 4 + 1) * 33 + pt],
+                                   gtile[(c4 * 4 + 2) * 33 + pt], gtile[(c4 * 4 + 3) * 33 + pt]);
+      // ---- point branch: ReLU mask, BN1d reductions
+      const size_t prow = ((size_t)b * n + i) * cp + c4 * 4;
+      const float4 pv = ld4(p + prow);
+      float4 ga;
+      ga.x = fmaf(pv.x, scp.x, shp.x) > 0.f ? g.x : 0.f;
+      ga.y = fmaf(pv.y, scp.y, shp.y) > 0.f ? g.y : 0.f;
+      ga.z = fmaf(pv.z, scp.z, shp.z) > 0.f ? g.z : 0.f;
+      ga.w = fmaf(pv.w, scp.w, shp.w) > 0.f ? g.w : 0.f;
+      st4(ga_cl + prow, ga);
+      S1.x += ga.x; S1.y += ga.y; S1.z += ga.z; S1.w += ga.w;
+      S2.x = fmaf(ga.x, (pv.x - mup.x) * isp.x, S2.x);
+      S2.y = fmaf(ga.y, (pv.y - mup.y) * isp.y, S2.y);
+      S2.z = fmaf(ga.z, (pv.z - mup.z) * isp.z, S2.z);
+      S2.w = fmaf(ga.w, (pv.w - mup.w) * isp.w, S2.w);
+      // ---- voxel branch: trilinear scatter of leaky'(.) * w * g, BN3d reductions
+      Corners k;
+      corner_setup(co[i], co[i + n], co[i + 2 * n], r, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const size_t vrow = ((size_t)b * r3 + k.idx[j]) * cp + c4 * 4;
+        const float4 v = ld4(y2 + vrow);
+        float4 gk;
+        gk.x = k.w[j] * g.x * (fmaf(v.x, sc2.x, sh2.x) > 0.f ? 1.0f : slope);
+        gk.y = k.w[j] * g.y * (fmaf(v.y, sc2.y, sh2.y) > 0.f ? 1.0f : slope);
+        gk.z = k.w[j] * g.z * (fmaf(v.z, sc2.z, sh2.z) > 0.f ? 1.0f : slope);
+        gk.w = k.w[j] * g.w * (fmaf(v.w, sc2.w, sh2.w) > 0.f ? 1.0f : slope);
+        T1.x += gk.x; T1.y += gk.y; T1.z += gk.z; T1.w += gk.w;
+        T2.x = fmaf(gk.x, (v.x - mu2.x) * is2.x, T2.x);
+        T2.y = fmaf(gk.y, (v.y - mu2.y) * is2.y, T2.y);
+        T2.z = fmaf(gk.z, (v.z - mu2.z) * is2.z, T2.z);
+        T2.w = fmaf(gk.w, (v.w - mu2.w) * is2.w, T2.w);
+        if (k.w[j] != 0.0f) red_add4(d2 + vrow, gk);
+      }
+    }
+    st4(red + ((size_t)warp * 4 + 0) * cp + c4 * 4, S1);
+    st4(red + ((size_t)warp * 4 + 1) * cp + c4 * 4, S2);
+    st4(red + ((size_t)warp * 4 + 2) * cp + c4 * 4, T1);
+    st4(red + ((size_t)warp * 4 + 3) * cp + c4 * 4, T2);
+  }
+  __syncthreads();
+  const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int t = threadIdx.x; t < 4 * cp; t += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < PT_WARPS; ++w) s += red[(size_t)w * 4 * cp + t];
+    partials[blk * 4 * cp + t] = s;
+  }
+}
+
+int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const float *grad_out,
+                      const float *norm_coords, const float *y2, BnCoef bn2, const float *p, BnCoef bnp, float *ga_cl,
+                      float *d2, float *partials, int *nblocks, cudaStream_t s) {
+  const size_t smem = ((size_t)cp * 33 + (size_t)PT_WARPS * 4 * cp) * sizeof(float);
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(bwd_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid(ceil_div(n, PT_TILE), b);
+  *nblocks = (int)(grid.x * grid.y);
+  PVB_LAUNCH(bwd_points_kernel, grid, 256, smem, s, n, c, cp, r, slope, grad_out, norm_coords, y2, bn2, p, bnp, ga_cl,
+             d2, partials);
+  return 0;
+}
+
+int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s) {
+  PVB_LAUNCH(reduce_partials_kernel, ceil_div(ncols, 256), 256, 0, s, nblocks, ncols, partials, sums);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// BatchNorm backward, input gradient:  dx = scale * (g' - mean(g') - xhat * mean(g' * xhat)),
+// g' = g (use_mask = 0) or leaky'(bn(y)) * g (use_mask = 1); s1/s2 are the RAW column sums of g' and
+// g'*xhat, inv_count = 1/rows.  Also emits column sums of dx (the conv-bias gradient).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) bn_bwd_apply_kernel(long long rows, int cp, int use_mask, float slope,
+                                                                   float inv_count, const float *__restrict__ g,
+                                                                   const float *__restrict__ y, BnCoef coef,
+                                                                   const float *__restrict__ s1,
+                                                                   const float *__restrict__ s2,
+                                                                   float *__restrict__ out,
+                                                                   float *__restrict__ out_lo,
+                                                                   float *__restrict__ partials) {
+  column_reduce<1>(rows, cp, partials, [&](long long r, int c4, float4 *acc) {
+    const size_t o = (size_t)r * cp + c4 * 4;
+    const float4 gv = ldg_stream4(g + o), yv = ldg_stream4(y + o);
+    const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
+    const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
+    const float4 a1 = ld4(s1 + c4 * 4), a2 = ld4(s2 + c4 * 4);
+    float4 d;
+#define PVB_BWD1(f)                                                                                   \
+  {                                                                                                   \
+    float gg = gv.f;                                                                                  \
+    if (use_mask) gg *= (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope);                                \
+    const float xh = (yv.f - mu.f) * is.f;                                                            \
+    d.f = sc.f * (gg - a1.f * inv_count - xh * (a2.f * inv_count));                                   \
+    acc[0].f += d.f;                                                                                  \
+  }
+    PVB_BWD1(x) PVB_BWD1(y) PVB_BWD1(z) PVB_BWD1(w)
+#undef PVB_BWD1
+    st4(out + o, d);
+    if (out_lo) st4(out_lo + o, tf32_lo4(d));
+  });
+}
+
+int launch_bn_bwd_apply(long long rows, int cp, int use_mask, float slope, const float *g, const float *y,
+                        BnCoef coef, const float *s1, const float *s2, float *out, float *out_lo,
+                        float *colsum_partials, int *nblocks, cudaStream_t s) {
+  PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
+  const int rl = RED_THREADS / (cp / 4);
+  const int gsz = grid_for(rows, rl * 8, RED_MAX_BLOCKS);
+  *nblocks = gsz;
+  PVB_LAUNCH(bn_bwd_apply_kernel, gsz, RED_THREADS, 0, s, rows, cp, use_mask, slope, (float)(1.0 / (double)rows), g, y,
+             coef, s1, s2, out, out_lo, colsum_partials);
+  return 0;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) bn_bwd_reduce_kernel(long long rows, int cp, float slope,
+                                                                    const float *__restrict__ g,
+                                                                    const float *__restrict__ y, BnCoef coef,
+                                                                    float *__restrict__ partials) {
+  column_reduce<2>(rows, cp, partials, [&](long long r, int c4, float4 *acc) {
+    const size_t o = (size_t)r * cp + c4 * 4;
+    const float4 gv = ld4(g + o), yv = ld4(y + o);
+    const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
+    const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
+#define PVB_RED1(f)                                                            \
+  {                                                                            \
+    const float gg = gv.f * (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope);     \
+    acc[0].f += gg;                                                            \
+    acc[1].f = fmaf(gg, (yv.f - mu.f) * is.f, acc[1].f);                       \
+  }
+    PVB_RED1(x) PVB_RED1(y) PVB_RED1(z) PVB_RED1(w)
+#undef PVB_RED1
+  });
+}
+
+int launch_bn_bwd_reduce(long long rows, int cp, float slope, const float *g, const float *y, BnCoef coef,
+                         float *partials, int *nblocks, cudaStream_t s) {
+  PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
+  const int rl = RED_THREADS / (cp / 4);
+  const int gsz = grid_for(rows, rl * 8, RED_MAX_BLOCKS);
+  *nblocks = gsz;
+  PVB_LAUNCH(bn_bwd_reduce_kernel, gsz, RED_THREADS, 0, s, rows, cp, slope, g, y, coef, partials);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// grad_features[b,c,i] = gG0[b*R^3 + ind_i, c] / cnt + gFpt[b*N+i, c]      (vox.cu:86-110 + add)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwd_final_kernel(int n, int c, int cp, int r3, const int *__restrict__ ind,
+                                                        const int *__restrict__ cnt,
+                                                        const float *__restrict__ gg0,
+                                                        const float *__restrict__ gfpt,
+                                                        float *__restrict__ gfeat) {
+  extern __shared__ float tile[];  // [cp][33]
+  const int b = blockIdx.y, i0 = blockIdx.x * PT_TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cp4 = cp >> 2;
+  for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
+    const int pt = warp * (PT_TILE / PT_WARPS) + q;
+    const int i = i0 + pt;
+    if (i >= n) break;
+    const int pos = ind[(size_t)b * n + i];
+    const int cur = cnt[(size_t)b * r3 + pos];
+    const float inv = cur > 0 ? (float)(1.0 / (double)(float)cur) : 0.0f;
+    for (int c4 = lane; c4 < cp4; c4 += 32) {
+      const float4 gv = ld4(gg0 + ((size_t)b * r3 + pos) * cp + c4 * 4);
+      const float4 pv = ld4(gfpt + ((size_t)b * n + i) * cp + c4 * 4);
+      tile[(c4 * 4 + 0) * 33 + pt] = fmaf(gv.x, inv, pv.x);
+      tile[(c4 * 4 + 1) * 33 + pt] = fmaf(gv.y, inv, pv.y);
+      tile[(c4 * 4 + 2) * 33 + pt] = fmaf(gv.z, inv, pv.z);
+      tile[(c4 * 4 + 3) * 33 + pt] = fmaf(gv.w, inv, pv.w);
+    }
+  }
+  __syncthreads();
+  const int i = i0 + lane;
+  if (i < n)
+    for (int ch = warp; ch < c; ch += PT_WARPS) gfeat[((size_t)b * c + ch) * n + i] = tile[ch * 33 + lane];
+}
+
+int launch_bwd_final(int b, int n, int c, int cp, int r3, const int *ind, const int *cnt, const float *gg0,
+                     const float *gfpt, float *grad_features, cudaStream_t s) {
+  const size_t smem = (size_t)cp * 33 * sizeof(float);
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(bwd_final_kernel, dim3(ceil_div(n, PT_TILE), b), 256, smem, s, n, c, cp, r3, ind, cnt, gg0, gfpt,
+             grad_features);
+  return 0;
+}
+
+int launch_memset_f32(float *p, long long n, cudaStream_t s) {
+  PVB_CUDA(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, s));
+  return 0;
+}
+
+}  // namespace pvb

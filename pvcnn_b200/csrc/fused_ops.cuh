@@ -1,0 +1,71 @@
+// fused_ops.cuh -- launchers of the channels-last kernels that surround the tcgen05 GEMMs in the fused
+// PVConv pipeline (pvconv_pipeline.cu).  All tensors are fp32, channels-last ("cl"): a grid is
+// [B*R^3, C] and a point set is [B*N, C] with C padded to a multiple of 4 (pad columns are zero).
+#pragma once
+#include "common.cuh"
+
+namespace pvb {
+
+// per-channel BatchNorm coefficients living in device memory
+struct BnCoef {
+  float *mean;     // [C] batch (or running) mean
+  float *invstd;   // [C] 1/sqrt(var + eps)
+  float *scale;    // [C] gamma * invstd
+  float *shift;    // [C] beta - mean * scale
+};
+
+// [B,C,N] -> [B*N, Cp] (+ lo = x - trunc_tf32(x)); pad columns zeroed
+int launch_points_to_cl(int b, int c, int n, int cp, const float *x, float *xcl, float *xcl_lo, cudaStream_t s);
+
+// voxel index / count (int32, reference semantics) from integer coords [B,3,N]
+int launch_vox_index_count(int b, int n, int r, const int *coords, int *ind, int *cnt, cudaStream_t s);
+
+// scatter-mean of point rows into the (pre-zeroed) grid [B*R^3, Cp]; warp-aggregated per voxel
+int launch_voxelize_cl(int b, int n, int r3, int cp, const int *ind, const int *cnt, const float *xcl, float *grid,
+                       cudaStream_t s);
+// lo = g - trunc(g) at occupied voxels only (grid_lo pre-zeroed)
+int launch_grid_lo_at_points(int b, int n, int r3, int cp, const int *ind, const float *grid, float *grid_lo,
+                             cudaStream_t s);
+
+// per-channel sum / sum of squares over rows -> partials[blocks][2][cp]; returns #blocks used via *nblocks
+int launch_bn_stats(long long rows, int cp, const float *y, float *partials, int *nblocks, cudaStream_t s);
+// reduce partials (fp64), produce mean/invstd/scale/shift, update running stats (momentum, unbiased var)
+int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
+                       const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
+                       cudaStream_t s);
+// eval mode: coefficients from running statistics
+int launch_bn_coef_from_running(int c, float eps, const float *gamma, const float *beta, const float *running_mean,
+                                const float *running_var, BnCoef coef, cudaStream_t s);
+
+// z = leaky(y*scale+shift) (+ z_lo)
+int launch_bn_apply_leaky(long long rows, int cp, float slope, const float *y, BnCoef coef, float *z, float *z_lo,
+                          cudaStream_t s);
+
+// out[b,c,i] = sum_k w_k * leaky(bn2(Y2[b, idx_k, c])) + relu(bnp(P[b*N+i, c]))
+int launch_devox_fused(int b, int n, int c, int cp, int r, float slope, const float *norm_coords, const float *y2,
+                       BnCoef bn2, const float *p, BnCoef bnp, float *out, cudaStream_t s);
+
+// ---- backward ----
+// stage 1 over points: relu-masked point-branch grad (ga_cl), BN reductions of both branches, and the
+// scatter of the voxel-branch gradient (already multiplied by leaky') into d2 (pre-zeroed)
+int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const float *grad_out,
+                      const float *norm_coords, const float *y2, BnCoef bn2, const float *p, BnCoef bnp,
+                      float *ga_cl, float *d2, float *partials /*[blocks][4][cp]*/, int *nblocks, cudaStream_t s);
+// sums[j] = sum over blocks (fp64) of partials[block][j], j < ncols
+int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s);
+// out = scale * (mask(y)*g - s1/rows - xhat(y)*s2/rows) (+ out_lo); s1/s2 = RAW column sums of g' and
+// g'*xhat; mask = leaky'(bn(y)) when use_mask; also emits column sums of out (conv-bias gradient)
+int launch_bn_bwd_apply(long long rows, int cp, int use_mask, float slope, const float *g, const float *y, BnCoef coef,
+                        const float *s1, const float *s2, float *out, float *out_lo, float *colsum_partials,
+                        int *nblocks, cudaStream_t s);
+// dense reductions for BN1 backward: U1 = sum leaky'(bn(y))*g, U2 = sum leaky'(..)*g*xhat
+int launch_bn_bwd_reduce(long long rows, int cp, float slope, const float *g, const float *y, BnCoef coef,
+                         float *partials /*[blocks][2][cp]*/, int *nblocks, cudaStream_t s);
+// grad_features[b,c,i] = gG0[b*R^3 + ind_i, c] / cnt + gFpt[b*N+i, c]
+int launch_bwd_final(int b, int n, int c, int cp, int r3, const int *ind, const int *cnt, const float *gg0,
+                     const float *gfpt, float *grad_features, cudaStream_t s);
+
+// small helpers
+int launch_memset_f32(float *p, long long n, cudaStream_t s);
+
+}  // namespace pvb

@@ -1,0 +1,203 @@
+// pvconv_pipeline.cu -- the fused PVConv block (forward + backward) as two C-ABI calls.
+// Orchestrates the channels-last kernels of fused_ops.cu around the tcgen05 GEMMs of
+// conv_igemm.cu / conv_wgrad.cu.  See include/pvcnn_b200.h for the contract and DESIGN.md for the
+// dataflow; reference: modules/pvconv.py:33-39 (forward wiring) and torch autograd (backward).
+#include "fused_ops.cuh"
+
+namespace pvb {
+int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                 int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                 int npass, cudaStream_t stream);
+int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
+                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s);
+
+static inline int pad4(int x) { return (x + 3) / 4 * 4; }
+static inline int ld32(int x) { return (x + 31) / 32 * 32; }
+
+struct WPrep {  // offsets (floats) into ws->wprep; each entry holds hi then lo
+  long long w1f, w2f, wpf, w1d, w2d, wpd, total;
+  long long n1f, n2f, npf, n1d, n2d, npd;  // floats of ONE copy (hi)
+};
+static WPrep wprep_layout(const pvcnn_pvconv_desc *d) {
+  WPrep w{};
+  w.n1f = 27LL * d->cout * ld32(d->cin);
+  w.n2f = 27LL * d->cout * ld32(d->cout);
+  w.npf = 1LL * d->cout * ld32(d->cin);
+  w.n1d = 27LL * d->cin * ld32(d->cout);
+  w.n2d = 27LL * d->cout * ld32(d->cout);
+  w.npd = 1LL * d->cin * ld32(d->cout);
+  long long o = 0;
+  w.w1f = o; o += 2 * w.n1f;
+  w.w2f = o; o += 2 * w.n2f;
+  w.wpf = o; o += 2 * w.npf;
+  w.w1d = o; o += 2 * w.n1d;
+  w.w2d = o; o += 2 * w.n2d;
+  w.wpd = o; o += 2 * w.npd;
+  w.total = o;
+  return w;
+}
+
+static BnCoef coef_at(float *base, int idx, int co) {
+  float *p = base + (size_t)idx * 4 * co;
+  return BnCoef{p, p + co, p + 2 * co, p + 3 * co};
+}
+}  // namespace pvb
+
+using namespace pvb;
+
+extern "C" int pvcnn_conv_weight_prep(int cout, int cin, int ntaps, int mode, int ld, const float *w, float *w_hi,
+                                      float *w_lo, void *stream);
+
+#define PVB_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+extern "C" {
+
+long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d) { return wprep_layout(d).total; }
+
+long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d) {
+  const long long co = pad4(d->cout > d->cin ? d->cout : d->cin);
+  const long long blocks_pts = (long long)d->b * ((d->n + 31) / 32);
+  const long long blocks = blocks_pts > kNumSMs * 4 ? blocks_pts : kNumSMs * 4;
+  return blocks * 4 * co;
+}
+
+int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, const float *coords,
+                         const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws, float *out, void *stream) {
+  PVB_CHECK_ARG(d && features && coords && prm && ws && out);
+  PVB_CHECK_ARG(d->b > 0 && d->n > 0 && d->cin > 0 && d->cout > 0 && d->r > 1 && (d->npass == 1 || d->npass == 3));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int b = d->b, n = d->n, r = d->r, r3 = r * r * r;
+  const int ci = pad4(d->cin), co = pad4(d->cout);
+  const long long Mv = (long long)b * r3, Mp = (long long)b * n;
+  const bool lo = d->npass > 1;
+  const WPrep W = wprep_layout(d);
+  float *wp = ws->wprep;
+  int nblk = 0;
+
+  // 1. coordinates -> voxel indices                               (modules/voxelization.py:17-24, vox.cu:18-34)
+  PVB_TRY(pvcnn_voxelize_coords(b, n, r, d->normalize, d->eps, coords, ws->nc, ws->vc, stream));
+  PVB_TRY(launch_vox_index_count(b, n, r, ws->vc, ws->ind, ws->cnt, s));
+  // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
+  PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
+  PVB_TRY(launch_memset_f32(ws->g0, Mv * ci, s));
+  PVB_TRY(launch_voxelize_cl(b, n, r3, ci, ws->ind, ws->cnt, ws->fcl, ws->g0, s));
+  if (lo) {
+    PVB_TRY(launch_memset_f32(ws->g0_lo, Mv * ci, s));
+    PVB_TRY(launch_grid_lo_at_points(b, n, r3, ci, ws->ind, ws->g0, ws->g0_lo, s));
+  }
+  // 3. weights -> GEMM operands
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 27, 0, ld32(d->cin), prm->w1, wp + W.w1f, wp + W.w1f + W.n1f, stream));
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cout, 27, 0, ld32(d->cout), prm->w2, wp + W.w2f, wp + W.w2f + W.n2f, stream));
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 1, 0, ld32(d->cin), prm->wp, wp + W.wpf, wp + W.wpf + W.npf, stream));
+
+  BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
+  // 4. conv1 -> BN1 -> LeakyReLU                                   (modules/pvconv.py:21-23)
+  PVB_TRY(igemm_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, wp + W.w1f, wp + W.w1f + W.n1f,
+                       ld32(d->cin), prm->b1, ws->y1, co, d->npass, s));
+  if (d->training) {
+    PVB_TRY(launch_bn_stats(Mv, co, ws->y1, ws->partials, &nblk, s));
+    PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g1, prm->be1,
+                               prm->rm1, prm->rv1, bn1, s));
+  } else {
+    PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g1, prm->be1, prm->rm1, prm->rv1, bn1, s));
+  }
+  PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, lo ? ws->z1_lo : nullptr, s));
+  // 5. conv2 -> BN2 statistics (BN2-apply + LeakyReLU are folded into the devoxelize gather)
+  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, wp + W.w2f, wp + W.w2f + W.n2f,
+                       ld32(d->cout), prm->b2, ws->y2, co, d->npass, s));
+  if (d->training) {
+    PVB_TRY(launch_bn_stats(Mv, co, ws->y2, ws->partials, &nblk, s));
+    PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g2, prm->be2,
+                               prm->rm2, prm->rv2, bn2, s));
+  } else {
+    PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g2, prm->be2, prm->rm2, prm->rv2, bn2, s));
+  }
+  // 6. point branch: 1x1 conv as a GEMM over all points             (modules/shared_mlp.py:10-12)
+  PVB_TRY(igemm_launch(1, 1, 1, (int)Mp, d->cin, d->cout, 1, ws->fcl, ws->fcl_lo, ci, wp + W.wpf, wp + W.wpf + W.npf,
+                       ld32(d->cin), prm->bp, ws->p, co, d->npass, s));
+  if (d->training) {
+    PVB_TRY(launch_bn_stats(Mp, co, ws->p, ws->partials, &nblk, s));
+    PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mp, d->bn_eps_pt, d->momentum, ws->partials, prm->gp, prm->bep,
+                               prm->rmp, prm->rvp, bnp, s));
+  } else {
+    PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_pt, prm->gp, prm->bep, prm->rmp, prm->rvp, bnp, s));
+  }
+  // 7. BN2-apply + LeakyReLU + trilinear devoxelize + BN1d-apply + ReLU + add + transpose
+  PVB_TRY(launch_devox_fused(b, n, d->cout, co, r, d->slope, ws->nc, ws->y2, bn2, ws->p, bnp, out, s));
+  return 0;
+}
+
+int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, const pvcnn_pvconv_params *prm,
+                          const pvcnn_pvconv_ws *ws, float *grad_features, const pvcnn_pvconv_grads *gr,
+                          void *stream) {
+  PVB_CHECK_ARG(d && grad_out && prm && ws && grad_features && gr && d->training);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int b = d->b, n = d->n, r = d->r, r3 = r * r * r;
+  const int ci = pad4(d->cin), co = pad4(d->cout);
+  const long long Mv = (long long)b * r3, Mp = (long long)b * n;
+  const bool lo = d->npass > 1;
+  const WPrep W = wprep_layout(d);
+  float *wp = ws->wprep;
+  BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
+  float *S = ws->sums;  // [16][co]: 0 S1, 1 S2, 2 T1, 3 T2, 4 U1, 5 U2, 6.. column sums
+  int nblk = 0;
+  const size_t cb = sizeof(float) * (size_t)d->cout;
+
+  // 1. per-point stage: point-branch ReLU mask + reductions; voxel-branch scatter (x leaky') + reductions
+  PVB_TRY(launch_memset_f32(ws->d2, Mv * co, s));
+  PVB_TRY(launch_bwd_points(b, n, d->cout, co, r, d->slope, grad_out, ws->nc, ws->y2, bn2, ws->p, bnp, ws->ga, ws->d2,
+                            ws->partials, &nblk, s));
+  PVB_TRY(launch_reduce_partials(nblk, 4 * co, ws->partials, S, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->bep, S + 0 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->gp, S + 1 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->be2, S + 2 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->g2, S + 3 * co, cb, cudaMemcpyDeviceToDevice, s));
+  // 2. BN1d / BN3d(2) input gradients (+ conv-bias gradients as column sums)
+  PVB_TRY(launch_bn_bwd_apply(Mp, co, 0, d->slope, ws->ga, ws->p, bnp, S + 0 * co, S + 1 * co, ws->gpp,
+                              lo ? ws->gpp_lo : nullptr, ws->partials, &nblk, s));
+  PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 6 * co, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->bp, S + 6 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_TRY(launch_bn_bwd_apply(Mv, co, 0, d->slope, ws->d2, ws->y2, bn2, S + 2 * co, S + 3 * co, ws->gy2,
+                              lo ? ws->gy2_lo : nullptr, ws->partials, &nblk, s));
+  PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 7 * co, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->b2, S + 7 * co, cb, cudaMemcpyDeviceToDevice, s));
+  // 3. data-gradient weights
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 27, 1, ld32(d->cout), prm->w1, wp + W.w1d, wp + W.w1d + W.n1d, stream));
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cout, 27, 1, ld32(d->cout), prm->w2, wp + W.w2d, wp + W.w2d + W.n2d, stream));
+  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 1, 1, ld32(d->cout), prm->wp, wp + W.wpd, wp + W.wpd + W.npd, stream));
+  // 4. point branch: dgrad + wgrad
+  PVB_TRY(igemm_launch(1, 1, 1, (int)Mp, d->cout, d->cin, 1, ws->gpp, ws->gpp_lo, co, wp + W.wpd, wp + W.wpd + W.npd,
+                       ld32(d->cout), nullptr, ws->gfpt, ci, d->npass, s));
+  PVB_TRY(wgrad_launch(1, 1, 1, (int)Mp, d->cin, d->cout, 1, ws->fcl, ws->fcl_lo, ci, ws->gpp, ws->gpp_lo, co, gr->wp,
+                       d->npass, s));
+  // 5. conv2: wgrad (needs z1, gy2) then dgrad into the d2 buffer (d2 was consumed in step 2)
+  PVB_TRY(wgrad_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, ws->gy2, ws->gy2_lo, co, gr->w2,
+                       d->npass, s));
+  float *gz1 = ws->d2;
+  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->gy2, ws->gy2_lo, co, wp + W.w2d, wp + W.w2d + W.n2d,
+                       ld32(d->cout), nullptr, gz1, co, d->npass, s));
+  // 6. LeakyReLU' + BN1 backward
+  PVB_TRY(launch_bn_bwd_reduce(Mv, co, d->slope, gz1, ws->y1, bn1, ws->partials, &nblk, s));
+  PVB_TRY(launch_reduce_partials(nblk, 2 * co, ws->partials, S + 4 * co, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->be1, S + 4 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->g1, S + 5 * co, cb, cudaMemcpyDeviceToDevice, s));
+  PVB_TRY(launch_bn_bwd_apply(Mv, co, 1, d->slope, gz1, ws->y1, bn1, S + 4 * co, S + 5 * co, ws->gy1,
+                              lo ? ws->gy1_lo : nullptr, ws->partials, &nblk, s));
+  PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 8 * co, s));
+  PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
+  // 7. conv1: wgrad, dgrad (into the d2 buffer again: gz1 is dead)
+  PVB_TRY(wgrad_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, ws->gy1, ws->gy1_lo, co, gr->w1,
+                       d->npass, s));
+  float *gg0 = ws->d2;
+  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cin, 27, ws->gy1, ws->gy1_lo, co, wp + W.w1d, wp + W.w1d + W.n1d,
+                       ld32(d->cout), nullptr, gg0, ci, d->npass, s));
+  // 8. avg_voxelize backward + point-branch gradient              (vox.cu:86-110)
+  PVB_TRY(launch_bwd_final(b, n, d->cin, ci, r3, ws->ind, ws->cnt, gg0, ws->gfpt, grad_features, s));
+  return 0;
+}
+
+}  // extern "C"

@@ -45,3 +45,13 @@ def igemm_conv(a_hi, a_lo, w_hi, w_lo, bias, npass=3, cout=None):
     _lib.call("pvcnn_igemm_conv", nb, sx, sy, sz, c, cout, ntaps, a_hi, a_lo if npass > 1 else None, c, w_hi,
               w_lo if npass > 1 else None, ldw, bias, out, ldo, npass)
     return out
+
+
+def conv_wgrad(x_hi, x_lo, g_hi, g_lo, cin, cout, ntaps, npass=3):
+    """x: layer input [B,X,Y,Z,Cx], g: output gradient [B,X,Y,Z,Cg] -> dW [cout, cin, ntaps] (torch layout)."""
+    nb, sx, sy, sz, ldx = x_hi.shape
+    ldg = g_hi.shape[-1]
+    dw = torch.empty((cout, cin, ntaps), dtype=torch.float32, device=x_hi.device)
+    _lib.call("pvcnn_conv_wgrad", nb, sx, sy, sz, cin, cout, ntaps, x_hi, x_lo if npass > 1 else None, ldx, g_hi,
+              g_lo if npass > 1 else None, ldg, dw, npass)
+    return dw

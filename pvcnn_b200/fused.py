@@ -1,0 +1,203 @@
+"""Host side of the fused PVConv block: one C-ABI call forward (pvcnn_pvconv_forward) and one backward
+(pvcnn_pvconv_backward).  torch is used for device memory, streams and autograd plumbing only.
+
+Reference being replaced: modules/pvconv.py:33-39 (forward wiring) + torch autograd of
+modules/voxelization.py, modules/functional/{voxelization,devoxelization}.py, nn.Conv3d / nn.BatchNorm3d /
+nn.LeakyReLU / nn.Conv1d / nn.BatchNorm1d / nn.ReLU.
+"""
+import ctypes
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+_F = ctypes.POINTER(ctypes.c_float)
+_I = ctypes.POINTER(ctypes.c_int)
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [("b", ctypes.c_int), ("n", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int),
+                ("r", ctypes.c_int), ("normalize", ctypes.c_int), ("eps", ctypes.c_float),
+                ("training", ctypes.c_int), ("npass", ctypes.c_int), ("bn_eps_vox", ctypes.c_float),
+                ("bn_eps_pt", ctypes.c_float), ("momentum", ctypes.c_float), ("slope", ctypes.c_float)]
+
+
+_PARAM_FIELDS = ["w1", "b1", "g1", "be1", "rm1", "rv1", "w2", "b2", "g2", "be2", "rm2", "rv2",
+                 "wp", "bp", "gp", "bep", "rmp", "rvp"]
+_GRAD_FIELDS = ["w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "wp", "bp", "gp", "bep"]
+_WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("fcl_lo", _F), ("g0", _F),
+              ("g0_lo", _F), ("y1", _F), ("z1", _F), ("z1_lo", _F), ("y2", _F), ("p", _F), ("coef", _F),
+              ("wprep", _F), ("partials", _F), ("sums", _F), ("ga", _F), ("gpp", _F), ("gpp_lo", _F),
+              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [(k, _F) for k in _PARAM_FIELDS]
+
+
+class Grads(ctypes.Structure):
+    _fields_ = [(k, _F) for k in _GRAD_FIELDS]
+
+
+class Workspace(ctypes.Structure):
+    _fields_ = _WS_FIELDS
+
+
+def _ptr(t, typ=_F):
+    return ctypes.cast(ctypes.c_void_p(0 if t is None else t.data_ptr()), typ)
+
+
+def precision_passes():
+    """PVCNN_B200_PRECISION=fp32 (default, 3xTF32, parity mode) | tf32 (single pass, like the
+    reference's cuDNN default)."""
+    return 1 if os.environ.get("PVCNN_B200_PRECISION", "fp32").lower() == "tf32" else 3
+
+
+def _pad4(x):
+    return (x + 3) // 4 * 4
+
+
+_SCRATCH = {}
+
+
+def _scratch(name, numel, device, dtype=torch.float32):
+    """Backward-only scratch is shared by every PVConv block on the device (grown on demand)."""
+    key = (name, str(device), dtype)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < numel:
+        t = torch.empty(int(numel), dtype=dtype, device=device)
+        _SCRATCH[key] = t
+    return t
+
+
+class _Plan:
+    """Buffers of one forward pass (kept alive for the backward)."""
+
+    def __init__(self, desc, device, need_backward):
+        lib = _lib.load()
+        lib.pvcnn_pvconv_wprep_floats.restype = ctypes.c_longlong
+        lib.pvcnn_pvconv_partials_floats.restype = ctypes.c_longlong
+        b, n, r = desc.b, desc.n, desc.r
+        ci, co = _pad4(desc.cin), _pad4(desc.cout)
+        mv, mp = b * r ** 3, b * n
+        lo = desc.npass > 1
+        f = lambda numel: torch.empty(int(numel), dtype=torch.float32, device=device)
+        i = lambda numel: torch.empty(int(numel), dtype=torch.int32, device=device)
+        alloc = {}
+        saved = dict(nc=b * 3 * n, fcl=mp * ci, g0=mv * ci, y1=mv * co, z1=mv * co, y2=mv * co, p=mp * co,
+                     coef=12 * co)
+        if lo:
+            saved.update(fcl_lo=mp * ci, g0_lo=mv * ci, z1_lo=mv * co)
+        for k, v in saved.items():
+            # activations needed by the backward belong to this call; in inference they are scratch
+            alloc[k] = f(v) if need_backward else _scratch("fwd_" + k, v, device)
+        alloc["nc"] = f(b * 3 * n)
+        alloc["vc"] = _scratch("vc", b * 3 * n, device, torch.int32)
+        alloc["ind"] = i(b * n) if need_backward else _scratch("ind", b * n, device, torch.int32)
+        alloc["cnt"] = i(b * r ** 3) if need_backward else _scratch("cnt", b * r ** 3, device, torch.int32)
+        alloc["wprep"] = _scratch("wprep", lib.pvcnn_pvconv_wprep_floats(ctypes.byref(desc)), device)
+        alloc["partials"] = _scratch("partials", lib.pvcnn_pvconv_partials_floats(ctypes.byref(desc)), device)
+        alloc["sums"] = _scratch("sums", 16 * max(ci, co), device)
+        self.t = alloc
+        self.desc = desc
+        self.device = device
+
+    def add_backward_scratch(self):
+        d = self.desc
+        ci, co = _pad4(d.cin), _pad4(d.cout)
+        mv, mp = d.b * d.r ** 3, d.b * d.n
+        lo = d.npass > 1
+        sizes = dict(ga=mp * co, gpp=mp * co, gfpt=mp * ci, d2=mv * max(ci, co), gy2=mv * co, gy1=mv * co)
+        if lo:
+            sizes.update(gpp_lo=mp * co, gy2_lo=mv * co, gy1_lo=mv * co)
+        for k, v in sizes.items():
+            self.t[k] = _scratch("bwd_" + k, v, self.device)
+
+    def struct(self):
+        ws = Workspace()
+        for name, typ in _WS_FIELDS:
+            setattr(ws, name, _ptr(self.t.get(name), typ))
+        return ws
+
+
+def _module_tensors(m):
+    c1, n1, c2, n2 = m.voxel_layers[0], m.voxel_layers[1], m.voxel_layers[3], m.voxel_layers[4]
+    cp, npt = m.point_features.layers[0], m.point_features.layers[1]
+    return [c1.weight, c1.bias, n1.weight, n1.bias, c2.weight, c2.bias, n2.weight, n2.bias,
+            cp.weight, cp.bias, npt.weight, npt.bias], [n1, n2, npt]
+
+
+class _PVConvFused(Function):
+    @staticmethod
+    def forward(ctx, features, coords, module, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep):
+        dev = features.device
+        if dev.type != "cuda":
+            raise RuntimeError("features must be a CUDA tensor")  # utils.hpp:7 semantics: no CPU path
+        features = features.contiguous().float()
+        coords = coords.detach().contiguous().float()
+        b, cin, n = features.shape
+        training = bool(module.training)
+        vox = module.voxelization
+        desc = Desc(b, n, cin, module.out_channels, int(module.resolution), int(bool(vox.normalize)), float(vox.eps),
+                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1)
+        bns = [module.voxel_layers[1], module.voxel_layers[4], module.point_features.layers[1]]
+        desc.bn_eps_vox = float(bns[0].eps)
+        desc.bn_eps_pt = float(bns[2].eps)
+        desc.momentum = float(bns[0].momentum if bns[0].momentum is not None else 0.1)
+        desc.slope = float(module.voxel_layers[2].negative_slope)
+        need_bwd = training and torch.is_grad_enabled() and any(
+            t.requires_grad for t in (features, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep))
+        plan = _Plan(desc, dev, need_bwd)
+        prm = Params()
+        vals = dict(w1=w1, b1=b1, g1=g1, be1=be1, rm1=bns[0].running_mean, rv1=bns[0].running_var,
+                    w2=w2, b2=b2, g2=g2, be2=be2, rm2=bns[1].running_mean, rv2=bns[1].running_var,
+                    wp=wp, bp=bp, gp=gp, bep=bep, rmp=bns[2].running_mean, rvp=bns[2].running_var)
+        keep = []
+        for k in _PARAM_FIELDS:
+            t = vals[k]
+            if t is not None:
+                t = t.detach()
+                if not t.is_contiguous() or t.dtype != torch.float32:
+                    raise RuntimeError("PVConv parameters must be contiguous float32 tensors")
+            keep.append(t)
+            setattr(prm, k, _ptr(t))
+        out = torch.empty((b, module.out_channels, n), dtype=torch.float32, device=dev)
+        ws = plan.struct()
+        _lib.call("pvcnn_pvconv_forward", ctypes.byref(desc), features, coords, ctypes.byref(prm), ctypes.byref(ws),
+                  out, device=dev)
+        if training:
+            for bn in bns:
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+        ctx.plan, ctx.prm, ctx.keep, ctx.desc = plan, prm, keep, desc
+        ctx.shapes = [t.shape for t in (w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep)]
+        ctx.in_shape = features.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        plan, desc = ctx.plan, ctx.desc
+        if not desc.training:
+            raise RuntimeError("PVConv backward requires training mode (batch statistics)")
+        dev = grad_out.device
+        grad_out = grad_out.contiguous().float()
+        plan.add_backward_scratch()
+        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        gs = Grads()
+        for k, t in zip(_GRAD_FIELDS, grads):
+            setattr(gs, k, _ptr(t))
+        gfeat = torch.empty(ctx.in_shape, dtype=torch.float32, device=dev)
+        ws = plan.struct()
+        _lib.call("pvcnn_pvconv_backward", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm), ctypes.byref(ws),
+                  gfeat, ctypes.byref(gs), device=dev)
+        return (gfeat, None, None, *grads)
+
+
+def pvconv_fused(module, features, coords):
+    """features [B,Cin,N], coords [B,3,N] -> fused features [B,Cout,N] (module: pvcnn_b200.nn.PVConv)."""
+    if module.with_se:
+        raise NotImplementedError("fused PVConv with SE3d")
+    params, _ = _module_tensors(module)
+    return _PVConvFused.apply(features, coords, module, *params)

@@ -111,3 +111,38 @@ def test_conv_linearity_full_size():
         patch = x1[3, i - 1:i + 2, j - 1:j + 2, k - 1:k + 2, :].double()      # [3,3,3,C]
         ref = torch.einsum("xyzc,ocxyz->o", patch, w.double())
         assert relerr(y[3, i, j, k], ref) < 2e-5
+
+
+@pytest.mark.parametrize("npass,tol", [(1, 3e-3), (3, 2e-5)])
+@pytest.mark.parametrize("b,r,cin,cout", [(1, 8, 16, 16), (2, 16, 64, 64), (1, 12, 64, 128), (1, 16, 9, 64),
+                                          (4, 32, 64, 64)])
+def test_conv3d_wgrad(npass, tol, b, r, cin, cout):
+    torch.manual_seed(5)
+    x = torch.randn(b, cin, r, r, r, device="cuda")
+    gy = torch.randn(b, cout, r, r, r, device="cuda")
+    conv = torch.nn.Conv3d(cin, cout, 3, padding=1).double()
+    xd = x.double().cpu()
+    conv(xd).backward(gy.double().cpu())
+    ref = conv.weight.grad.reshape(cout, cin, 27)
+    cp = (cin + 3) // 4 * 4
+    xcl = torch.zeros(b, r, r, r, cp, device="cuda")
+    xcl[..., :cin] = x.permute(0, 2, 3, 4, 1)
+    gcl = gy.permute(0, 2, 3, 4, 1).contiguous()
+    x_hi, x_lo = dense.split_tf32(xcl, want_hi=False)
+    g_hi, g_lo = dense.split_tf32(gcl, want_hi=False)
+    dw = dense.conv_wgrad(x_hi, x_lo, g_hi, g_lo, cin, cout, 27, npass=npass)
+    assert relerr(dw.cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("m,cin,cout", [(4096, 64, 64), (65536, 64, 64), (2048, 16, 32), (5000, 9, 64)])
+def test_pointwise_wgrad(m, cin, cout):
+    torch.manual_seed(6)
+    cp = (cin + 3) // 4 * 4
+    x = torch.zeros(m, cp, device="cuda")
+    x[:, :cin] = torch.randn(m, cin, device="cuda")
+    g = torch.randn(m, cout, device="cuda")
+    ref = g.double().t() @ x[:, :cin].double()
+    x_hi, x_lo = dense.split_tf32(x.view(1, 1, 1, m, cp), want_hi=False)
+    g_hi, g_lo = dense.split_tf32(g.view(1, 1, 1, m, cout), want_hi=False)
+    dw = dense.conv_wgrad(x_hi, x_lo, g_hi, g_lo, cin, cout, 1, npass=3)
+    assert relerr(dw[:, :, 0], ref) < 1e-5
