@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- PVConv forward+backward points/sec (BASELINE.json metric).
+
+Workload: one modules.PVConv(64, 64, kernel_size=3, resolution=32) in train mode,
+features ~ N(0,1) [16,64,4096], coords ~ U(0,1.5)xU(0,1.5)xU(0,3.0) [16,3,4096], fixed grad_out ~ N(0,1),
+seed 1588147245.  A "step" = zero grads, forward, backward (+ one NCCL all-reduce of the flat parameter
+gradients when N > 1).  Weak scaling: B=16 per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tf32]
+
+`--impl reference`: the reference has NO CPU implementation of this path (modules/functional/src/utils.hpp:7),
+so the reference arm is the CPU oracle (oracle/: C restatement of the reference kernels + the same torch dense
+ops the reference calls, on the host cores), on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, N, C, R = 16, 4096, 64, 32
+SEED = 1588147245
+CONV_FLOPS = 2.0 * B * R ** 3 * C * C * 27  # one 3x3x3 conv pass at the metric shape (115.96 GFLOP)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_inputs(torch, device, batch=B):
+    g = torch.Generator(device="cpu").manual_seed(SEED)
+    feats = torch.randn(batch, C, N, generator=g)
+    coords = torch.rand(batch, 3, N, generator=g) * torch.tensor([1.5, 1.5, 3.0]).view(1, 3, 1)
+    gout = torch.randn(batch, C, N, generator=g)
+    return feats, coords, gout
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ["PVCNN_B200_PRECISION"] = args.precision
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import modules
+    from pvcnn_b200 import _lib
+    torch.manual_seed(SEED)
+    m = modules.PVConv(C, C, 3, R).to(dev).train()
+    params = [p for p in m.parameters()]
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+    feats_h, coords_h, gout_h = [t.pin_memory() for t in make_inputs(torch, dev)]
+    feats = feats_h.to(dev).requires_grad_(True)
+    coords, gout = coords_h.to(dev), gout_h.to(dev)
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    def step(f, c, go):
+        for p in params:
+            p.grad = None
+        f.grad = None
+        out, _ = m((f, c))
+        out.backward(go)
+        if world > 1:  # ONE collective: flat fp32 gradient bucket over NCCL / NVLink
+            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return out
+
+    # L2 hygiene: the step streams > 2 GB of activations through a 126 MB L2, so consecutive steps
+    # cannot serve each other's data from cache; no explicit flush is needed ("inputs larger than L2").
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(feats, coords, gout)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(feats, coords, gout)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end: host buffers in, host buffers out, copies inside the timed region
+    out_h = torch.empty(B, C, N).pin_memory()
+    gfe_h = torch.empty(B, C, N).pin_memory()
+    f_d = torch.empty(B, C, N, device=dev, requires_grad=True)
+    c_d = torch.empty(B, 3, N, device=dev)
+    g_d = torch.empty(B, C, N, device=dev)
+
+    def e2e_step():
+        with torch.no_grad():
+            f_d.copy_(feats_h, non_blocking=True)
+            c_d.copy_(coords_h, non_blocking=True)
+            g_d.copy_(gout_h, non_blocking=True)
+        out = step(f_d, c_d, g_d)
+        out_h.copy_(out.detach(), non_blocking=True)
+        gfe_h.copy_(f_d.grad, non_blocking=True)
+
+    for _ in range(max(3, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    extra = {}
+    if rank == 0 and world == 1:
+        extra = single_gpu_extras(torch, dev, m, args)
+    if rank == 0:
+        pk = peaks()
+        line = {
+            "metric": "PVConv fwd+bwd points/sec (B=16,N=4096,C=64,R=32)", "value": world * B * N / ms * 1e3,
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 error-compensated tensor-core passes)" if args.precision == "fp32" else "tf32",
+            "data": "synthetic",
+            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, B=16/GPU N=4096",
+                       "parallelism": "dp%d" % world, "precision": args.precision,
+                       "l2": "activations (>2 GB/step) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * N / ms_e2e * 1e3, "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 4 * (2 * B * C * N + B * 3 * N), "d2h_bytes_per_step": 4 * 2 * B * C * N},
+            "gpu_launches": int(launches),
+            "peaks": pk,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def single_gpu_extras(torch, dev, m, args):
+    """roofline of the dominant kernel (timed alone with CUDA events), GPU-reference arm, cpu_baseline."""
+    from pvcnn_b200 import dense
+    pk = peaks()
+    extra = {}
+    npass = 3 if args.precision == "fp32" else 1
+    x = torch.randn(B, R, R, R, C, device=dev)
+    w_hi, w_lo = dense.prep_weight(m.voxel_layers[3].weight)
+    x_hi, x_lo = dense.split_tf32(x, want_hi=False)
+    for _ in range(3):
+        dense.igemm_conv(x_hi, x_lo, w_hi, w_lo, None, npass=npass)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        dense.igemm_conv(x_hi, x_lo, w_hi, w_lo, None, npass=npass)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    achieved = CONV_FLOPS / k_ms / 1e9
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    extra["roofline"] = {
+        "kernel": "igemm_conv_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32)", "bound": "tensor",
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": None, "kernel_ms": k_ms,
+        "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of the kernel "
+                "run alone; executed tensor FLOPs are %dx that. peak = %s bf16_tflops_sustained / 2 (tf32 is the "
+                "half-rate kind; no direct tf32 measurement in MEASURED_PEAKS.json)" % (CONV_FLOPS / 1e9, npass,
+                                                                                       pk["source"]),
+    }
+    # GPU reference arm (reference CUDA ops + cuDNN), informational
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ref_gpu_time
+        extra["reference_gpu"] = [ref_gpu_time.run(True, steps=10, warmup=5), ref_gpu_time.run(False, steps=5, warmup=2)]
+    except Exception as e:  # noqa: BLE001
+        extra["reference_gpu"] = {"unavailable": repr(e)[:200]}
+    extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
+    return extra
+
+
+def cpu_baseline(sample_batch=2, iters=2):
+    """The oracle (CPU port of the reference kernels + torch CPU dense ops) timed on the host cores."""
+    import numpy as np
+    import torch
+    import oracle
+    torch.manual_seed(SEED)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    feats, coords, gout = make_inputs(torch, None, batch=sample_batch)
+    ref = torch.nn.Sequential()  # parameters with the reference's shapes / default init
+    conv1, conv2 = torch.nn.Conv3d(C, C, 3, padding=1), torch.nn.Conv3d(C, C, 3, padding=1)
+    bn1, bn2 = torch.nn.BatchNorm3d(C, eps=1e-4), torch.nn.BatchNorm3d(C, eps=1e-4)
+    cp, bnp = torch.nn.Conv1d(C, C, 1), torch.nn.BatchNorm1d(C)
+    params = {"voxel_layers.0.weight": conv1.weight, "voxel_layers.0.bias": conv1.bias,
+              "voxel_layers.1.weight": bn1.weight, "voxel_layers.1.bias": bn1.bias,
+              "voxel_layers.3.weight": conv2.weight, "voxel_layers.3.bias": conv2.bias,
+              "voxel_layers.4.weight": bn2.weight, "voxel_layers.4.bias": bn2.bias,
+              "point_features.layers.0.weight": cp.weight, "point_features.layers.0.bias": cp.bias,
+              "point_features.layers.1.weight": bnp.weight, "point_features.layers.1.bias": bnp.bias}
+    params = {k: v.detach().numpy() for k, v in params.items()}
+    f, c, g = feats.numpy(), coords.numpy(), gout.numpy()
+    oracle.pvconv_forward_backward(params, f, c, g, R)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        oracle.pvconv_forward_backward(params, f, c, g, R)
+    dt = (time.perf_counter() - t0) / iters
+    return {"value": sample_batch * N / dt, "unit": "points/s", "cores": threads, "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": "B=%d of the 16 clouds (N=4096, C=64, R=32), fwd+bwd, %d iterations after 1 warm-up; the "
+                      "reference has no CPU path, this is the oracle port (C kernels + torch CPU conv/BN)" %
+                      (sample_batch, iters)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sample = 2
+    cb = cpu_baseline(sample_batch=sample, iters=max(1, min(args.steps, 3)))
+    ms = cb["ms_per_step"]
+    line = {"impl": "reference", "metric": "PVConv fwd+bwd points/sec (B=16,N=4096,C=64,R=32)", "value": cb["value"],
+            "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, bounded sample B=%d" % sample,
+                       "parallelism": "host threads"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PVCNN_B200_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

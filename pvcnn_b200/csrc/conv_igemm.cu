@@ -296,24 +296,28 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *gdim, const cuuint64_t *gstride,
-                      const cuuint32_t *box) {
+                      const cuuint32_t *box, bool atom32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return PVCNN_E_UNSUPPORTED;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (200000 + (int)r);
 }
 
-// 5-D map over a channels-last tensor [nb,sx,sy,sz,ld] with k valid channels and a {32, bz, by, bx, 1} box
+// 5-D map over a channels-last tensor [nb,sx,sy,sz,ld] with k valid channels and a {32, bz, by, bx, 1} box.
+// atom32: 128B swizzle with 32-byte atoms -- the only shared-memory layout tcgen05 accepts for MN-major
+// tf32 operands (UMMA layout type SWIZZLE_128B_BASE32B).
 int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, int sx, int sy, int sz, int bz, int by,
-                     int bx) {
+                     int bx, bool atom32) {
   cuuint64_t gdim[5] = {(cuuint64_t)k, (cuuint64_t)sz, (cuuint64_t)sy, (cuuint64_t)sx, (cuuint64_t)nb};
   cuuint64_t gstr[4] = {(cuuint64_t)ld * 4, (cuuint64_t)sz * ld * 4, (cuuint64_t)sy * sz * ld * 4,
                         (cuuint64_t)sx * sy * sz * ld * 4};
   cuuint32_t box[5] = {(cuuint32_t)IG_KC, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
-  return encode_map(map, ptr, 5, gdim, gstr, box);
+  return encode_map(map, ptr, 5, gdim, gstr, box, atom32);
 }
 
 static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps

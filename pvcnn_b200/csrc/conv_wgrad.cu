@@ -144,15 +144,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           const uint32_t d_main = tmem_base + (uint32_t)buf * tmem_cols_per_buf + (uint32_t)(g * p.block_n);
           const uint32_t d_corr = d_main + (uint32_t)(G * p.block_n);
           for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint32_t koff = (uint32_t)ks * 1024u;  // 8 voxel rows = one 1024-byte swizzle atom
-            // MN-major SW128: LBO = stride between 32-channel blocks, SBO = stride between 8-row K groups
-            const uint64_t da_hi = make_smem_desc(a_hi + koff, WG_BLK, 1024, kLayoutSW128);
-            const uint64_t db_hi = make_smem_desc(g_hi + koff, WG_BLK, 1024, kLayoutSW128);
+            const uint32_t koff = (uint32_t)ks * 1024u;  // 8 voxel rows of 128 bytes per MMA
+            // MN-major tf32 operands use the 128B swizzle with 32-byte atoms (4-row repeat): LBO = stride
+            // between 32-channel blocks, SBO = stride between 4-row K groups (rows are 128 B apart)
+            const uint64_t da_hi = make_smem_desc(a_hi + koff, WG_BLK, 512, kLayoutSW128Base32);
+            const uint64_t db_hi = make_smem_desc(g_hi + koff, WG_BLK, 512, kLayoutSW128Base32);
             const uint32_t accum = (pos_in_chain | ks) != 0;
             mma_tf32_ss(d_main, da_hi, db_hi, idesc, accum);
             if (p.npass > 1) {
-              const uint64_t da_lo = make_smem_desc(a_lo + koff, WG_BLK, 1024, kLayoutSW128);
-              const uint64_t db_lo = make_smem_desc(g_lo + koff, WG_BLK, 1024, kLayoutSW128);
+              const uint64_t da_lo = make_smem_desc(a_lo + koff, WG_BLK, 512, kLayoutSW128Base32);
+              const uint64_t db_lo = make_smem_desc(g_lo + koff, WG_BLK, 512, kLayoutSW128Base32);
               mma_tf32_ss(d_corr, da_hi, db_lo, idesc, accum);
               mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
             }
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 }
 
 int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, int sx, int sy, int sz, int bz, int by,
-                     int bx);  // conv_igemm.cu
+                     int bx, bool atom32);  // conv_igemm.cu
 
 static int *g_wg_err = nullptr;
 
@@ -277,10 +278,10 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
 
   CUtensorMap mx_hi, mx_lo, mg_hi, mg_lo;
   int rc;
-  if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
-  if ((rc = encode_map_5d_cl(&mx_lo, npass > 1 ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
-  if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
-  if ((rc = encode_map_5d_cl(&mg_lo, npass > 1 ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1))) return rc;
+  if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mx_lo, npass > 1 ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_lo, npass > 1 ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   const size_t smem = (size_t)WG_STAGES * p.stage_bytes + 1024;
   if (p.groups_per_cta == 2) {
     PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -142,6 +142,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 constexpr uint32_t kLayoutSW128 = 2;
+constexpr uint32_t kLayoutSW128Base32 = 1;  // 128B swizzle, 32-byte atoms (MN-major 32-bit operands)
 
 }  // namespace umma
 }  // namespace pvb
