@@ -103,7 +103,8 @@ def run_ours(args):
     feats_h, coords_h, gout_h = [t.pin_memory() for t in make_inputs(torch, dev)]
     feats = feats_h.to(dev).requires_grad_(True)
     coords, gout = coords_h.to(dev), gout_h.to(dev)
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    from pvcnn_b200.parallel import GradBucket
+    bucket = GradBucket(params, dev)
 
     def step(f, c, go):
         for p in params:
@@ -111,10 +112,7 @@ def run_ours(args):
         f.grad = None
         out, _ = m((f, c))
         out.backward(go)
-        if world > 1:  # ONE collective: flat fp32 gradient bucket over NCCL / NVLink
-            torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-            dist.all_reduce(flat)
-            flat.div_(world)
+        bucket.all_reduce_mean()  # ONE collective: flat fp32 gradient bucket over NCCL / NVLink (no-op at N=1)
         return out
 
     # L2 hygiene: the step streams > 2 GB of activations through a 126 MB L2, so consecutive steps

@@ -207,14 +207,21 @@ int launch_bn_stats(long long rows, int cp, const float *y, float *partials, int
   return 0;
 }
 
-// sums[set][c] = sum over blocks (fp64) of partials[block][set][c]
+// sums[j] = sum over blocks (fp64) of partials[block][j]; one warp per column, lanes stride over blocks
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void __launch_bounds__(256) reduce_partials_kernel(int nblocks, int ncols, const float *__restrict__ partials,
                                                               float *__restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= ncols) return;
   double s = 0.0;
-  for (int k = 0; k < nblocks; ++k) s += (double)partials[(size_t)k * ncols + c];
-  sums[c] = (float)s;
+  for (int k = lane; k < nblocks; k += 32) s += (double)partials[(size_t)k * ncols + c];
+  s = warp_sum_d(s);
+  if (lane == 0) sums[c] = (float)s;
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, int cp, double rows, float eps,
@@ -222,17 +229,20 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
                                                           const float *__restrict__ gamma,
                                                           const float *__restrict__ beta, float *running_mean,
                                                           float *running_var, BnCoef coef) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per channel
   if (ch >= cp) return;
   if (ch >= c) {
-    coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f;
+    if (lane == 0) { coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f; }
     return;
   }
   double s = 0.0, ss = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
+  for (int k = lane; k < nblocks; k += 32) {
     s += (double)partials[((size_t)k * 2 + 0) * cp + ch];
     ss += (double)partials[((size_t)k * 2 + 1) * cp + ch];
   }
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  if (lane != 0) return;
   const double mean = s / rows;
   double var = ss / rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
 int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
                        const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
                        cudaStream_t s) {
-  PVB_LAUNCH(bn_finalize_kernel, ceil_div(cp, 256), 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
+  PVB_LAUNCH(bn_finalize_kernel, ceil_div(cp, 8), 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
              gamma, beta, running_mean, running_var, coef);
   return 0;
 }
@@ -507,7 +517,7 @@ int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const flo
 }
 
 int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s) {
-  PVB_LAUNCH(reduce_partials_kernel, ceil_div(ncols, 256), 256, 0, s, nblocks, ncols, partials, sums);
+  PVB_LAUNCH(reduce_partials_kernel, ceil_div(ncols, 8), 256, 0, s, nblocks, ncols, partials, sums);
   return 0;
 }
 
