@@ -1,0 +1,312 @@
+// conv_halo.cu -- second-generation 3x3x3 implicit-GEMM convolution (forward / data gradient) for sm_100a.
+//
+// v1 (conv_igemm.cu) fetches one [128 voxel x 32 channel] tile per (tap, chunk) and is bound by the
+// L2->SMEM pipe (ncu: 10.9 GB pulled from L2 per launch, tensor pipe 38 % active).  This kernel keeps a HALO
+// block of the input in shared memory and serves the 9 (dy,dx) taps of a z-shift from it:
+//
+//   * a CTA produces 2 output tiles (two x-planes of [TY x BZ] = 128 voxels) per iteration;
+//   * per phase (dz in {-1,0,1}, 16-channel chunk) ONE 5-D TMA box brings the (TX+2) x (TY+2) x BZ halo
+//     (z pre-shifted by dz, out-of-bounds rows zero-filled = conv padding) into 64-byte-swizzled rows;
+//     a tap (dy,dx) of tile t is then just a row offset of the UMMA descriptor (multiples of 8 rows, so the
+//     swizzle phase is preserved) -- 18 tile-operands from one 768-row load instead of 18 loads of 128 rows;
+//   * the `lo` halves of the 3xTF32 split are computed IN the kernel by 4 converter warps
+//     (lo = x - trunc_tf32(x), generic-proxy writes + fence.proxy.async), so activations need no `lo`
+//     tensor in HBM and the A-side L2 traffic halves again;
+//   * weights stream through a 4-deep ring of [Cout x 16] tiles (hi, lo), one per tap and phase;
+//   * accumulators: per tile two main chains (phases 0-5 / 6-11: <= 108 MMAs each, the tensor core
+//     truncates when accumulating) and one chain for the correction terms; summed in fp32 RN in the epilogue.
+//
+// L2->SMEM traffic per conv at the metric shape: ~3.1 GB (v1: 10.9 GB).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pvb {
+using namespace umma;
+
+constexpr int HC_THREADS = 384;   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue, w8-11 converters
+constexpr int HC_KC = 16;         // channels per phase (64-byte rows, SWIZZLE_64B)
+constexpr int HC_TX = 2;          // output x-planes (tiles) per CTA iteration
+constexpr int HC_BSTAGES = 4;     // weight-tile ring
+constexpr uint32_t kLayoutSW64 = 4;
+
+struct HaloParams {
+  int nb, sx, sy, sz;             // sz = BZ (full z rows), 128 % sz == 0, sz % 8 == 0
+  int ty;                         // y rows per tile = 128 / sz
+  int tiles_y, pairs_x;           // sy / ty (ceil), sx / 2 (ceil)
+  int num_units;                  // nb * pairs_x * tiles_y
+  int kchunks;                    // ceil(k / 16)
+  int cout, block_n;              // block_n = cout padded to 16 (<= 64)
+  int npass;
+  int ldo;
+  uint32_t a_rows, a_bytes;       // halo rows, bytes of one halo copy (rows * 64)
+  uint32_t b_bytes;               // bytes of one weight tile copy (block_n * 64)
+  const float *bias;
+  float *out;
+  int *err;
+};
+
+__global__ void __launch_bounds__(HC_THREADS, 1)
+    conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w_hi,
+                     const __grid_constant__ CUtensorMap map_w_lo, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t a_full[2], a_ready[2], a_empty[2], b_full[HC_BSTAGES], b_empty[HC_BSTAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool three = p.npass > 1;
+  // smem carve-up: [A buf0: hi, lo][A buf1: hi, lo][B ring: (hi, lo) x stages]
+  const uint32_t a_buf_bytes = p.a_bytes * 2;
+  uint8_t *smem_b = smem + 2 * a_buf_bytes;
+  const uint32_t b_stage_bytes = p.b_bytes * 2;
+  const int nphases = 3 * p.kchunks;
+  const int half_phase = (nphases + 1) / 2;
+  const uint32_t tmem_cols = 512;  // 2 tiles x (main0, main1, corr) x block_n <= 384 -> allocate all
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_w_hi);
+    if (three) prefetch_tensormap(&map_w_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < HC_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int abuf = 0, bst = 0;
+      uint32_t aphase = 0, bphase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int u = unit;
+        const int y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
+        const int x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
+        const int b = u;
+        for (int ph = 0; ph < nphases; ++ph) {
+          const int dz = ph / p.kchunks - 1, cc = ph % p.kchunks;
+          mbar_wait(&a_empty[abuf], aphase ^ 1, p.err, 21);
+          mbar_arrive_expect_tx(&a_full[abuf], p.a_bytes);
+          tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
+          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+          for (int t9 = 0; t9 < 9; ++t9) {  // taps (dx, dy) of this dz
+            const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
+            const int tap = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
+            mbar_wait(&b_empty[bst], bphase ^ 1, p.err, 22);
+            uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
+            mbar_arrive_expect_tx(&b_full[bst], three ? 2 * p.b_bytes : p.b_bytes);
+            tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * HC_KC, 0, tap);
+            if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * HC_KC, 0, tap);
+            if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
+      const uint32_t row_bytes = HC_KC * 4;  // 64
+      int abuf = 0, bst = 0, it = 0;
+      uint32_t aphase = 0, bphase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+        mbar_wait(&acc_empty, (uint32_t)((it & 1) ^ 1), p.err, 23);
+        tc_fence_after();
+        for (int ph = 0; ph < nphases; ++ph) {
+          mbar_wait(&a_ready[abuf], aphase, p.err, 24);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + (size_t)abuf * a_buf_bytes);
+          const uint32_t a_lo = a_hi + p.a_bytes;
+          const int slot = ph < half_phase ? 0 : 1;
+          const bool slot_fresh = (ph == 0) || (ph == half_phase);
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
+            mbar_wait(&b_full[bst], bphase, p.err, 25);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(smem_b + (size_t)bst * b_stage_bytes);
+            const uint32_t b_lo = b_hi + p.b_bytes;
+#pragma unroll
+            for (int t = 0; t < HC_TX; ++t) {
+              // halo rows are ordered (x_local, y_local, z); tile t / tap (dy,dx) starts at this row
+              const uint32_t row0 = (uint32_t)(((t + dx + 1) * (p.ty + 2) + (dy + 1)) * p.sz);
+              const uint32_t d_main = tmem_base + (uint32_t)((t * 3 + slot) * p.block_n);
+              const uint32_t d_corr = tmem_base + (uint32_t)((t * 3 + 2) * p.block_n);
+#pragma unroll
+              for (int ks = 0; ks < HC_KC / 8; ++ks) {
+                const uint32_t off = row0 * row_bytes + (uint32_t)ks * 32u;
+                const uint64_t da_hi = make_smem_desc(a_hi + off, 0, 512, kLayoutSW64);
+                const uint64_t db_hi = make_smem_desc(b_hi + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
+                mma_tf32_ss(d_main, da_hi, db_hi, idesc, !(slot_fresh && t9 == 0 && ks == 0));
+                if (three) {
+                  const uint64_t da_lo = make_smem_desc(a_lo + off, 0, 512, kLayoutSW64);
+                  const uint64_t db_lo = make_smem_desc(b_lo + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
+                  mma_tf32_ss(d_corr, da_hi, db_lo, idesc, !(ph == 0 && t9 == 0 && ks == 0));
+                  mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
+                }
+              }
+            }
+            mma_commit(&b_empty[bst]);
+            if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
+          }
+          mma_commit(&a_empty[abuf]);
+          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+        }
+        mma_commit(&acc_full);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ converters: lo = x - trunc_tf32(x) ================================
+    const int tid = threadIdx.x - 8 * 32;  // 0..127
+    int abuf = 0;
+    uint32_t aphase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      for (int ph = 0; ph < nphases; ++ph) {
+        mbar_wait(&a_full[abuf], aphase, p.err, 26);
+        if (three) {
+          const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)abuf * a_buf_bytes);
+          float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)abuf * a_buf_bytes + p.a_bytes);
+          const int n16 = (int)(p.a_bytes >> 4);
+          // elementwise on the swizzled bytes: hi and lo share the same layout
+          for (int i = tid; i < n16; i += 128) {
+            const float4 v = src[i];
+            float4 l;
+            l.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+            l.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+            l.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+            l.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+            dst[i] = l;
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        }
+        mbar_arrive(&a_ready[abuf]);
+        if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int we = warp - 4;
+    const int m = we * 32 + lane;
+    const int lz = m % p.sz, ly = m / p.sz;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      int u = unit;
+      const int y = (u % p.tiles_y) * p.ty + ly; u /= p.tiles_y;
+      const int x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
+      const int b = u;
+      mbar_wait(&acc_full, (uint32_t)(it & 1), p.err, 27);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < HC_TX; ++t) {
+        const int x = x0 + t;
+        const bool valid = x < p.sx && y < p.sy;
+        float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + lz) * p.ldo;
+        const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(t * 3 * p.block_n);
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          float v[16], w[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld16(taddr + p.block_n + c0, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += w[i];
+          if (three) {
+            tmem_ld16(taddr + 2 * p.block_n + c0, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+          if (valid && c0 < p.cout) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.cout) v[i] += __ldg(p.bias + c0 + i);
+            }
+            if (c0 + 16 <= p.cout) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4 *>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+              for (int i = 0; i < 16 && c0 + i < p.cout; ++i) orow[c0 + i] = v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsigned long long *gdim,
+                       const unsigned long long *gstride_bytes, const unsigned *box, int swizzle_kind);  // conv_igemm.cu
+
+static int *g_halo_err = nullptr;
+
+// Returns PVCNN_E_UNSUPPORTED when the shape is outside this kernel's envelope (caller falls back to v1).
+int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
+                     const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream) {
+  if (!(sz % 8 == 0 && sz <= 128 && 128 % sz == 0 && cout <= 64 && sx >= 2)) return PVCNN_E_UNSUPPORTED;
+  PVB_CHECK_ARG(a && w_hi && out && (npass == 1 || w_lo) && lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0);
+  if (!g_halo_err) {
+    PVB_CUDA(cudaMalloc((void **)&g_halo_err, sizeof(int)));
+    PVB_CUDA(cudaMemset(g_halo_err, 0, sizeof(int)));
+  }
+  HaloParams p{};
+  p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
+  p.ty = 128 / sz;
+  p.tiles_y = ceil_div(sy, p.ty);
+  p.pairs_x = ceil_div(sx, HC_TX);
+  p.num_units = nb * p.pairs_x * p.tiles_y;
+  p.kchunks = ceil_div(k, HC_KC);
+  p.cout = cout;
+  p.block_n = max(16, ((cout + 15) / 16) * 16);
+  p.npass = npass;
+  p.ldo = ldo;
+  p.a_rows = (uint32_t)(sz * (p.ty + 2) * (HC_TX + 2));
+  p.a_bytes = p.a_rows * HC_KC * 4;
+  p.b_bytes = (uint32_t)p.block_n * HC_KC * 4;
+  p.bias = bias; p.out = out; p.err = g_halo_err;
+  if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
+
+  CUtensorMap ma, mw_hi, mw_lo;
+  {
+    unsigned long long gdim[5] = {(unsigned long long)k, (unsigned long long)sz, (unsigned long long)sy,
+                                  (unsigned long long)sx, (unsigned long long)nb};
+    unsigned long long gstr[4] = {(unsigned long long)lda * 4, (unsigned long long)sz * lda * 4,
+                                  (unsigned long long)sy * sz * lda * 4, (unsigned long long)sx * sy * sz * lda * 4};
+    unsigned box[5] = {(unsigned)HC_KC, (unsigned)sz, (unsigned)(p.ty + 2), (unsigned)(HC_TX + 2), 1};
+    int rc = encode_map_generic(&ma, a, 5, gdim, gstr, box, 64);
+    if (rc) return rc;
+  }
+  {
+    unsigned long long gdim[3] = {(unsigned long long)k, (unsigned long long)cout, 27ull};
+    unsigned long long gstr[2] = {(unsigned long long)ldw * 4, (unsigned long long)cout * ldw * 4};
+    unsigned box[3] = {(unsigned)HC_KC, (unsigned)p.block_n, 1};
+    int rc = encode_map_generic(&mw_hi, w_hi, 3, gdim, gstr, box, 64);
+    if (rc) return rc;
+    rc = encode_map_generic(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box, 64);
+    if (rc) return rc;
+  }
+  const size_t smem = 2 * (size_t)p.a_bytes * 2 + (size_t)HC_BSTAGES * p.b_bytes * 2 + 1024;
+  if (smem > 227 * 1024 - 512) return PVCNN_E_UNSUPPORTED;
+  PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(kNumSMs, p.num_units);
+  PVB_LAUNCH(conv_halo_kernel, grid, HC_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+  return 0;
+}
+
+}  // namespace pvb

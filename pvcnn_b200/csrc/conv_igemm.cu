@@ -23,6 +23,7 @@
 //     accumulator and (2) the main chain is split over up to 3 accumulators of <= 72 MMAs each;
 //     the epilogue adds the partial sums in round-to-nearest fp32.
 //     npass=1 is plain TF32 (what cuDNN does by default in the reference).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -320,6 +321,28 @@ int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, 
   return encode_map(map, ptr, 5, gdim, gstr, box, atom32);
 }
 
+// generic tiled map; swizzle_kind: 128 (SWIZZLE_128B), 64 (SWIZZLE_64B), 32 (SWIZZLE_128B_ATOM_32B)
+int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsigned long long *gdim,
+                       const unsigned long long *gstride_bytes, const unsigned *box, int swizzle_kind) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return PVCNN_E_UNSUPPORTED;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gd[i] = gdim[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = gstride_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_kind == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_kind == 32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                     : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (200000 + (int)r);
+}
+
+int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
+                     const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass,
+                     cudaStream_t stream);  // conv_halo.cu
+
 static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps
 
 }  // namespace pvb
@@ -366,6 +389,14 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && k > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
   PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || (a_lo && w_lo)));
   PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
+  if (ntaps == 27) {
+    // second-generation kernel (smem halo reuse, in-kernel lo) when the shape is inside its envelope
+    static const bool force_v1 = [] { const char *e = getenv("PVCNN_B200_CONV"); return e && e[0] == 'v' && e[1] == '1'; }();
+    if (!force_v1) {
+      const int rc = conv_halo_launch(nb, sx, sy, sz, k, cout, a_hi, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream);
+      if (rc != PVCNN_E_UNSUPPORTED) return rc;
+    }
+  }
   if (!g_err_flag) {
     PVB_CUDA(cudaMalloc((void **)&g_err_flag, sizeof(int)));
     PVB_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));

@@ -25,6 +25,11 @@ flops = 2.0 * b * r ** 3 * c * c * 27
 for npass in (1, 3):
     ms = timeit(lambda: dense.igemm_conv(hi, lo, w_hi, w_lo, None, npass=npass))
     print(json.dumps({"op": "conv3d_fwd", "npass": npass, "ms": ms, "tflops_algorithmic": flops / ms / 1e9}))
+g = torch.randn(b, r, r, r, c, device="cuda")
+g_hi, g_lo = dense.split_tf32(g, want_hi=False)
+for npass in (1, 3):
+    ms = timeit(lambda: dense.conv_wgrad(hi, lo, g_hi, g_lo, c, c, 27, npass=npass))
+    print(json.dumps({"op": "conv3d_wgrad", "npass": npass, "ms": ms, "tflops_algorithmic": flops / ms / 1e9}))
 xp = torch.randn(1, 1, 1, b * 4096, c, device="cuda")
 wp = torch.randn(c, c, 1, device="cuda")
 wp_hi, wp_lo = dense.prep_weight(wp)
