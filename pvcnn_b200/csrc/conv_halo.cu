@@ -23,7 +23,7 @@
 namespace pvb {
 using namespace umma;
 
-constexpr int HC_THREADS = 384;   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-7 epilogue, w8-11 converters
+constexpr int HC_THREADS = 384;   // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-7 epilogue, w8-11 converters
 constexpr int HC_KC = 16;         // channels per phase (64-byte rows, SWIZZLE_64B)
 constexpr int HC_TX = 2;          // output x-planes (tiles) per CTA iteration
 constexpr int HC_BSTAGES = 4;     // weight-tile ring
@@ -85,10 +85,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer: activation halos ================================
+    // (own thread, so the next phase's halo is requested as soon as its buffer frees up, independent of
+    //  how far the weight ring has advanced)
     if (elect_one()) {
-      int abuf = 0, bst = 0;
-      uint32_t aphase = 0, bphase = 0;
+      int abuf = 0;
+      uint32_t aphase = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         int u = unit;
         const int y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
@@ -100,6 +102,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
           mbar_arrive_expect_tx(&a_full[abuf], p.a_bytes);
           tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
           if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ TMA producer: weight tiles ================================
+    if (elect_one()) {
+      int bst = 0;
+      uint32_t bphase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        for (int ph = 0; ph < nphases; ++ph) {
+          const int dz = ph / p.kchunks - 1, cc = ph % p.kchunks;
           for (int t9 = 0; t9 < 9; ++t9) {  // taps (dx, dy) of this dz
             const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
             const int tap = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);

@@ -391,7 +391,8 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
   PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
   if (ntaps == 27) {
     // second-generation kernel (smem halo reuse, in-kernel lo) when the shape is inside its envelope
-    static const bool force_v1 = [] { const char *e = getenv("PVCNN_B200_CONV"); return e && e[0] == 'v' && e[1] == '1'; }();
+    const char *e_conv = getenv("PVCNN_B200_CONV");
+    const bool force_v1 = e_conv && e_conv[0] == 'v' && e_conv[1] == '1';
     if (!force_v1) {
       const int rc = conv_halo_launch(nb, sx, sy, sz, k, cout, a_hi, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream);
       if (rc != PVCNN_E_UNSUPPORTED) return rc;
