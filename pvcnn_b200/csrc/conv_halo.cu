@@ -17,6 +17,8 @@
 //     truncates when accumulating) and one chain for the correction terms; summed in fp32 RN in the epilogue.
 //
 // L2->SMEM traffic per conv at the metric shape: ~3.1 GB (v1: 10.9 GB).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -43,6 +45,7 @@ struct HaloParams {
   const float *bias;
   float *out;
   int *err;
+  int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 2 A-collector reuse, 4 skip MMA3
 };
 
 __global__ void __launch_bounds__(HC_THREADS, 1)
@@ -160,12 +163,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
                 const uint32_t off = row0 * row_bytes + (uint32_t)ks * 32u;
                 const uint64_t da_hi = make_smem_desc(a_hi + off, 0, 512, kLayoutSW64);
                 const uint64_t db_hi = make_smem_desc(b_hi + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
-                mma_tf32_ss(d_main, da_hi, db_hi, idesc, !(slot_fresh && t9 == 0 && ks == 0));
+                const uint32_t acc_main = !(slot_fresh && t9 == 0 && ks == 0);
                 if (three) {
                   const uint64_t da_lo = make_smem_desc(a_lo + off, 0, 512, kLayoutSW64);
                   const uint64_t db_lo = make_smem_desc(b_lo + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
-                  mma_tf32_ss(d_corr, da_hi, db_lo, idesc, !(ph == 0 && t9 == 0 && ks == 0));
-                  mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
+                  const uint32_t acc_corr = !(ph == 0 && t9 == 0 && ks == 0);
+                  if (p.exp & 2) {  // A_hi is fetched from shared memory once and reused from the collector
+                    mma_tf32_ss_coll(d_main, da_hi, db_hi, idesc, acc_main, 1);
+                    mma_tf32_ss_coll(d_corr, da_hi, db_lo, idesc, acc_corr, 2);
+                  } else {
+                    mma_tf32_ss(d_main, da_hi, db_hi, idesc, acc_main);
+                    mma_tf32_ss(d_corr, da_hi, db_lo, idesc, acc_corr);
+                  }
+                  if (!(p.exp & 4)) mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
+                } else {
+                  mma_tf32_ss(d_main, da_hi, db_hi, idesc, acc_main);
                 }
               }
             }
@@ -186,7 +198,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       for (int ph = 0; ph < nphases; ++ph) {
         mbar_wait(&a_full[abuf], aphase, p.err, 26);
-        if (three) {
+        if (three && !(p.exp & 1)) {
           const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)abuf * a_buf_bytes);
           float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)abuf * a_buf_bytes + p.a_bytes);
           const int n16 = (int)(p.a_bytes >> 4);
@@ -293,6 +305,7 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
   p.a_bytes = p.a_rows * HC_KC * 4;
   p.b_bytes = (uint32_t)p.block_n * HC_KC * 4;
   p.bias = bias; p.out = out; p.err = g_halo_err;
+  { const char *e = getenv("PVCNN_HALO_EXP"); p.exp = e ? atoi(e) : 0; }
   if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
 
   CUtensorMap ma, mw_hi, mw_lo;

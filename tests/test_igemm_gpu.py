@@ -65,7 +65,7 @@ def test_conv3d_forward(npass, tol, b, r, cin, cout):
     ref = torch.nn.functional.conv3d(x.double().cpu(), conv.weight.double().cpu(), conv.bias.double().cpu(), padding=1)
     xcl = torch.zeros(b, r, r, r, cp, device="cuda")
     xcl[..., :cin] = x.permute(0, 2, 3, 4, 1)
-    a_hi, a_lo = dense.split_tf32(xcl)
+    a_hi, a_lo = dense.split_tf32(xcl, want_hi=False)
     w_hi, w_lo = dense.prep_weight(conv.weight)
     out = dense.igemm_conv(a_hi, a_lo, w_hi, w_lo, conv.bias.detach(), npass=npass)
     got = out[..., :cout].permute(0, 4, 1, 2, 3).cpu()
@@ -80,7 +80,7 @@ def test_conv3d_dgrad(b, r, cin, cout):
     gy = torch.randn(b, cout, r, r, r, dtype=torch.float64)
     conv(x).backward(gy)
     gcl = gy.float().permute(0, 2, 3, 4, 1).contiguous().cuda()
-    g_hi, g_lo = dense.split_tf32(gcl)
+    g_hi, g_lo = dense.split_tf32(gcl, want_hi=False)
     w_hi, w_lo = dense.prep_weight(conv.weight.float().cuda(), mode=1)
     out = dense.igemm_conv(g_hi, g_lo, w_hi, w_lo, None, npass=3)
     got = out[..., :cin].permute(0, 4, 1, 2, 3).cpu()
@@ -98,7 +98,7 @@ def test_conv_linearity_full_size():
     w_hi, w_lo = dense.prep_weight(w)
 
     def conv(t):
-        hi, lo = dense.split_tf32(t)
+        hi, lo = dense.split_tf32(t, want_hi=False)
         return dense.igemm_conv(hi, lo, w_hi, w_lo, None, npass=3)
 
     lhs = conv(2.5 * x1 + x2)
