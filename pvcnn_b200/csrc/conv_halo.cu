@@ -133,7 +133,15 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
-      const uint32_t row_bytes = HC_KC * 4;  // 64
+      constexpr uint32_t dhi = desc_hi32(512, kLayoutSW64);
+      // descriptor offsets (16-byte units) of tile t / tap t9 inside the halo: rows are (x_local, y_local, z)
+      uint32_t tap_off[9][HC_TX];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9)
+#pragma unroll
+        for (int t = 0; t < HC_TX; ++t)
+          tap_off[t9][t] = (uint32_t)(((t + t9 / 3) * (p.ty + 2) + (t9 % 3)) * p.sz) * (HC_KC * 4 / 16);
+      const uint32_t bn = (uint32_t)p.block_n;
       int abuf = 0, bst = 0, it = 0;
       uint32_t aphase = 0, bphase = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
@@ -142,42 +150,29 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         for (int ph = 0; ph < nphases; ++ph) {
           mbar_wait(&a_ready[abuf], aphase, p.err, 24);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + (size_t)abuf * a_buf_bytes);
-          const uint32_t a_lo = a_hi + p.a_bytes;
-          const int slot = ph < half_phase ? 0 : 1;
-          const bool slot_fresh = (ph == 0) || (ph == half_phase);
+          const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)abuf * a_buf_bytes), 0);
+          const uint32_t a_lo = a_hi + (p.a_bytes >> 4);
+          const uint32_t slot_col = ph < half_phase ? 0u : bn;
+          const uint32_t fresh_main = ((ph == 0) || (ph == half_phase)) ? 0u : 1u;
+          const uint32_t fresh_corr = ph == 0 ? 0u : 1u;
+#pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {
-            const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
             mbar_wait(&b_full[bst], bphase, p.err, 25);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(smem_b + (size_t)bst * b_stage_bytes);
-            const uint32_t b_lo = b_hi + p.b_bytes;
+            const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
+            const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
 #pragma unroll
             for (int t = 0; t < HC_TX; ++t) {
-              // halo rows are ordered (x_local, y_local, z); tile t / tap (dy,dx) starts at this row
-              const uint32_t row0 = (uint32_t)(((t + dx + 1) * (p.ty + 2) + (dy + 1)) * p.sz);
-              const uint32_t d_main = tmem_base + (uint32_t)((t * 3 + slot) * p.block_n);
-              const uint32_t d_corr = tmem_base + (uint32_t)((t * 3 + 2) * p.block_n);
+              const uint32_t d_main = tmem_base + (uint32_t)t * 3u * bn + slot_col;
+              const uint32_t d_corr = tmem_base + (uint32_t)t * 3u * bn + 2u * bn;
 #pragma unroll
               for (int ks = 0; ks < HC_KC / 8; ++ks) {
-                const uint32_t off = row0 * row_bytes + (uint32_t)ks * 32u;
-                const uint64_t da_hi = make_smem_desc(a_hi + off, 0, 512, kLayoutSW64);
-                const uint64_t db_hi = make_smem_desc(b_hi + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
-                const uint32_t acc_main = !(slot_fresh && t9 == 0 && ks == 0);
+                const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
+                const uint32_t first = (t9 == 0 && ks == 0) ? 1u : 0u;
+                mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
                 if (three) {
-                  const uint64_t da_lo = make_smem_desc(a_lo + off, 0, 512, kLayoutSW64);
-                  const uint64_t db_lo = make_smem_desc(b_lo + (uint32_t)ks * 32u, 0, 512, kLayoutSW64);
-                  const uint32_t acc_corr = !(ph == 0 && t9 == 0 && ks == 0);
-                  if (p.exp & 2) {  // A_hi is fetched from shared memory once and reused from the collector
-                    mma_tf32_ss_coll(d_main, da_hi, db_hi, idesc, acc_main, 1);
-                    mma_tf32_ss_coll(d_corr, da_hi, db_lo, idesc, acc_corr, 2);
-                  } else {
-                    mma_tf32_ss(d_main, da_hi, db_hi, idesc, acc_main);
-                    mma_tf32_ss(d_corr, da_hi, db_lo, idesc, acc_corr);
-                  }
-                  if (!(p.exp & 4)) mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
-                } else {
-                  mma_tf32_ss(d_main, da_hi, db_hi, idesc, acc_main);
+                  mma_tf32_lo32(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+                  if (!(p.exp & 4)) mma_tf32_lo32(d_corr, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
                 }
               }
             }

@@ -150,21 +150,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
           const uint32_t d_tmem = tile_tmem + (uint32_t)(slot * p.block_n);
           const bool fresh = slot != prev_slot;
           prev_slot = slot;
-          const uint32_t a_hi = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t a_lo = a_hi + IG_A_TILE_BYTES;
-          const uint32_t b_hi = a_hi + p.a_bytes;
-          const uint32_t b_lo = b_hi + p.b_bytes / 2;
+          constexpr uint32_t dhi = desc_hi32(1024, kLayoutSW128);
+          const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)stage * p.stage_bytes), 0);
+          const uint32_t a_lo = a_hi + (IG_A_TILE_BYTES >> 4);
+          const uint32_t b_hi = a_hi + (p.a_bytes >> 4);
+          const uint32_t b_lo = b_hi + (p.b_bytes >> 5);
+          const uint32_t fresh_corr = kb != 0;
 #pragma unroll
           for (int k = 0; k < IG_KC / 8; ++k) {
-            const uint32_t koff = k * 8 * 4;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
-            const uint64_t da_hi = make_smem_desc(a_hi + koff, 0, 1024, kLayoutSW128);
-            const uint64_t db_hi = make_smem_desc(b_hi + koff, 0, 1024, kLayoutSW128);
-            mma_tf32_ss(d_tmem, da_hi, db_hi, idesc, !(fresh && k == 0));
+            const uint32_t ko = (uint32_t)k * 2u;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
+            mma_tf32_lo32(d_tmem, a_hi + ko, b_hi + ko, dhi, idesc, (k == 0) ? (fresh ? 0u : 1u) : 1u);
             if (p.npass > 1) {
-              const uint64_t da_lo = make_smem_desc(a_lo + koff, 0, 1024, kLayoutSW128);
-              const uint64_t db_lo = make_smem_desc(b_lo + koff, 0, 1024, kLayoutSW128);
-              mma_tf32_ss(corr_tmem, da_hi, db_lo, idesc, (kb | k) != 0);
-              mma_tf32_ss(corr_tmem, da_lo, db_hi, idesc, 1);
+              mma_tf32_lo32(corr_tmem, a_hi + ko, b_lo + ko, dhi, idesc, (k == 0) ? fresh_corr : 1u);
+              mma_tf32_lo32(corr_tmem, a_lo + ko, b_hi + ko, dhi, idesc, 1u);
             }
           }
           mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire

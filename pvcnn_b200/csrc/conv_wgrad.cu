@@ -135,27 +135,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         }
         mbar_wait(&full_bar[stage], phase, p.err, 13);
         tc_fence_after();
+        // MN-major tf32 operands: 128B swizzle with 32-byte atoms (4-row repeat); LBO = stride between
+        // 32-channel blocks, SBO = stride between 4-row K groups; +1024 bytes (64 units) per 8-voxel k-step
+        constexpr uint32_t dhi = desc_hi32(512, kLayoutSW128Base32);
         const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t g_hi = st, g_lo = st + (uint32_t)p.chunks_out * WG_BLK;
-        const uint32_t a_base = st + p.g_bytes;
-        for (int g = 0; g < ngroups; ++g) {
-          const uint32_t a_hi = a_base + (uint32_t)(g * 4) * WG_BLK;
-          const uint32_t a_lo = a_base + (uint32_t)(G * 4 + g * 4) * WG_BLK;
-          const uint32_t d_main = tmem_base + (uint32_t)buf * tmem_cols_per_buf + (uint32_t)(g * p.block_n);
-          const uint32_t d_corr = d_main + (uint32_t)(G * p.block_n);
-          for (int ks = 0; ks < p.ksteps; ++ks) {
-            const uint32_t koff = (uint32_t)ks * 1024u;  // 8 voxel rows of 128 bytes per MMA
-            // MN-major tf32 operands use the 128B swizzle with 32-byte atoms (4-row repeat): LBO = stride
-            // between 32-channel blocks, SBO = stride between 4-row K groups (rows are 128 B apart)
-            const uint64_t da_hi = make_smem_desc(a_hi + koff, WG_BLK, 512, kLayoutSW128Base32);
-            const uint64_t db_hi = make_smem_desc(g_hi + koff, WG_BLK, 512, kLayoutSW128Base32);
-            const uint32_t accum = (pos_in_chain | ks) != 0;
-            mma_tf32_ss(d_main, da_hi, db_hi, idesc, accum);
-            if (p.npass > 1) {
-              const uint64_t da_lo = make_smem_desc(a_lo + koff, WG_BLK, 512, kLayoutSW128Base32);
-              const uint64_t db_lo = make_smem_desc(g_lo + koff, WG_BLK, 512, kLayoutSW128Base32);
-              mma_tf32_ss(d_corr, da_hi, db_lo, idesc, accum);
-              mma_tf32_ss(d_corr, da_lo, db_hi, idesc, 1);
+        const uint32_t g_hi = desc_lo32(st, WG_BLK);
+        const uint32_t g_lo = g_hi + (uint32_t)p.chunks_out * (WG_BLK >> 4);
+        const uint32_t a_base = g_hi + (p.g_bytes >> 4);
+        const uint32_t first = pos_in_chain == 0 ? 0u : 1u;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g < ngroups) {
+            const uint32_t a_hi = a_base + (uint32_t)(g * 4) * (WG_BLK >> 4);
+            const uint32_t a_lo = a_base + (uint32_t)(G * 4 + g * 4) * (WG_BLK >> 4);
+            const uint32_t d_main = tmem_base + (uint32_t)buf * tmem_cols_per_buf + (uint32_t)(g * p.block_n);
+            const uint32_t d_corr = d_main + (uint32_t)(G * p.block_n);
+            for (int ks = 0; ks < p.ksteps; ++ks) {
+              const uint32_t ko = (uint32_t)ks * 64u;
+              const uint32_t accum = ks == 0 ? first : 1u;
+              mma_tf32_lo32(d_main, a_hi + ko, g_hi + ko, dhi, idesc, accum);
+              if (p.npass > 1) {
+                mma_tf32_lo32(d_corr, a_hi + ko, g_lo + ko, dhi, idesc, accum);
+                mma_tf32_lo32(d_corr, a_lo + ko, g_hi + ko, dhi, idesc, 1u);
+              }
             }
           }
         }

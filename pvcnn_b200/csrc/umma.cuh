@@ -107,6 +107,28 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Issue-cost-minimal form: both descriptors share the constant high word; the low words (start address
+// >> 4 plus the caller's running offsets) are plain 32-bit registers.  One elected thread issues every
+// MMA of the CTA, so the instructions around each tcgen05.mma are on the critical path.
+__device__ __forceinline__ void mma_tf32_lo32(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// low / high words of a shared-memory descriptor (see make_smem_desc)
+__device__ __forceinline__ uint32_t desc_lo32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi32(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+
 // same, with an A-operand collector hint: 1 = fill (keep A for the next MMA), 2 = lastuse (reuse the kept A)
 __device__ __forceinline__ void mma_tf32_ss_coll(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                  uint32_t accumulate, int coll) {
