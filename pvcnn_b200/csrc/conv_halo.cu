@@ -45,7 +45,7 @@ struct HaloParams {
   const float *bias;
   float *out;
   int *err;
-  int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 2 A-collector reuse, 4 skip MMA3
+  int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 4 skip MMA3, 8 no A loads, 16 no B loads, 32 no epilogue stores
 };
 
 __global__ void __launch_bounds__(HC_THREADS, 1)
@@ -102,8 +102,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         for (int ph = 0; ph < nphases; ++ph) {
           const int dz = ph / p.kchunks - 1, cc = ph % p.kchunks;
           mbar_wait(&a_empty[abuf], aphase ^ 1, p.err, 21);
-          mbar_arrive_expect_tx(&a_full[abuf], p.a_bytes);
-          tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
+          if (p.exp & 8) {  // experiment: no activation traffic
+            mbar_arrive(&a_full[abuf]);
+          } else {
+            mbar_arrive_expect_tx(&a_full[abuf], p.a_bytes);
+            tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
+          }
           if (++abuf == 2) { abuf = 0; aphase ^= 1; }
         }
       }
@@ -121,9 +125,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
             const int tap = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
             mbar_wait(&b_empty[bst], bphase ^ 1, p.err, 22);
             uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
-            mbar_arrive_expect_tx(&b_full[bst], three ? 2 * p.b_bytes : p.b_bytes);
-            tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * HC_KC, 0, tap);
-            if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * HC_KC, 0, tap);
+            if (p.exp & 16) {  // experiment: no weight traffic
+              mbar_arrive(&b_full[bst]);
+            } else {
+              mbar_arrive_expect_tx(&b_full[bst], three ? 2 * p.b_bytes : p.b_bytes);
+              tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * HC_KC, 0, tap);
+              if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * HC_KC, 0, tap);
+            }
             if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
           }
         }
@@ -155,9 +163,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
           const uint32_t slot_col = ph < half_phase ? 0u : bn;
           const uint32_t fresh_main = ((ph == 0) || (ph == half_phase)) ? 0u : 1u;
           const uint32_t fresh_corr = ph == 0 ? 0u : 1u;
+          // software-pipelined barrier polling: the try_wait for the NEXT weight tile is issued before this
+          // tile's MMAs, so its latency hides behind the MMA issue instead of sitting on the critical path
+          bool b_ready = mbar_try_wait(&b_full[bst], bphase);
 #pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {
-            mbar_wait(&b_full[bst], bphase, p.err, 25);
+            if (!b_ready) mbar_wait(&b_full[bst], bphase, p.err, 25);
+            {
+              const int nst = (bst + 1 == HC_BSTAGES) ? 0 : bst + 1;
+              const uint32_t nph = (bst + 1 == HC_BSTAGES) ? (bphase ^ 1) : bphase;
+              b_ready = mbar_try_wait(&b_full[nst], nph);
+            }
             tc_fence_after();
             const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
             const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += w[i];
           }
-          if (valid && c0 < p.cout) {
+          if (valid && c0 < p.cout && !(p.exp & 32)) {
             if (p.bias) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)

@@ -20,7 +20,7 @@
 namespace pvb {
 using namespace umma;
 
-constexpr int WG_THREADS = 384;       // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 drain
+constexpr int WG_THREADS = 512;       // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 drain, warps 12-15 lo converters
 constexpr int WG_ROWS = 32;           // voxels per k-tile (box rows), 4 MMA K-steps
 constexpr uint32_t WG_BLK = WG_ROWS * 128;  // bytes of one [32 rows x 32 channels] block
 constexpr int WG_STAGES = 2;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                       const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
                       const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint64_t full_bar[WG_STAGES], ready_bar[WG_STAGES], empty_bar[WG_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     if (p.npass > 1) { prefetch_tensormap(&map_x_lo); prefetch_tensormap(&map_g_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 256); }
     fence_barrier_init();
   }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      const uint32_t tx_bytes = p.box_bytes * passes * (uint32_t)(p.chunks_out + nab);
+      const uint32_t tx_bytes = p.box_bytes * (uint32_t)(p.chunks_out + nab);  // lo halves are computed in-kernel
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = 0; t < my_tiles; ++t) {
@@ -102,8 +102,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         for (int cc = 0; cc < p.chunks_out; ++cc) {
           tma_load_5d(st + (size_t)cc * WG_BLK, &map_g_hi, &full_bar[stage], cc * 32, z0, y0, x0, b);
-          if (p.npass > 1)
-            tma_load_5d(st + (size_t)(p.chunks_out + cc) * WG_BLK, &map_g_lo, &full_bar[stage], cc * 32, z0, y0, x0, b);
         }
         uint8_t *sa = st + p.g_bytes;
         for (int a = 0; a < nab; ++a) {
@@ -112,9 +110,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           int dx = 0, dy = 0, dz = 0;
           if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
           tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], cc * 32, z0 + dz, y0 + dy, x0 + dx, b);
-          if (p.npass > 1)
-            tma_load_5d(sa + (size_t)(G * 4 + a) * WG_BLK, &map_x_lo, &full_bar[stage], cc * 32, z0 + dz, y0 + dy,
-                        x0 + dx, b);
         }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -133,7 +128,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1, p.err, 12);
           tc_fence_after();
         }
-        mbar_wait(&full_bar[stage], phase, p.err, 13);
+        mbar_wait(&ready_bar[stage], phase, p.err, 13);
         tc_fence_after();
         // MN-major tf32 operands: 128B swizzle with 32-byte atoms (4-row repeat); LBO = stride between
         // 32-channel blocks, SBO = stride between 4-row K groups; +1024 bytes (64 units) per 8-voxel k-step
@@ -168,6 +163,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           ++chain;
         }
       }
+    }
+  } else if (warp >= 12) {
+    // ================================ converters: lo = x - trunc_tf32(x) ================================
+    // (activations and gradients carry no `lo` tensors in HBM; elementwise on the swizzled bytes)
+    const int tid = threadIdx.x - 12 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = 0; t < my_tiles; ++t) {
+      mbar_wait(&full_bar[stage], phase, p.err, 15);
+      if (p.npass > 1) {
+        uint8_t *st = smem + (size_t)stage * p.stage_bytes;
+        const int ng16 = p.chunks_out * (int)(WG_BLK >> 4), na16 = nab * (int)(WG_BLK >> 4);
+        const float4 *g_src = reinterpret_cast<const float4 *>(st);
+        float4 *g_dst = reinterpret_cast<float4 *>(st + (size_t)p.chunks_out * WG_BLK);
+        const float4 *a_src = reinterpret_cast<const float4 *>(st + p.g_bytes);
+        float4 *a_dst = reinterpret_cast<float4 *>(st + p.g_bytes + (size_t)(G * 4) * WG_BLK);
+        for (int i = tid; i < ng16 + na16; i += 128) {
+          const bool is_g = i < ng16;
+          const float4 v = is_g ? g_src[i] : a_src[i - ng16];
+          float4 l;
+          l.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+          l.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+          l.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+          l.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+          if (is_g) g_dst[i] = l; else a_dst[i - ng16] = l;
+        }
+        fence_proxy_async();
+      }
+      mbar_arrive(&ready_bar[stage]);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ drain / epilogue ================================
@@ -243,7 +268,8 @@ static int *g_wg_err = nullptr;
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
-  PVB_CHECK_ARG(x_hi && g_hi && dw && (npass == 1 || (x_lo && g_lo)) && ldx % 4 == 0 && ldg % 4 == 0);
+  (void)x_lo; (void)g_lo;  // accepted for ABI stability; the kernel derives lo = x - trunc_tf32(x) itself
+  PVB_CHECK_ARG(x_hi && g_hi && dw && ldx % 4 == 0 && ldg % 4 == 0);
   if (cout > 128) return PVCNN_E_UNSUPPORTED;  // TODO(round 2): N tiling for wide SharedMLPs
   if (!g_wg_err) {
     PVB_CUDA(cudaMalloc((void **)&g_wg_err, sizeof(int)));
@@ -281,9 +307,9 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   CUtensorMap mx_hi, mx_lo, mg_hi, mg_lo;
   int rc;
   if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  if ((rc = encode_map_5d_cl(&mx_lo, npass > 1 ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mx_lo, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  if ((rc = encode_map_5d_cl(&mg_lo, npass > 1 ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_lo, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   const size_t smem = (size_t)WG_STAGES * p.stage_bytes + 1024;
   if (p.groups_per_cta == 2) {
     PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
