@@ -290,12 +290,23 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
 int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsigned long long *gdim,
                        const unsigned long long *gstride_bytes, const unsigned *box, int swizzle_kind);  // conv_igemm.cu
 
+// shape envelope of this kernel (also used by the pipeline to decide whether `lo` grids are needed at all)
+bool conv_halo_supported(int sx, int sy, int sz, int cout) {
+  (void)sy;
+  if (!(sz % 8 == 0 && sz <= 128 && 128 % sz == 0 && cout <= 64 && sx >= 2)) return false;
+  const int ty = 128 / sz;
+  const size_t a_bytes = (size_t)sz * (ty + 2) * (HC_TX + 2) * HC_KC * 4;
+  const int bn = max(16, ((cout + 15) / 16) * 16);
+  const size_t smem = 2 * a_bytes * 2 + (size_t)HC_BSTAGES * bn * HC_KC * 4 * 2 + 1024;
+  return a_bytes % 1024 == 0 && smem <= 227 * 1024 - 512;
+}
+
 static int *g_halo_err = nullptr;
 
 // Returns PVCNN_E_UNSUPPORTED when the shape is outside this kernel's envelope (caller falls back to v1).
 int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
                      const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream) {
-  if (!(sz % 8 == 0 && sz <= 128 && 128 % sz == 0 && cout <= 64 && sx >= 2)) return PVCNN_E_UNSUPPORTED;
+  if (!conv_halo_supported(sx, sy, sz, cout)) return PVCNN_E_UNSUPPORTED;
   PVB_CHECK_ARG(a && w_hi && out && (npass == 1 || w_lo) && lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0);
   if (!g_halo_err) {
     PVB_CUDA(cudaMalloc((void **)&g_halo_err, sizeof(int)));

@@ -385,7 +385,7 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
                  int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                  int npass, cudaStream_t stream) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && k > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
-  PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || (a_lo && w_lo)));
+  PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || w_lo));
   PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
   if (ntaps == 27) {
     // second-generation kernel (smem halo reuse, in-kernel lo) when the shape is inside its envelope
@@ -396,6 +396,7 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
       if (rc != PVCNN_E_UNSUPPORTED) return rc;
     }
   }
+  PVB_CHECK_ARG(npass == 1 || a_lo);  // the v1 kernel reads a materialised lo tensor
   if (!g_err_flag) {
     PVB_CUDA(cudaMalloc((void **)&g_err_flag, sizeof(int)));
     PVB_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));

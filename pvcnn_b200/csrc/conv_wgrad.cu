@@ -23,7 +23,7 @@ using namespace umma;
 constexpr int WG_THREADS = 512;       // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 drain, warps 12-15 lo converters
 constexpr int WG_ROWS = 32;           // voxels per k-tile (box rows), 4 MMA K-steps
 constexpr uint32_t WG_BLK = WG_ROWS * 128;  // bytes of one [32 rows x 32 channels] block
-constexpr int WG_STAGES = 2;
+constexpr int WG_MAX_STAGES = 4;      // TMA ring depth (bytes in flight hide the ~3000-cycle load latency)
 constexpr int WG_DRAIN_TILES = 16;    // k-tiles per TMEM chain: 16 * 4 = 64 MMAs
 
 struct WgradParams {
@@ -42,6 +42,7 @@ struct WgradParams {
   int ksteps;               // rows / 8
   uint32_t stage_bytes, g_bytes;  // g_bytes: bytes of the gY part of a stage (hi [+lo])
   uint32_t box_bytes;             // bytes one TMA box really delivers (rows * 128)
+  int stages;
   float *dw;                // [cout][cin][ntaps], zero-initialised by the launcher
   int *err;
 };
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
                       const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
                       const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[WG_STAGES], ready_bar[WG_STAGES], empty_bar[WG_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint64_t full_bar[WG_MAX_STAGES], ready_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     if (p.npass > 1) { prefetch_tensormap(&map_x_lo); prefetch_tensormap(&map_g_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 256); }
     fence_barrier_init();
   }
@@ -92,11 +93,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = 0; t < my_tiles; ++t) {
-        long long kt = split + t * p.ksplit;
-        const int z0 = (int)(kt % p.tz) * p.bz; kt /= p.tz;
-        const int y0 = (int)(kt % p.ty) * p.by; kt /= p.ty;
-        const int x0 = (int)(kt % p.sx); kt /= p.sx;
-        const int b = (int)kt;
+        int kt = (int)(split + t * p.ksplit);  // num_ktiles < 2^31 (checked by the launcher)
+        const int z0 = (kt % p.tz) * p.bz; kt /= p.tz;
+        const int y0 = (kt % p.ty) * p.by; kt /= p.ty;
+        const int x0 = kt % p.sx; kt /= p.sx;
+        const int b = kt;
         mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
           tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], cc * 32, z0 + dz, y0 + dy, x0 + dx, b);
         }
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           }
         }
         mma_commit(&empty_bar[stage]);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (pos_in_chain == WG_DRAIN_TILES - 1 || t == my_tiles - 1) {
           mma_commit(&tmem_full_bar[buf]);
           ++chain;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         fence_proxy_async();
       }
       mbar_arrive(&ready_bar[stage]);
-      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ drain / epilogue ================================
@@ -290,7 +291,9 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   p.chunks_out = ceil_div(cout, 32);
   p.n_ablocks = ntaps * p.chunks_in;
   p.block_n = max(16, ((cout + 15) / 16) * 16);
-  p.groups_per_cta = p.block_n <= 64 ? 2 : 1;
+  // one M=128 operand group per CTA: a 48 KB stage (hi + in-kernel lo) allows a 4-deep TMA ring, which
+  // matters more than operand reuse here (the 2-group / 2-stage variant was load-latency bound: 1.27 ms)
+  p.groups_per_cta = 1;
   const int ngroups = ceil_div(p.n_ablocks, 4);
   p.num_sets = ceil_div(ngroups, p.groups_per_cta);
   p.ksplit = max(1, kNumSMs / p.num_sets);
@@ -302,6 +305,8 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   p.box_bytes = (uint32_t)rows * 128u;
   p.dw = dw;
   p.err = g_wg_err;
+  p.stages = min(WG_MAX_STAGES, (int)((227 * 1024 - 2048) / p.stage_bytes));
+  PVB_CHECK_ARG(p.stages >= 2 && p.num_ktiles < (1LL << 31));
   PVB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * cin * ntaps, s));
 
   CUtensorMap mx_hi, mx_lo, mg_hi, mg_lo;
@@ -310,7 +315,7 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   if ((rc = encode_map_5d_cl(&mx_lo, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_lo, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  const size_t smem = (size_t)WG_STAGES * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   if (p.groups_per_cta == 2) {
     PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PVB_LAUNCH(conv_wgrad_kernel<2>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);

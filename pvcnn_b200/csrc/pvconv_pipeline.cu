@@ -2,6 +2,8 @@
 // Orchestrates the channels-last kernels of fused_ops.cu around the tcgen05 GEMMs of
 // conv_igemm.cu / conv_wgrad.cu.  See include/pvcnn_b200.h for the contract and DESIGN.md for the
 // dataflow; reference: modules/pvconv.py:33-39 (forward wiring) and torch autograd (backward).
+#include <cstdlib>
+
 #include "fused_ops.cuh"
 
 namespace pvb {
@@ -10,6 +12,17 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
                  int npass, cudaStream_t stream);
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s);
+
+bool conv_halo_supported(int sx, int sy, int sz, int cout);  // conv_halo.cu
+
+// The halo conv kernel and the wgrad kernel derive lo = x - trunc_tf32(x) on the fly; `lo` GRID tensors are
+// only materialised when a conv of this block has to run on the v1 kernel (odd resolutions, > 64 channels).
+static bool needs_grid_lo(const pvcnn_pvconv_desc *d) {
+  if (d->npass == 1) return false;
+  const char *e = getenv("PVCNN_B200_CONV");
+  if (e && e[0] == 'v' && e[1] == '1') return true;
+  return !(conv_halo_supported(d->r, d->r, d->r, d->cout) && conv_halo_supported(d->r, d->r, d->r, d->cin));
+}
 
 static inline int pad4(int x) { return (x + 3) / 4 * 4; }
 static inline int ld32(int x) { return (x + 31) / 32 * 32; }
@@ -58,6 +71,8 @@ extern "C" {
 
 long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d) { return wprep_layout(d).total; }
 
+int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d) { return needs_grid_lo(d) ? 1 : 0; }
+
 long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d) {
   const long long co = pad4(d->cout > d->cin ? d->cout : d->cin);
   const long long blocks_pts = (long long)d->b * ((d->n + 31) / 32);
@@ -73,7 +88,10 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   const int b = d->b, n = d->n, r = d->r, r3 = r * r * r;
   const int ci = pad4(d->cin), co = pad4(d->cout);
   const long long Mv = (long long)b * r3, Mp = (long long)b * n;
-  const bool lo = d->npass > 1;
+  const bool lo = d->npass > 1;        // point-set lo tensors (1x1 GEMM runs on the v1 kernel)
+  const bool glo = needs_grid_lo(d);   // grid lo tensors
+  PVB_CHECK_ARG(!lo || (ws->fcl_lo != nullptr));
+  PVB_CHECK_ARG(!glo || (ws->g0_lo && ws->z1_lo));
   const WPrep W = wprep_layout(d);
   float *wp = ws->wprep;
   int nblk = 0;
@@ -85,7 +103,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
   PVB_TRY(launch_memset_f32(ws->g0, Mv * ci, s));
   PVB_TRY(launch_voxelize_cl(b, n, r3, ci, ws->ind, ws->cnt, ws->fcl, ws->g0, s));
-  if (lo) {
+  if (glo) {
     PVB_TRY(launch_memset_f32(ws->g0_lo, Mv * ci, s));
     PVB_TRY(launch_grid_lo_at_points(b, n, r3, ci, ws->ind, ws->g0, ws->g0_lo, s));
   }
@@ -105,7 +123,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   } else {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g1, prm->be1, prm->rm1, prm->rv1, bn1, s));
   }
-  PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, lo ? ws->z1_lo : nullptr, s));
+  PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, glo ? ws->z1_lo : nullptr, s));
   // 5. conv2 -> BN2 statistics (BN2-apply + LeakyReLU are folded into the devoxelize gather)
   PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, wp + W.w2f, wp + W.w2f + W.n2f,
                        ld32(d->cout), prm->b2, ws->y2, co, d->npass, s));
@@ -140,6 +158,8 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   const int ci = pad4(d->cin), co = pad4(d->cout);
   const long long Mv = (long long)b * r3, Mp = (long long)b * n;
   const bool lo = d->npass > 1;
+  const bool glo = needs_grid_lo(d);
+  PVB_CHECK_ARG(!glo || (ws->gy2_lo && ws->gy1_lo));
   const WPrep W = wprep_layout(d);
   float *wp = ws->wprep;
   BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
@@ -162,7 +182,7 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 6 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->bp, S + 6 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_TRY(launch_bn_bwd_apply(Mv, co, 0, d->slope, ws->d2, ws->y2, bn2, S + 2 * co, S + 3 * co, ws->gy2,
-                              lo ? ws->gy2_lo : nullptr, ws->partials, &nblk, s));
+                              glo ? ws->gy2_lo : nullptr, ws->partials, &nblk, s));
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 7 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->b2, S + 7 * co, cb, cudaMemcpyDeviceToDevice, s));
   // 3. data-gradient weights
@@ -186,7 +206,7 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_CUDA(cudaMemcpyAsync(gr->be1, S + 4 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_CUDA(cudaMemcpyAsync(gr->g1, S + 5 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_TRY(launch_bn_bwd_apply(Mv, co, 1, d->slope, gz1, ws->y1, bn1, S + 4 * co, S + 5 * co, ws->gy1,
-                              lo ? ws->gy1_lo : nullptr, ws->partials, &nblk, s));
+                              glo ? ws->gy1_lo : nullptr, ws->partials, &nblk, s));
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 8 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
   // 7. conv1: wgrad, dgrad (into the d2 buffer again: gz1 is dead)

@@ -83,13 +83,16 @@ class _Plan:
         ci, co = _pad4(desc.cin), _pad4(desc.cout)
         mv, mp = b * r ** 3, b * n
         lo = desc.npass > 1
+        self.grid_lo = bool(lib.pvcnn_pvconv_needs_grid_lo(ctypes.byref(desc)))
         f = lambda numel: torch.empty(int(numel), dtype=torch.float32, device=device)
         i = lambda numel: torch.empty(int(numel), dtype=torch.int32, device=device)
         alloc = {}
         saved = dict(nc=b * 3 * n, fcl=mp * ci, g0=mv * ci, y1=mv * co, z1=mv * co, y2=mv * co, p=mp * co,
                      coef=12 * co)
         if lo:
-            saved.update(fcl_lo=mp * ci, g0_lo=mv * ci, z1_lo=mv * co)
+            saved.update(fcl_lo=mp * ci)
+        if self.grid_lo:
+            saved.update(g0_lo=mv * ci, z1_lo=mv * co)
         for k, v in saved.items():
             # activations needed by the backward belong to this call; in inference they are scratch
             alloc[k] = f(v) if need_backward else _scratch("fwd_" + k, v, device)
@@ -111,7 +114,9 @@ class _Plan:
         lo = d.npass > 1
         sizes = dict(ga=mp * co, gpp=mp * co, gfpt=mp * ci, d2=mv * max(ci, co), gy2=mv * co, gy1=mv * co)
         if lo:
-            sizes.update(gpp_lo=mp * co, gy2_lo=mv * co, gy1_lo=mv * co)
+            sizes.update(gpp_lo=mp * co)
+        if self.grid_lo:
+            sizes.update(gy2_lo=mv * co, gy1_lo=mv * co)
         for k, v in sizes.items():
             self.t[k] = _scratch("bwd_" + k, v, self.device)
 
