@@ -134,6 +134,8 @@ PVCNN_API int pvcnn_igemm_conv(int nb, int sx, int sy, int sz, int k, int cout, 
                                const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                                int npass, void *stream);
 PVCNN_API int pvcnn_igemm_last_error(int *host_code);
+/* PVCNN_STALL_PROFILE=1: stall-cycle counters of CTA 0 of the last tensor-core kernel (diagnostic) */
+PVCNN_API int pvcnn_stall_profile_read(long long *host8);
 
 /* dW[co][ci][tap] = sum_v g[v][co] * x[v+off(tap)][ci]   (weight gradient of pvcnn_igemm_conv; torch
  * weight layout).  x: layer input [nb,sx,sy,sz,ldx], g: output gradient [nb,sx,sy,sz,ldg]; lo

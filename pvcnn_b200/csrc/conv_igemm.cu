@@ -341,6 +341,22 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
                      const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass,
                      cudaStream_t stream);  // conv_halo.cu
 
+// Optional device buffer [8] of stall-cycle counters written by CTA 0 of the tensor-core kernels when
+// PVCNN_STALL_PROFILE=1 (tools/stall_profile.py reads it back through pvcnn_stall_profile_read).
+long long *stall_profile_buffer() {
+  static long long *buf = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char *e = getenv("PVCNN_STALL_PROFILE");
+    if (e && e[0] == '1' && cudaMalloc((void **)&buf, 8 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(buf, 0, 8 * sizeof(long long));
+    else
+      buf = nullptr;
+  }
+  return buf;
+}
+
 static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps
 
 }  // namespace pvb
@@ -474,6 +490,12 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
 }  // namespace pvb
 
 extern "C" {
+int pvcnn_stall_profile_read(long long *host8) {
+  long long *b = pvb::stall_profile_buffer();
+  if (!b) return PVCNN_E_UNSUPPORTED;
+  return (int)cudaMemcpy(host8, b, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+}
+
 /* Diagnostic: code of the mbarrier wait that starved (0 = none); readable after a trapped launch only
  * through a fresh context, so mainly useful under compute-sanitizer / in bring-up tests. */
 int pvcnn_igemm_last_error(int *host_code) {

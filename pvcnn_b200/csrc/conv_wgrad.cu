@@ -45,6 +45,7 @@ struct WgradParams {
   int stages;
   float *dw;                // [cout][cin][ntaps], zero-initialised by the launcher
   int *err;
+  long long *dbg;           // optional [8] stall-cycle counters of CTA 0 (PVCNN_STALL_PROFILE)
 };
 
 template <int G>
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     // ================================ TMA producer ================================
     if (elect_one()) {
       const uint32_t tx_bytes = p.box_bytes * (uint32_t)(p.chunks_out + nab);  // lo halves are computed in-kernel
+      long long stall = 0;
+      const long long t_begin = clock64();
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = 0; t < my_tiles; ++t) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const int y0 = (kt % p.ty) * p.by; kt /= p.ty;
         const int x0 = kt % p.sx; kt /= p.sx;
         const int b = kt;
-        mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
+        mbar_wait_t(&empty_bar[stage], phase ^ 1, p.err, 11, stall);
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         for (int cc = 0; cc < p.chunks_out; ++cc) {
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = stall; p.dbg[1] = clock64() - t_begin; }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -122,14 +126,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       int chain = 0;  // index of the current TMEM chain
+      long long stall_t = 0, stall_r = 0;
+      const long long t_begin = clock64();
       for (long long t = 0; t < my_tiles; ++t) {
         const int pos_in_chain = (int)(t % WG_DRAIN_TILES);
         const int buf = chain & 1;
         if (pos_in_chain == 0) {
-          mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1, p.err, 12);
+          mbar_wait_t(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1, p.err, 12, stall_t);
           tc_fence_after();
         }
-        mbar_wait(&ready_bar[stage], phase, p.err, 13);
+        mbar_wait_t(&ready_bar[stage], phase, p.err, 13, stall_r);
         tc_fence_after();
         // MN-major tf32 operands: 128B swizzle with 32-byte atoms (4-row repeat); LBO = stride between
         // 32-channel blocks, SBO = stride between 4-row K groups; +1024 bytes (64 units) per 8-voxel k-step
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           ++chain;
         }
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[2] = stall_r; p.dbg[3] = stall_t; p.dbg[4] = clock64() - t_begin; }
     }
   } else if (warp >= 12) {
     // ================================ converters: lo = x - trunc_tf32(x) ================================
@@ -171,8 +178,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     const int tid = threadIdx.x - 12 * 32;
     int stage = 0;
     uint32_t phase = 0;
+    long long stall_c = 0;
+    const long long t_begin = clock64();
     for (long long t = 0; t < my_tiles; ++t) {
-      mbar_wait(&full_bar[stage], phase, p.err, 15);
+      mbar_wait_t(&full_bar[stage], phase, p.err, 15, stall_c);
       if (p.npass > 1) {
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         const int ng16 = p.chunks_out * (int)(WG_BLK >> 4), na16 = nab * (int)(WG_BLK >> 4);
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       mbar_arrive(&ready_bar[stage]);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (p.dbg && blockIdx.x == 0 && tid == 0) { p.dbg[5] = stall_c; p.dbg[6] = clock64() - t_begin; }
   } else if (warp >= 4) {
     // ================================ drain / epilogue ================================
     const int e = warp - 4;
@@ -263,6 +273,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, int sx, int sy, int sz, int bz, int by,
                      int bx, bool atom32);  // conv_igemm.cu
 
+long long *stall_profile_buffer();  // conv_igemm.cu
+
 static int *g_wg_err = nullptr;
 
 // x: layer input [nb,sx,sy,sz,ldx] (cin valid), g: output gradient [nb,sx,sy,sz,ldg] (cout valid)
@@ -305,6 +317,7 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   p.box_bytes = (uint32_t)rows * 128u;
   p.dw = dw;
   p.err = g_wg_err;
+  p.dbg = pvb::stall_profile_buffer();
   p.stages = min(WG_MAX_STAGES, (int)((227 * 1024 - 2048) / p.stage_bytes));
   PVB_CHECK_ARG(p.stages >= 2 && p.num_ktiles < (1LL << 31));
   PVB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * cin * ntaps, s));
