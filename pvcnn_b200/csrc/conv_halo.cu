@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         const int y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
         const int x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
         const int b = u;
+        int dz = -1, cc = 0;
         for (int ph = 0; ph < nphases; ++ph) {
-          const int dz = ph / p.kchunks - 1, cc = ph % p.kchunks;
           mbar_wait(&a_empty[abuf], aphase ^ 1, p.err, 21);
           if (p.exp & 8) {  // experiment: no activation traffic
             mbar_arrive(&a_full[abuf]);
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
             tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
           }
           if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+          if (++cc == p.kchunks) { cc = 0; ++dz; }
         }
       }
     }
@@ -118,8 +119,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
       int bst = 0;
       uint32_t bphase = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int dz = -1, cc = 0;
         for (int ph = 0; ph < nphases; ++ph) {
-          const int dz = ph / p.kchunks - 1, cc = ph % p.kchunks;
+#pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {  // taps (dx, dy) of this dz
             const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
             const int tap = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
             }
             if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
           }
+          if (++cc == p.kchunks) { cc = 0; ++dz; }
         }
       }
     }

@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
         const int y0 = (mt % p.ty) * p.by; mt /= p.ty;
         const int x0 = (mt % p.tx) * p.bx; mt /= p.tx;
         const int b = mt;
+        int tap = 0, cc = 0;  // advanced incrementally: no runtime division on the producer's critical path
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.cin_chunks, cc = kb - tap * p.cin_chunks;
           int dx = 0, dy = 0, dz = 0;
           if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
           mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
                         tap);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++cc == p.cin_chunks) { cc = 0; ++tap; }
         }
       }
     }

@@ -84,8 +84,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  // number of k-tiles this CTA walks
-  const long long my_tiles = p.num_ktiles > split ? (p.num_ktiles - split + p.ksplit - 1) / p.ksplit : 0;
+  // contiguous range of k-tiles walked by this CTA (coordinates advance incrementally: no div/mod per stage)
+  const long long per_cta = (p.num_ktiles + p.ksplit - 1) / p.ksplit;
+  const long long kt_begin = (long long)split * per_cta;
+  const long long my_tiles = max(0LL, min(p.num_ktiles, kt_begin + per_cta) - kt_begin);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -95,27 +97,37 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       const long long t_begin = clock64();
       int stage = 0;
       uint32_t phase = 0;
+      // this CTA's operand blocks never change: decode (tap, chunk) -> box offsets once
+      int blk_c[G * 4], blk_dx[G * 4], blk_dy[G * 4], blk_dz[G * 4];
+#pragma unroll
+      for (int a = 0; a < G * 4; ++a) {
+        const int ab = min(ab0 + a, p.n_ablocks - 1);
+        const int tap = ab / p.chunks_in;
+        blk_c[a] = (ab - tap * p.chunks_in) * 32;
+        blk_dx[a] = p.ntaps == 27 ? tap / 9 - 1 : 0;
+        blk_dy[a] = p.ntaps == 27 ? (tap / 3) % 3 - 1 : 0;
+        blk_dz[a] = p.ntaps == 27 ? tap % 3 - 1 : 0;
+      }
+      int kt = (int)kt_begin;
+      int tzi = kt % p.tz; kt /= p.tz;
+      int tyi = kt % p.ty; kt /= p.ty;
+      int x0 = kt % p.sx; kt /= p.sx;
+      int b = kt;
       for (long long t = 0; t < my_tiles; ++t) {
-        int kt = (int)(split + t * p.ksplit);  // num_ktiles < 2^31 (checked by the launcher)
-        const int z0 = (kt % p.tz) * p.bz; kt /= p.tz;
-        const int y0 = (kt % p.ty) * p.by; kt /= p.ty;
-        const int x0 = kt % p.sx; kt /= p.sx;
-        const int b = kt;
+        const int z0 = tzi * p.bz, y0 = tyi * p.by;
         mbar_wait_t(&empty_bar[stage], phase ^ 1, p.err, 11, stall);
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        for (int cc = 0; cc < p.chunks_out; ++cc) {
+        for (int cc = 0; cc < p.chunks_out; ++cc)
           tma_load_5d(st + (size_t)cc * WG_BLK, &map_g_hi, &full_bar[stage], cc * 32, z0, y0, x0, b);
-        }
         uint8_t *sa = st + p.g_bytes;
-        for (int a = 0; a < nab; ++a) {
-          const int ab = ab0 + a;
-          const int tap = ab / p.chunks_in, cc = ab - tap * p.chunks_in;
-          int dx = 0, dy = 0, dz = 0;
-          if (p.ntaps == 27) { dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1; }
-          tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], cc * 32, z0 + dz, y0 + dy, x0 + dx, b);
-        }
+#pragma unroll
+        for (int a = 0; a < G * 4; ++a)
+          if (a < nab)
+            tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], blk_c[a], z0 + blk_dz[a], y0 + blk_dy[a],
+                        x0 + blk_dx[a], b);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++tzi == p.tz) { tzi = 0; if (++tyi == p.ty) { tyi = 0; if (++x0 == p.sx) { x0 = 0; ++b; } } }
       }
       if (p.dbg && blockIdx.x == 0) { p.dbg[0] = stall; p.dbg[1] = clock64() - t_begin; }
     }
@@ -189,15 +201,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         float4 *g_dst = reinterpret_cast<float4 *>(st + (size_t)p.chunks_out * WG_BLK);
         const float4 *a_src = reinterpret_cast<const float4 *>(st + p.g_bytes);
         float4 *a_dst = reinterpret_cast<float4 *>(st + p.g_bytes + (size_t)(G * 4) * WG_BLK);
-        for (int i = tid; i < ng16 + na16; i += 128) {
-          const bool is_g = i < ng16;
-          const float4 v = is_g ? g_src[i] : a_src[i - ng16];
-          float4 l;
-          l.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-          l.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-          l.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-          l.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-          if (is_g) g_dst[i] = l; else a_dst[i - ng16] = l;
+        const int total16 = ng16 + na16;
+        for (int i0 = tid; i0 < total16; i0 += 4 * 128) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            if (i < total16) v[u] = (i < ng16) ? g_src[i] : a_src[i - ng16];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            if (i < total16) {
+              float4 l;
+              l.x = __fsub_rn(v[u].x, __uint_as_float(__float_as_uint(v[u].x) & 0xFFFFE000u));
+              l.y = __fsub_rn(v[u].y, __uint_as_float(__float_as_uint(v[u].y) & 0xFFFFE000u));
+              l.z = __fsub_rn(v[u].z, __uint_as_float(__float_as_uint(v[u].z) & 0xFFFFE000u));
+              l.w = __fsub_rn(v[u].w, __uint_as_float(__float_as_uint(v[u].w) & 0xFFFFE000u));
+              if (i < ng16) g_dst[i] = l; else a_dst[i - ng16] = l;
+            }
+          }
         }
         fence_proxy_async();
       }

@@ -65,8 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *e
 
 // wait + accumulate the stalled cycles into `acc` (pipeline-stall profile, see tools/stall_profile.py)
 __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, int *err, int code, long long &acc) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  const long long t0 = clock64();  // try_wait itself may suspend the thread, so time the whole wait
   mbar_wait(bar, parity, err, code);
   acc += clock64() - t0;
 }
