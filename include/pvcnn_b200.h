@@ -195,9 +195,8 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
   float *gy2, *gy2_lo, *gy1, *gy1_lo; /* Mv*co */
 } pvcnn_pvconv_ws;
 
-/* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided: only if one of the
- * block's convolutions falls outside the halo kernel's envelope (the halo and wgrad kernels compute
- * lo = x - trunc_tf32(x) on the fly).  Otherwise those pointers may be NULL. */
+/* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided (3xTF32 mode: the weight-
+ * gradient kernel TMA-loads them); otherwise those pointers may be NULL. */
 PVCNN_API int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d);

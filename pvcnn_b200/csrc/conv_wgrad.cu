@@ -14,6 +14,8 @@
 //     warps drain each finished chain into fp32 REGISTER accumulators (round-to-nearest adds) while the
 //     MMA warp fills the other TMEM buffer.  The 3xTF32 correction terms use their own accumulators.
 //   * split-K over the SMs; partial results are combined with fp32 reductions into the zeroed dW.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -43,6 +45,7 @@ struct WgradParams {
   uint32_t stage_bytes, g_bytes;  // g_bytes: bytes of the gY part of a stage (hi [+lo])
   uint32_t box_bytes;             // bytes one TMA box really delivers (rows * 128)
   int stages;
+  int lo_in_kernel;               // 1: converter warps derive lo from hi in shared memory; 0: lo tensors are TMA-loaded
   float *dw;                // [cout][cin][ntaps], zero-initialised by the launcher
   int *err;
   long long *dbg;           // optional [8] stall-cycle counters of CTA 0 (PVCNN_STALL_PROFILE)
@@ -92,7 +95,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      const uint32_t tx_bytes = p.box_bytes * (uint32_t)(p.chunks_out + nab);  // lo halves are computed in-kernel
+      const uint32_t tx_bytes = p.box_bytes * (uint32_t)(p.chunks_out + nab) * ((p.npass > 1 && !p.lo_in_kernel) ? 2u : 1u);
+      const bool load_lo = p.npass > 1 && !p.lo_in_kernel;
       long long stall = 0;
       const long long t_begin = clock64();
       int stage = 0;
@@ -118,14 +122,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         mbar_wait_t(&empty_bar[stage], phase ^ 1, p.err, 11, stall);
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-        for (int cc = 0; cc < p.chunks_out; ++cc)
+        for (int cc = 0; cc < p.chunks_out; ++cc) {
           tma_load_5d(st + (size_t)cc * WG_BLK, &map_g_hi, &full_bar[stage], cc * 32, z0, y0, x0, b);
+          if (load_lo)
+            tma_load_5d(st + (size_t)(p.chunks_out + cc) * WG_BLK, &map_g_lo, &full_bar[stage], cc * 32, z0, y0, x0, b);
+        }
         uint8_t *sa = st + p.g_bytes;
 #pragma unroll
         for (int a = 0; a < G * 4; ++a)
-          if (a < nab)
+          if (a < nab) {
             tma_load_5d(sa + (size_t)a * WG_BLK, &map_x_hi, &full_bar[stage], blk_c[a], z0 + blk_dz[a], y0 + blk_dy[a],
                         x0 + blk_dx[a], b);
+            if (load_lo)
+              tma_load_5d(sa + (size_t)(G * 4 + a) * WG_BLK, &map_x_lo, &full_bar[stage], blk_c[a], z0 + blk_dz[a],
+                          y0 + blk_dy[a], x0 + blk_dx[a], b);
+          }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if (++tzi == p.tz) { tzi = 0; if (++tyi == p.ty) { tyi = 0; if (++x0 == p.sx) { x0 = 0; ++b; } } }
       }
@@ -190,11 +201,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     const int tid = threadIdx.x - 12 * 32;
     int stage = 0;
     uint32_t phase = 0;
-    long long stall_c = 0;
+    long long stall_c = 0, fence_cycles = 0;
     const long long t_begin = clock64();
     for (long long t = 0; t < my_tiles; ++t) {
       mbar_wait_t(&full_bar[stage], phase, p.err, 15, stall_c);
-      if (p.npass > 1) {
+      if (p.npass > 1 && p.lo_in_kernel) {
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         const int ng16 = p.chunks_out * (int)(WG_BLK >> 4), na16 = nab * (int)(WG_BLK >> 4);
         const float4 *g_src = reinterpret_cast<const float4 *>(st);
@@ -222,12 +233,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             }
           }
         }
+        const long long tf0 = clock64();
         fence_proxy_async();
+        fence_cycles += clock64() - tf0;
       }
       mbar_arrive(&ready_bar[stage]);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    if (p.dbg && blockIdx.x == 0 && tid == 0) { p.dbg[5] = stall_c; p.dbg[6] = clock64() - t_begin; }
+    if (p.dbg && blockIdx.x == 0 && tid == 0) { p.dbg[5] = stall_c; p.dbg[6] = clock64() - t_begin; p.dbg[7] = fence_cycles; }
   } else if (warp >= 4) {
     // ================================ drain / epilogue ================================
     const int e = warp - 4;
@@ -304,7 +317,6 @@ static int *g_wg_err = nullptr;
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
-  (void)x_lo; (void)g_lo;  // accepted for ABI stability; the kernel derives lo = x - trunc_tf32(x) itself
   PVB_CHECK_ARG(x_hi && g_hi && dw && ldx % 4 == 0 && ldg % 4 == 0);
   if (cout > 128) return PVCNN_E_UNSUPPORTED;  // TODO(round 2): N tiling for wide SharedMLPs
   if (!g_wg_err) {
@@ -326,9 +338,14 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   p.chunks_out = ceil_div(cout, 32);
   p.n_ablocks = ntaps * p.chunks_in;
   p.block_n = max(16, ((cout + 15) / 16) * 16);
-  // one M=128 operand group per CTA: a 48 KB stage (hi + in-kernel lo) allows a 4-deep TMA ring, which
-  // matters more than operand reuse here (the 2-group / 2-stage variant was load-latency bound: 1.27 ms)
-  p.groups_per_cta = 1;
+  // Measured on B200 (tools/stall_profile.py, 3xTF32, metric shape):
+  //   G=2 + lo tensors TMA-loaded 0.83 ms | G=1 + loaded lo 1.04 ms | G=2 + in-kernel lo 1.38 ms | G=1 + in-kernel 1.73 ms.
+  // The N=64 tf32 MMAs are bound by shared-memory bandwidth (6 KB of operands per MMA); converting lo in the
+  // kernel adds 2x its bytes to the same pipe, so wgrad reads materialised lo tensors when the caller has them.
+  p.groups_per_cta = p.block_n <= 64 ? 2 : 1;
+  { const char *e = getenv("PVCNN_WGRAD_G"); if (e && e[0] == '1') p.groups_per_cta = 1; }
+  p.lo_in_kernel = (x_lo == nullptr || g_lo == nullptr) ? 1 : 0;
+  { const char *e = getenv("PVCNN_WGRAD_LO"); if (e && e[0] == 'k') p.lo_in_kernel = 1; }
   const int ngroups = ceil_div(p.n_ablocks, 4);
   p.num_sets = ceil_div(ngroups, p.groups_per_cta);
   p.ksplit = max(1, kNumSMs / p.num_sets);
@@ -348,9 +365,9 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   CUtensorMap mx_hi, mx_lo, mg_hi, mg_lo;
   int rc;
   if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  if ((rc = encode_map_5d_cl(&mx_lo, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mx_lo, (npass > 1 && !p.lo_in_kernel) ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  if ((rc = encode_map_5d_cl(&mg_lo, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_lo, (npass > 1 && !p.lo_in_kernel) ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   if (p.groups_per_cta == 2) {
     PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
