@@ -60,3 +60,77 @@ def test_pvconv_train_step(mode, b, n, c, r, monkeypatch):
             assert np.abs(got - want).max() < 1e-4 * scale, name
         else:
             assert rel_err(got, want) < 5e-5, name
+
+
+@pytest.mark.parametrize("b,n,cin,cout,r,normalize,eps", [
+    (2, 1500, 9, 64, 16, True, 0.0),      # first-layer shape: Cin=9 (padded to 12), ragged N
+    (2, 1024, 64, 128, 12, True, 0.0),    # R=12 and Cout=128 -> v1 conv kernel + single-group wgrad
+    (3, 777, 16, 32, 8, False, 0.0),      # normalize=False (ShapeNet), odd N
+    (2, 1024, 4, 64, 16, True, 1e-15),    # KITTI first layer: Cin=4, eps set
+])
+def test_pvconv_fused_shapes(b, n, cin, cout, r, normalize, eps, monkeypatch):
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
+    g = rng(31)
+    f = g.standard_normal((b, cin, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n)
+    if not normalize:
+        co = co * 0.3
+    go = g.standard_normal((b, cout, n), dtype=np.float32)
+    m = make_block(cin, cout, r, normalize=normalize, eps=eps).cuda().train()
+    ref = run_oracle(m, f, co, go, r, dtype="float64", normalize=normalize, eps=eps)
+    ft = torch.from_numpy(f).cuda().requires_grad_(True)
+    out, _ = m((ft, torch.from_numpy(co).cuda()))
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) < 1e-5
+    assert rel_err(ft.grad.cpu().numpy(), ref["grad_features"]) < 2e-5
+    for name, p in m.named_parameters():
+        got, want = p.grad.cpu().numpy(), ref["grads"][name]
+        if name in ("voxel_layers.0.bias", "voxel_layers.3.bias", "point_features.layers.0.bias"):
+            scale = np.abs(ref["grads"][name.replace("bias", "weight")]).max()
+            assert np.abs(got - want).max() < 1e-4 * scale, name
+        else:
+            assert rel_err(got, want) < 5e-5, name
+
+
+def test_pvconv_running_stats_and_eval_mode(monkeypatch):
+    """train step updates the BN buffers like torch (momentum 0.1, unbiased variance); eval mode then uses them."""
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
+    g = rng(32)
+    b, n, c, r = 2, 1024, 16, 8
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n)
+    m = make_block(c, c, r).cuda().train()
+    ref = run_oracle(m, f, co, None, r, dtype="float64")
+    with torch.no_grad():
+        m((torch.from_numpy(f).cuda(), torch.from_numpy(co).cuda()))
+    # oracle batch statistics -> expected running buffers after one step from (0, 1)
+    for key, bn, nelem in (("conv1", m.voxel_layers[1], b * r ** 3), ("conv2", m.voxel_layers[4], b * r ** 3)):
+        y = ref["stats"][key]
+        mean = y.mean(dim=(0, 2, 3, 4)).numpy()
+        var = y.var(dim=(0, 2, 3, 4), unbiased=True).numpy()
+        assert np.abs(bn.running_mean.cpu().numpy() - 0.1 * mean).max() < 1e-5
+        assert np.abs(bn.running_var.cpu().numpy() - (0.9 + 0.1 * var)).max() < 1e-5
+        assert int(bn.num_batches_tracked) == 1
+    m.eval()
+    refe = run_oracle(m, f, co, None, r, training=False, dtype="float64")
+    with torch.no_grad():
+        out, _ = m((torch.from_numpy(f).cuda(), torch.from_numpy(co).cuda()))
+    assert rel_err(out.cpu().numpy(), refe["out"]) < 1e-5
+
+
+def test_precision_modes(monkeypatch):
+    """tf32 mode = one tensor-core pass (the reference's cuDNN default precision): ~1e-3, not 1e-5."""
+    g = rng(33)
+    b, n, c, r = 2, 1024, 32, 16
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n)
+    m = make_block(c, c, r).cuda().train()
+    ref = run_oracle(m, f, co, None, r, dtype="float64")
+    errs = {}
+    for mode in ("fp32", "tf32"):
+        monkeypatch.setenv("PVCNN_B200_PRECISION", mode)
+        with torch.no_grad():
+            out, _ = m((torch.from_numpy(f).cuda(), torch.from_numpy(co).cuda()))
+        errs[mode] = rel_err(out.cpu().numpy(), ref["out"])
+    assert errs["fp32"] < 1e-5
+    assert 1e-5 < errs["tf32"] < 5e-3
