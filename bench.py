@@ -221,7 +221,7 @@ def single_gpu_extras(torch, dev, m, args):
     achieved = CONV_FLOPS / k_ms / 1e9
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0
     extra["roofline"] = {
-        "kernel": "igemm_conv_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32)", "bound": "tensor",
+        "kernel": "conv_halo_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32, smem halo reuse)", "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
         "traffic": None, "kernel_ms": k_ms,
         "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of the kernel "

@@ -195,7 +195,7 @@ def three_nn_interpolate_grad(grad_y, idx, w, m):
 # PVConv block oracle: modules/pvconv.py:33-39 wiring, dense ops through torch CPU.
 # ----------------------------------------------------------------------------------------------
 def pvconv_forward_backward(params, features, coords, grad_out, resolution, *, training=True, normalize=True,
-                            eps=0.0, with_se=False, dtype="float32", bn_eps=1e-4, momentum=0.1, buffers=None):
+                            eps=0.0, with_se=False, dtype="float32", bn_eps=1e-4, momentum=0.1, buffers=None, threads=None):
     """Forward (+ backward when grad_out is not None) of one PVConv block on CPU.
 
     params: dict with the reference state_dict names:
@@ -209,6 +209,8 @@ def pvconv_forward_backward(params, features, coords, grad_out, resolution, *, t
     import torch
     import torch.nn.functional as TF
 
+    if threads is not None:
+        torch.set_num_threads(int(threads))
     td = getattr(torch, dtype)
     r = int(resolution)
     feats = torch.as_tensor(np.asarray(features), dtype=torch.float32)
