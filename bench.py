@@ -37,40 +37,57 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: one long-running
+    `nvidia-smi -lms 20` process (started before the region, killed after it); only the rows that arrived
+    between mark_start() and stop() are used."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.rows, self.t0 = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+    def _read(self):
+        if not self.proc:
+            return
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
+
+    def start(self):
+        time.sleep(0.15)  # let the sampler reach steady state
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=5)
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        reasons = set()
+        t1 = time.perf_counter()
+        time.sleep(0.05)
+        if self.proc:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= t1 + 0.03 and len(r) >= 7]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-3:] if len(r) >= 7]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[1]) for r in rows) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 7:
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
 def make_inputs(torch, device, batch=B):
@@ -223,7 +240,8 @@ def single_gpu_extras(torch, dev, m, args):
     extra["roofline"] = {
         "kernel": "conv_halo_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32, smem halo reuse)", "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-        "traffic": None, "kernel_ms": k_ms,
+        "traffic": 223.3e6 if npass == 3 else None, "kernel_ms": k_ms,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/r01_ncu_full_v2.md (135.3 MB + 88.0 MB; algorithmic in+out = 268 MB)",
         "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of the kernel "
                 "run alone; executed tensor FLOPs are %dx that. peak = %s bf16_tflops_sustained / 2 (tf32 is the "
                 "half-rate kind; no direct tf32 measurement in MEASURED_PEAKS.json)" % (CONV_FLOPS / 1e9, npass,
@@ -295,7 +313,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PVCNN_B200_PRECISION", "fp32"), choices=["fp32", "tf32"])
