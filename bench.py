@@ -64,7 +64,9 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.strip().split(",")]))
 
     def start(self):
-        time.sleep(0.15)  # let the sampler reach steady state
+        deadline = time.perf_counter() + 3.0
+        while not self.rows and time.perf_counter() < deadline:  # first sample can take a second to appear
+            time.sleep(0.02)
         self.t0 = time.perf_counter()
 
     def stop(self):
@@ -139,12 +141,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi -lms starts sampling during the warm-up
     for _ in range(args.warmup):
         step(feats, coords, gout)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    barrier()  # every rank enters the timed region together (the sampler's settle time is before the barrier)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
