@@ -148,7 +148,7 @@ PVCNN_API int pvcnn_conv_wgrad(int nb, int sx, int sy, int sz, int cin, int cout
  * Fused PVConv block: replaces modules.PVConv.forward (modules/pvconv.py:33-39) and its autograd
  * backward, i.e. Voxelization (modules/voxelization.py:16-25) -> Conv3d/BN3d/LeakyReLU x2
  * (modules/pvconv.py:20-27) -> trilinear_devoxelize, plus SharedMLP (modules/shared_mlp.py:29-33)
- * and the residual add, as ONE call each way.  with_se is not part of this entry point yet.
+ * and the residual add, as ONE call each way; SE3d (modules/se.py:6-17) is folded in when desc.with_se is set.
  *
  * Sizes below use  Mv = b*r^3, Mp = b*n, ci = pad4(cin), co = pad4(cout), ld(x) = roundup(x,32).
  * ===================================================================================== */
@@ -162,16 +162,19 @@ typedef struct {
   float bn_eps_pt;    /* 1e-5 (nn.BatchNorm1d default)                     */
   float momentum;     /* 0.1                                               */
   float slope;        /* LeakyReLU 0.1                                     */
+  int with_se;        /* SE3d after the second conv block (modules/se.py), hidden = cout / 8 */
 } pvcnn_pvconv_desc;
 
 typedef struct { /* parameters in torch layouts; running stats are updated in training mode */
   const float *w1, *b1, *g1, *be1; float *rm1, *rv1;   /* voxel_layers.0 / .1 */
   const float *w2, *b2, *g2, *be2; float *rm2, *rv2;   /* voxel_layers.3 / .4 */
   const float *wp, *bp, *gp, *bep; float *rmp, *rvp;   /* point_features.layers.0 / .1 */
+  const float *se_w1, *se_w2;                          /* voxel_layers.6.fc.{0,2}.weight (with_se) */
 } pvcnn_pvconv_params;
 
 typedef struct { /* parameter gradients (same shapes as the parameters) */
   float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *wp, *bp, *gp, *bep;
+  float *se_w1, *se_w2;
 } pvcnn_pvconv_grads;
 
 typedef struct { /* caller-allocated device buffers (element counts in comments) */
@@ -193,6 +196,7 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
   float *gfpt;              /* Mp*ci */
   float *d2;                /* Mv*max(ci,co) */
   float *gy2, *gy2_lo, *gy1, *gy1_lo; /* Mv*co */
+  float *se;                /* with_se: b*(7*co + cout/8)  (pooled sums, mean, hidden, gate, d gate, dense term) */
 } pvcnn_pvconv_ws;
 
 /* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided (3xTF32 mode: the weight-

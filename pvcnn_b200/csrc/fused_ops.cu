@@ -161,7 +161,8 @@ constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = kNumSMs * 4;
 
 template <int NSETS, typename F>
-__device__ __forceinline__ void column_reduce(long long rows, int cp, float *partials, F &&body) {
+__device__ __forceinline__ void column_reduce(long long rows, int cp, float *partials, F &&body,
+                                              long long row_begin = 0, long long part_block = -1) {
   __shared__ float4 red[NSETS][RED_THREADS];
   const int cp4 = cp >> 2;
   const int rl = RED_THREADS / cp4;  // row lanes (cp4 <= 256)
@@ -169,9 +170,10 @@ __device__ __forceinline__ void column_reduce(long long rows, int cp, float *par
   float4 acc[NSETS];
 #pragma unroll
   for (int k = 0; k < NSETS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (part_block < 0) part_block = blockIdx.x;
   if (lane_r < rl)
     for (long long r = (long long)blockIdx.x * rl + lane_r; r < rows; r += (long long)gridDim.x * rl)
-      body(r, c4, acc);
+      body(row_begin + r, c4, acc);
 #pragma unroll
   for (int k = 0; k < NSETS; ++k) red[k][threadIdx.x] = acc[k];
   __syncthreads();
@@ -183,7 +185,7 @@ __device__ __forceinline__ void column_reduce(long long rows, int cp, float *par
         const float4 v = red[k][threadIdx.x + j * cp4];
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
-      st4(partials + ((size_t)blockIdx.x * NSETS + k) * cp + threadIdx.x * 4, s);
+      st4(partials + ((size_t)part_block * NSETS + k) * cp + threadIdx.x * 4, s);
     }
   }
 }
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, 
                                                           const float *__restrict__ nc,
                                                           const float *__restrict__ y2, BnCoef bn2,
                                                           const float *__restrict__ p, BnCoef bnp,
-                                                          float *__restrict__ out) {
+                                                          const float *__restrict__ se_s, float *__restrict__ out) {
   extern __shared__ float tile[];
   const int b = blockIdx.y, i0 = blockIdx.x * PT_TILE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -395,6 +397,10 @@ __global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, 
         acc.z = fmaf(k.w[j], leaky(fmaf(v.z, sc.z, sh.z), slope), acc.z);
         acc.w = fmaf(k.w[j], leaky(fmaf(v.w, sc.w, sh.w), slope), acc.w);
       }
+      if (se_s) {  // SE3d gate: a per-(sample, channel) scale commutes with the (linear) trilinear gather
+        const float4 sv = ld4(se_s + (size_t)b * cp + c4 * 4);
+        acc.x *= sv.x; acc.y *= sv.y; acc.z *= sv.z; acc.w *= sv.w;
+      }
       const float4 pv = ld4(prow + c4 * 4);
       const float4 ps = ld4(bnp.scale + c4 * 4), ph = ld4(bnp.shift + c4 * 4);
       tile[(c4 * 4 + 0) * 33 + pt] = acc.x + fmaxf(fmaf(pv.x, ps.x, ph.x), 0.0f);
@@ -410,12 +416,12 @@ __global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, 
 }
 
 int launch_devox_fused(int b, int n, int c, int cp, int r, float slope, const float *norm_coords, const float *y2,
-                       BnCoef bn2, const float *p, BnCoef bnp, float *out, cudaStream_t s) {
+                       BnCoef bn2, const float *p, BnCoef bnp, const float *se_s, float *out, cudaStream_t s) {
   const size_t smem = (size_t)cp * 33 * sizeof(float);
   if (smem > 48 * 1024)
     PVB_CUDA(cudaFuncSetAttribute(devox_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PVB_LAUNCH(devox_fused_kernel, dim3(ceil_div(n, PT_TILE), b), 256, smem, s, n, c, cp, r, slope, norm_coords, y2, bn2,
-             p, bnp, out);
+             p, bnp, se_s, out);
   return 0;
 }
 
@@ -429,10 +435,12 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
                                                          const float *__restrict__ y2, BnCoef bn2,
                                                          const float *__restrict__ p, BnCoef bnp,
                                                          float *__restrict__ ga_cl, float *__restrict__ d2,
-                                                         float *__restrict__ partials) {
+                                                         float *__restrict__ partials,
+                                                         const float *__restrict__ se_s,
+                                                         float *__restrict__ ds_partials) {
   extern __shared__ float sm[];
   float *gtile = sm;                 // [cp][33]
-  float *red = sm + (size_t)cp * 33;  // [PT_WARPS][4][cp]
+  float *red = sm + (size_t)cp * 33;  // [PT_WARPS][5][cp]
   const int b = blockIdx.y, i0 = blockIdx.x * PT_TILE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r3 = r * r * r, cp4 = cp >> 2;
@@ -448,7 +456,9 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
     const float4 mu2 = ld4(bn2.mean + c4 * 4), is2 = ld4(bn2.invstd + c4 * 4);
     const float4 scp = ld4(bnp.scale + c4 * 4), shp = ld4(bnp.shift + c4 * 4);
     const float4 mup = ld4(bnp.mean + c4 * 4), isp = ld4(bnp.invstd + c4 * 4);
-    float4 S1 = make_float4(0.f, 0.f, 0.f, 0.f), S2 = S1, T1 = S1, T2 = S1;
+    float4 S1 = make_float4(0.f, 0.f, 0.f, 0.f), S2 = S1, T1 = S1, T2 = S1, DS = S1;
+    float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (se_s) sv = ld4(se_s + (size_t)b * cp + c4 * 4);
     for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
       const int pt = warp * (PT_TILE / PT_WARPS) + q;
       const int i = i0 + pt;
@@ -472,15 +482,23 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
       // ---- voxel branch: trilinear scatter of leaky'(.) * w * g, BN3d reductions
       Corners k;
       corner_setup(co[i], co[i + n], co[i + 2 * n], r, k);
+      const float4 gs = make_float4(g.x * sv.x, g.y * sv.y, g.z * sv.z, g.w * sv.w);  // gradient behind the SE gate
+      float4 V = make_float4(0.f, 0.f, 0.f, 0.f);  // un-gated voxel-branch output (needed for d gate)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const size_t vrow = ((size_t)b * r3 + k.idx[j]) * cp + c4 * 4;
         const float4 v = ld4(y2 + vrow);
+        const float zx = fmaf(v.x, sc2.x, sh2.x), zy = fmaf(v.y, sc2.y, sh2.y), zz = fmaf(v.z, sc2.z, sh2.z),
+                    zw = fmaf(v.w, sc2.w, sh2.w);
+        if (se_s) {
+          V.x = fmaf(k.w[j], leaky(zx, slope), V.x); V.y = fmaf(k.w[j], leaky(zy, slope), V.y);
+          V.z = fmaf(k.w[j], leaky(zz, slope), V.z); V.w = fmaf(k.w[j], leaky(zw, slope), V.w);
+        }
         float4 gk;
-        gk.x = k.w[j] * g.x * (fmaf(v.x, sc2.x, sh2.x) > 0.f ? 1.0f : slope);
-        gk.y = k.w[j] * g.y * (fmaf(v.y, sc2.y, sh2.y) > 0.f ? 1.0f : slope);
-        gk.z = k.w[j] * g.z * (fmaf(v.z, sc2.z, sh2.z) > 0.f ? 1.0f : slope);
-        gk.w = k.w[j] * g.w * (fmaf(v.w, sc2.w, sh2.w) > 0.f ? 1.0f : slope);
+        gk.x = k.w[j] * gs.x * (zx > 0.f ? 1.0f : slope);
+        gk.y = k.w[j] * gs.y * (zy > 0.f ? 1.0f : slope);
+        gk.z = k.w[j] * gs.z * (zz > 0.f ? 1.0f : slope);
+        gk.w = k.w[j] * gs.w * (zw > 0.f ? 1.0f : slope);
         T1.x += gk.x; T1.y += gk.y; T1.z += gk.z; T1.w += gk.w;
         T2.x = fmaf(gk.x, (v.x - mu2.x) * is2.x, T2.x);
         T2.y = fmaf(gk.y, (v.y - mu2.y) * is2.y, T2.y);
@@ -488,31 +506,34 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
         T2.w = fmaf(gk.w, (v.w - mu2.w) * is2.w, T2.w);
         if (k.w[j] != 0.0f) red_add4(d2 + vrow, gk);
       }
+      DS.x = fmaf(g.x, V.x, DS.x); DS.y = fmaf(g.y, V.y, DS.y); DS.z = fmaf(g.z, V.z, DS.z); DS.w = fmaf(g.w, V.w, DS.w);
     }
-    st4(red + ((size_t)warp * 4 + 0) * cp + c4 * 4, S1);
-    st4(red + ((size_t)warp * 4 + 1) * cp + c4 * 4, S2);
-    st4(red + ((size_t)warp * 4 + 2) * cp + c4 * 4, T1);
-    st4(red + ((size_t)warp * 4 + 3) * cp + c4 * 4, T2);
+    st4(red + ((size_t)warp * 5 + 0) * cp + c4 * 4, S1);
+    st4(red + ((size_t)warp * 5 + 1) * cp + c4 * 4, S2);
+    st4(red + ((size_t)warp * 5 + 2) * cp + c4 * 4, T1);
+    st4(red + ((size_t)warp * 5 + 3) * cp + c4 * 4, T2);
+    st4(red + ((size_t)warp * 5 + 4) * cp + c4 * 4, DS);
   }
   __syncthreads();
-  const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-  for (int t = threadIdx.x; t < 4 * cp; t += blockDim.x) {
+  const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;  // blocks of one sample are contiguous
+  for (int t = threadIdx.x; t < 5 * cp; t += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < PT_WARPS; ++w) s += red[(size_t)w * 4 * cp + t];
-    partials[blk * 4 * cp + t] = s;
+    for (int w = 0; w < PT_WARPS; ++w) s += red[(size_t)w * 5 * cp + t];
+    if (t < 4 * cp) partials[blk * 4 * cp + t] = s;
+    else if (ds_partials) ds_partials[blk * cp + (t - 4 * cp)] = s;
   }
 }
 
 int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const float *grad_out,
                       const float *norm_coords, const float *y2, BnCoef bn2, const float *p, BnCoef bnp, float *ga_cl,
-                      float *d2, float *partials, int *nblocks, cudaStream_t s) {
-  const size_t smem = ((size_t)cp * 33 + (size_t)PT_WARPS * 4 * cp) * sizeof(float);
+                      float *d2, float *partials, int *nblocks, const float *se_s, float *ds_partials, cudaStream_t s) {
+  const size_t smem = ((size_t)cp * 33 + (size_t)PT_WARPS * 5 * cp) * sizeof(float);
   if (smem > 48 * 1024)
     PVB_CUDA(cudaFuncSetAttribute(bwd_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid(ceil_div(n, PT_TILE), b);
   *nblocks = (int)(grid.x * grid.y);
   PVB_LAUNCH(bwd_points_kernel, grid, 256, smem, s, n, c, cp, r, slope, grad_out, norm_coords, y2, bn2, p, bnp, ga_cl,
-             d2, partials);
+             d2, partials, se_s, ds_partials);
   return 0;
 }
 
@@ -533,18 +554,23 @@ __global__ void __launch_bounds__(RED_THREADS) bn_bwd_apply_kernel(long long row
                                                                    const float *__restrict__ s2,
                                                                    float *__restrict__ out,
                                                                    float *__restrict__ out_lo,
-                                                                   float *__restrict__ partials) {
+                                                                   float *__restrict__ partials,
+                                                                   const float *__restrict__ extra,
+                                                                   long long rows_per_sample) {
   column_reduce<1>(rows, cp, partials, [&](long long r, int c4, float4 *acc) {
     const size_t o = (size_t)r * cp + c4 * 4;
     const float4 gv = ldg_stream4(g + o), yv = ldg_stream4(y + o);
     const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
     const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
     const float4 a1 = ld4(s1 + c4 * 4), a2 = ld4(s2 + c4 * 4);
+    float4 ex = make_float4(0.f, 0.f, 0.f, 0.f);  // dense SE term: d(mean over voxels) reaches every voxel
+    if (extra) ex = ld4(extra + (size_t)(r / rows_per_sample) * cp + c4 * 4);
     float4 d;
 #define PVB_BWD1(f)                                                                                   \
   {                                                                                                   \
     float gg = gv.f;                                                                                  \
     if (use_mask) gg *= (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope);                                \
+    if (extra) gg += (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope) * ex.f;                            \
     const float xh = (yv.f - mu.f) * is.f;                                                            \
     d.f = sc.f * (gg - a1.f * inv_count - xh * (a2.f * inv_count));                                   \
     acc[0].f += d.f;                                                                                  \
@@ -558,13 +584,14 @@ __global__ void __launch_bounds__(RED_THREADS) bn_bwd_apply_kernel(long long row
 
 int launch_bn_bwd_apply(long long rows, int cp, int use_mask, float slope, const float *g, const float *y,
                         BnCoef coef, const float *s1, const float *s2, float *out, float *out_lo,
-                        float *colsum_partials, int *nblocks, cudaStream_t s) {
+                        float *colsum_partials, int *nblocks, cudaStream_t s, const float *extra,
+                        long long rows_per_sample) {
   PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
   const int rl = RED_THREADS / (cp / 4);
   const int gsz = grid_for(rows, rl * 8, RED_MAX_BLOCKS);
   *nblocks = gsz;
   PVB_LAUNCH(bn_bwd_apply_kernel, gsz, RED_THREADS, 0, s, rows, cp, use_mask, slope, (float)(1.0 / (double)rows), g, y,
-             coef, s1, s2, out, out_lo, colsum_partials);
+             coef, s1, s2, out, out_lo, colsum_partials, extra, rows_per_sample > 0 ? rows_per_sample : 1);
   return 0;
 }
 
@@ -595,6 +622,168 @@ int launch_bn_bwd_reduce(long long rows, int cp, float slope, const float *g, co
   const int gsz = grid_for(rows, rl * 8, RED_MAX_BLOCKS);
   *nblocks = gsz;
   PVB_LAUNCH(bn_bwd_reduce_kernel, gsz, RED_THREADS, 0, s, rows, cp, slope, g, y, coef, partials);
+  return 0;
+}
+
+
+// --------------------------------------------------------------------------------------------
+// SE3d (modules/se.py:6-17) inside the fused block.
+//   forward : pooled[b,c] = mean_v leaky(bn2(Y2)), gate s = sigmoid(W2 relu(W1 pooled)); the gate multiplies the
+//             devoxelized voxel branch (a per-(sample,channel) scale commutes with the linear gather)
+//   backward: d gate from the un-gated voxel output; d pooled is a dense 1/R^3 term on every voxel, folded into the
+//             BN2 backward reductions (via A1 = sum leaky', A2 = sum leaky'*xhat per sample) and bn_bwd_apply.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) se_pool_kernel(long long rows_per_sample, int cp, float slope,
+                                                              const float *__restrict__ y, BnCoef coef,
+                                                              float *__restrict__ partials) {
+  const long long b = blockIdx.y;
+  column_reduce<3>(rows_per_sample, cp, partials, [&](long long r, int c4, float4 *acc) {
+    const float4 v = ld4(y + (size_t)r * cp + c4 * 4);
+    const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
+    const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
+#define PVB_SE1(f)                                        \
+  {                                                       \
+    const float z = fmaf(v.f, sc.f, sh.f);                \
+    const float dl = z > 0.f ? 1.0f : slope;              \
+    acc[0].f += z * dl;                                   \
+    acc[1].f += dl;                                       \
+    acc[2].f = fmaf(dl, (v.f - mu.f) * is.f, acc[2].f);   \
+  }
+    PVB_SE1(x) PVB_SE1(y) PVB_SE1(z) PVB_SE1(w)
+#undef PVB_SE1
+  }, b * rows_per_sample, b * gridDim.x + blockIdx.x);
+}
+
+// sums[b][j] = sum over the sample's blocks of partials[b][blk][j]
+__global__ void __launch_bounds__(256) reduce_partials_batched_kernel(int nblocks, int ncols,
+                                                                      const float *__restrict__ partials,
+                                                                      float *__restrict__ sums) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int k = lane; k < nblocks; k += 32) s += (double)partials[((size_t)b * nblocks + k) * ncols + c];
+  s = warp_sum_d(s);
+  if (lane == 0) sums[(size_t)b * ncols + c] = (float)s;
+}
+
+int launch_se_pool(int b, long long rows_per_sample, int cp, float slope, const float *y, BnCoef coef, float *partials,
+                   float *pooled3 /*[b][3][cp]*/, cudaStream_t s) {
+  PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
+  const int rl = RED_THREADS / (cp / 4);
+  int gx = grid_for(rows_per_sample, rl * 8, max(1, RED_MAX_BLOCKS / b));
+  PVB_LAUNCH(se_pool_kernel, dim3(gx, b), RED_THREADS, 0, s, rows_per_sample, cp, slope, y, coef, partials);
+  PVB_LAUNCH(reduce_partials_batched_kernel, dim3(ceil_div(3 * cp, 8), b), 256, 0, s, gx, 3 * cp, partials, pooled3);
+  return 0;
+}
+
+int launch_reduce_partials_batched(int b, int nblocks_per_sample, int ncols, const float *partials, float *sums,
+                                   cudaStream_t s) {
+  PVB_LAUNCH(reduce_partials_batched_kernel, dim3(ceil_div(ncols, 8), b), 256, 0, s, nblocks_per_sample, ncols,
+             partials, sums);
+  return 0;
+}
+
+// one CTA per sample: gate = sigmoid(W2 relu(W1 mean));  smem: mean[c] + hidden[h]
+__global__ void __launch_bounds__(128) se_fc_kernel(int c, int cp, int hid, float inv_rows,
+                                                    const float *__restrict__ pooled3, const float *__restrict__ w1,
+                                                    const float *__restrict__ w2, float *__restrict__ mean_out,
+                                                    float *__restrict__ hidden_out, float *__restrict__ gate) {
+  extern __shared__ float sm[];
+  float *m = sm, *h = sm + cp;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+    const float v = i < c ? pooled3[((size_t)b * 3 + 0) * cp + i] * inv_rows : 0.f;
+    m[i] = v;
+    mean_out[(size_t)b * cp + i] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    float a = 0.f;
+    for (int i = 0; i < c; ++i) a = fmaf(w1[(size_t)j * c + i], m[i], a);
+    a = fmaxf(a, 0.f);
+    h[j] = a;
+    hidden_out[(size_t)b * hid + j] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+    float a = 0.f;
+    if (i < c) {
+      for (int j = 0; j < hid; ++j) a = fmaf(w2[(size_t)i * hid + j], h[j], a);
+      a = 1.0f / (1.0f + expf(-a));
+    }
+    gate[(size_t)b * cp + i] = a;
+  }
+}
+
+int launch_se_fc(int b, int c, int cp, int hid, long long rows_per_sample, const float *pooled3, const float *w1,
+                 const float *w2, float *mean_out, float *hidden_out, float *gate, cudaStream_t s) {
+  PVB_LAUNCH(se_fc_kernel, b, 128, (cp + hid) * sizeof(float), s, c, cp, hid, (float)(1.0 / (double)rows_per_sample),
+             pooled3, w1, w2, mean_out, hidden_out, gate);
+  return 0;
+}
+
+// single CTA: backward through sigmoid / FC2 / ReLU / FC1 for every sample; emits dW1, dW2 and
+// extra[b][c] = d pooled[b][c] / rows_per_sample (the dense per-voxel gradient of the mean)
+__global__ void __launch_bounds__(256) se_fc_bwd_kernel(int nb, int c, int cp, int hid, float inv_rows,
+                                                        const float *__restrict__ dgate_sum /*[b][cp]*/,
+                                                        const float *__restrict__ gate,
+                                                        const float *__restrict__ hidden,
+                                                        const float *__restrict__ mean, const float *__restrict__ w1,
+                                                        const float *__restrict__ w2, float *__restrict__ dw1,
+                                                        float *__restrict__ dw2, float *__restrict__ extra) {
+  extern __shared__ float sm[];
+  float *dsig = sm, *dh = sm + cp;
+  for (int i = threadIdx.x; i < hid * c; i += blockDim.x) { dw1[i] = 0.f; dw2[i] = 0.f; }
+  __syncthreads();
+  for (int b = 0; b < nb; ++b) {
+    for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+      const float sg = gate[(size_t)b * cp + i];
+      dsig[i] = i < c ? dgate_sum[(size_t)b * cp + i] * sg * (1.0f - sg) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+      float a = 0.f;
+      for (int i = 0; i < c; ++i) a = fmaf(w2[(size_t)i * hid + j], dsig[i], a);
+      dh[j] = hidden[(size_t)b * hid + j] > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < c * hid; t += blockDim.x) {
+      const int i = t / hid, j = t % hid;                      // dw2[i][j], dw1[j][i]
+      dw2[(size_t)i * hid + j] += dsig[i] * hidden[(size_t)b * hid + j];
+      dw1[(size_t)j * c + i] += dh[j] * mean[(size_t)b * cp + i];
+    }
+    for (int i = threadIdx.x; i < cp; i += blockDim.x) {
+      float a = 0.f;
+      if (i < c)
+        for (int j = 0; j < hid; ++j) a = fmaf(w1[(size_t)j * c + i], dh[j], a);
+      extra[(size_t)b * cp + i] = a * inv_rows;
+    }
+    __syncthreads();
+  }
+}
+
+// T1[c] += sum_b extra[b][c] * A1[b][c],  T2[c] += sum_b extra[b][c] * A2[b][c]
+__global__ void __launch_bounds__(256) se_fix_sums_kernel(int nb, int cp, const float *__restrict__ extra,
+                                                          const float *__restrict__ pooled3, float *t1, float *t2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cp) return;
+  float a1 = 0.f, a2 = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    const float e = extra[(size_t)b * cp + i];
+    a1 = fmaf(e, pooled3[((size_t)b * 3 + 1) * cp + i], a1);
+    a2 = fmaf(e, pooled3[((size_t)b * 3 + 2) * cp + i], a2);
+  }
+  t1[i] += a1;
+  t2[i] += a2;
+}
+
+int launch_se_backward(int nb, int c, int cp, int hid, long long rows_per_sample, const float *dgate_sum,
+                       const float *gate, const float *hidden, const float *mean, const float *pooled3,
+                       const float *w1, const float *w2, float *dw1, float *dw2, float *extra, float *t1, float *t2,
+                       cudaStream_t s) {
+  PVB_LAUNCH(se_fc_bwd_kernel, 1, 256, (cp + hid) * sizeof(float), s, nb, c, cp, hid,
+             (float)(1.0 / (double)rows_per_sample), dgate_sum, gate, hidden, mean, w1, w2, dw1, dw2, extra);
+  PVB_LAUNCH(se_fix_sums_kernel, ceil_div(cp, 256), 256, 0, s, nb, cp, extra, pooled3, t1, t2);
   return 0;
 }
 

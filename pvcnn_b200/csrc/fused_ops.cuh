@@ -43,27 +43,40 @@ int launch_bn_apply_leaky(long long rows, int cp, float slope, const float *y, B
 
 // out[b,c,i] = sum_k w_k * leaky(bn2(Y2[b, idx_k, c])) + relu(bnp(P[b*N+i, c]))
 int launch_devox_fused(int b, int n, int c, int cp, int r, float slope, const float *norm_coords, const float *y2,
-                       BnCoef bn2, const float *p, BnCoef bnp, float *out, cudaStream_t s);
+                       BnCoef bn2, const float *p, BnCoef bnp, const float *se_s /*[B,cp] or NULL*/, float *out, cudaStream_t s);
 
 // ---- backward ----
 // stage 1 over points: relu-masked point-branch grad (ga_cl), BN reductions of both branches, and the
 // scatter of the voxel-branch gradient (already multiplied by leaky') into d2 (pre-zeroed)
 int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const float *grad_out,
                       const float *norm_coords, const float *y2, BnCoef bn2, const float *p, BnCoef bnp,
-                      float *ga_cl, float *d2, float *partials /*[blocks][4][cp]*/, int *nblocks, cudaStream_t s);
+                      float *ga_cl, float *d2, float *partials /*[blocks][4][cp]*/, int *nblocks,
+                      const float *se_s /*or NULL*/, float *ds_partials /*[blocks][cp] or NULL*/, cudaStream_t s);
 // sums[j] = sum over blocks (fp64) of partials[block][j], j < ncols
 int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s);
 // out = scale * (mask(y)*g - s1/rows - xhat(y)*s2/rows) (+ out_lo); s1/s2 = RAW column sums of g' and
 // g'*xhat; mask = leaky'(bn(y)) when use_mask; also emits column sums of out (conv-bias gradient)
 int launch_bn_bwd_apply(long long rows, int cp, int use_mask, float slope, const float *g, const float *y, BnCoef coef,
                         const float *s1, const float *s2, float *out, float *out_lo, float *colsum_partials,
-                        int *nblocks, cudaStream_t s);
+                        int *nblocks, cudaStream_t s, const float *extra = nullptr, long long rows_per_sample = 0);
 // dense reductions for BN1 backward: U1 = sum leaky'(bn(y))*g, U2 = sum leaky'(..)*g*xhat
 int launch_bn_bwd_reduce(long long rows, int cp, float slope, const float *g, const float *y, BnCoef coef,
                          float *partials /*[blocks][2][cp]*/, int *nblocks, cudaStream_t s);
 // grad_features[b,c,i] = gG0[b*R^3 + ind_i, c] / cnt + gFpt[b*N+i, c]
 int launch_bwd_final(int b, int n, int c, int cp, int r3, const int *ind, const int *cnt, const float *gg0,
                      const float *gfpt, float *grad_features, cudaStream_t s);
+
+// ---- SE3d inside the fused block (see fused_ops.cu) ----
+int launch_se_pool(int b, long long rows_per_sample, int cp, float slope, const float *y, BnCoef coef, float *partials,
+                   float *pooled3 /*[b][3][cp]: sum leaky(bn(y)), sum leaky', sum leaky'*xhat*/, cudaStream_t s);
+int launch_se_fc(int b, int c, int cp, int hid, long long rows_per_sample, const float *pooled3, const float *w1,
+                 const float *w2, float *mean_out, float *hidden_out, float *gate, cudaStream_t s);
+int launch_reduce_partials_batched(int b, int nblocks_per_sample, int ncols, const float *partials, float *sums,
+                                   cudaStream_t s);
+int launch_se_backward(int nb, int c, int cp, int hid, long long rows_per_sample, const float *dgate_sum,
+                       const float *gate, const float *hidden, const float *mean, const float *pooled3,
+                       const float *w1, const float *w2, float *dw1, float *dw2, float *extra, float *t1, float *t2,
+                       cudaStream_t s);
 
 // small helpers
 int launch_memset_f32(float *p, long long n, cudaStream_t s);

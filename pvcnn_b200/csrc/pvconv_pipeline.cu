@@ -46,6 +46,22 @@ static WPrep wprep_layout(const pvcnn_pvconv_desc *d) {
   return w;
 }
 
+struct SeBuf {  // views into ws->se
+  float *pooled3, *mean, *hidden, *gate, *dgate, *extra;
+  int hid;
+};
+static SeBuf se_at(float *base, int b, int co, int cout) {
+  SeBuf v;
+  v.hid = cout / 8;
+  v.pooled3 = base;
+  v.mean = v.pooled3 + (size_t)b * 3 * co;
+  v.gate = v.mean + (size_t)b * co;
+  v.dgate = v.gate + (size_t)b * co;
+  v.extra = v.dgate + (size_t)b * co;
+  v.hidden = v.extra + (size_t)b * co;
+  return v;
+}
+
 static BnCoef coef_at(float *base, int idx, int co) {
   float *p = base + (size_t)idx * 4 * co;
   return BnCoef{p, p + co, p + 2 * co, p + 3 * co};
@@ -73,7 +89,7 @@ long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d) {
   const long long co = pad4(d->cout > d->cin ? d->cout : d->cin);
   const long long blocks_pts = (long long)d->b * ((d->n + 31) / 32);
   const long long blocks = blocks_pts > kNumSMs * 4 ? blocks_pts : kNumSMs * 4;
-  return blocks * 4 * co;
+  return blocks * 5 * co;  // 4 reduction sets + the per-sample SE gate partials
 }
 
 int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, const float *coords,
@@ -140,8 +156,17 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   } else {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_pt, prm->gp, prm->bep, prm->rmp, prm->rvp, bnp, s));
   }
-  // 7. BN2-apply + LeakyReLU + trilinear devoxelize + BN1d-apply + ReLU + add + transpose
-  PVB_TRY(launch_devox_fused(b, n, d->cout, co, r, d->slope, ws->nc, ws->y2, bn2, ws->p, bnp, out, s));
+  // 6b. SE3d gate from the pooled (post BN2 + LeakyReLU) grid                  (modules/se.py:16-17)
+  const float *gate = nullptr;
+  if (d->with_se) {
+    PVB_CHECK_ARG(ws->se && prm->se_w1 && prm->se_w2 && d->cout >= 8);
+    SeBuf se = se_at(ws->se, b, co, d->cout);
+    PVB_TRY(launch_se_pool(b, r3, co, d->slope, ws->y2, bn2, ws->partials, se.pooled3, s));
+    PVB_TRY(launch_se_fc(b, d->cout, co, se.hid, r3, se.pooled3, prm->se_w1, prm->se_w2, se.mean, se.hidden, se.gate, s));
+    gate = se.gate;
+  }
+  // 7. BN2-apply + LeakyReLU + trilinear devoxelize (+ SE gate) + BN1d-apply + ReLU + add + transpose
+  PVB_TRY(launch_devox_fused(b, n, d->cout, co, r, d->slope, ws->nc, ws->y2, bn2, ws->p, bnp, gate, out, s));
   return 0;
 }
 
@@ -165,9 +190,23 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
 
   // 1. per-point stage: point-branch ReLU mask + reductions; voxel-branch scatter (x leaky') + reductions
   PVB_TRY(launch_memset_f32(ws->d2, Mv * co, s));
+  SeBuf se{};
+  float *ds_partials = nullptr;
+  if (d->with_se) {
+    PVB_CHECK_ARG(ws->se && prm->se_w1 && prm->se_w2 && gr->se_w1 && gr->se_w2);
+    se = se_at(ws->se, b, co, d->cout);
+    ds_partials = ws->partials + (size_t)b * ((n + 31) / 32) * 4 * co;
+  }
   PVB_TRY(launch_bwd_points(b, n, d->cout, co, r, d->slope, grad_out, ws->nc, ws->y2, bn2, ws->p, bnp, ws->ga, ws->d2,
-                            ws->partials, &nblk, s));
+                            ws->partials, &nblk, d->with_se ? se.gate : nullptr, ds_partials, s));
   PVB_TRY(launch_reduce_partials(nblk, 4 * co, ws->partials, S, s));
+  const float *extra = nullptr;
+  if (d->with_se) {  // d gate -> FC backward -> dense d(mean) term folded into the BN2 reductions
+    PVB_TRY(launch_reduce_partials_batched(b, (n + 31) / 32, co, ds_partials, se.dgate, s));
+    PVB_TRY(launch_se_backward(b, d->cout, co, se.hid, r3, se.dgate, se.gate, se.hidden, se.mean, se.pooled3, prm->se_w1,
+                               prm->se_w2, gr->se_w1, gr->se_w2, se.extra, S + 2 * co, S + 3 * co, s));
+    extra = se.extra;
+  }
   PVB_CUDA(cudaMemcpyAsync(gr->bep, S + 0 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_CUDA(cudaMemcpyAsync(gr->gp, S + 1 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_CUDA(cudaMemcpyAsync(gr->be2, S + 2 * co, cb, cudaMemcpyDeviceToDevice, s));
@@ -178,7 +217,7 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 6 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->bp, S + 6 * co, cb, cudaMemcpyDeviceToDevice, s));
   PVB_TRY(launch_bn_bwd_apply(Mv, co, 0, d->slope, ws->d2, ws->y2, bn2, S + 2 * co, S + 3 * co, ws->gy2,
-                              glo ? ws->gy2_lo : nullptr, ws->partials, &nblk, s));
+                              glo ? ws->gy2_lo : nullptr, ws->partials, &nblk, s, extra, r3));
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 7 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->b2, S + 7 * co, cb, cudaMemcpyDeviceToDevice, s));
   // 3. data-gradient weights

@@ -21,16 +21,17 @@ class Desc(ctypes.Structure):
     _fields_ = [("b", ctypes.c_int), ("n", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int),
                 ("r", ctypes.c_int), ("normalize", ctypes.c_int), ("eps", ctypes.c_float),
                 ("training", ctypes.c_int), ("npass", ctypes.c_int), ("bn_eps_vox", ctypes.c_float),
-                ("bn_eps_pt", ctypes.c_float), ("momentum", ctypes.c_float), ("slope", ctypes.c_float)]
+                ("bn_eps_pt", ctypes.c_float), ("momentum", ctypes.c_float), ("slope", ctypes.c_float),
+                ("with_se", ctypes.c_int)]
 
 
 _PARAM_FIELDS = ["w1", "b1", "g1", "be1", "rm1", "rv1", "w2", "b2", "g2", "be2", "rm2", "rv2",
-                 "wp", "bp", "gp", "bep", "rmp", "rvp"]
-_GRAD_FIELDS = ["w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "wp", "bp", "gp", "bep"]
+                 "wp", "bp", "gp", "bep", "rmp", "rvp", "se_w1", "se_w2"]
+_GRAD_FIELDS = ["w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "wp", "bp", "gp", "bep", "se_w1", "se_w2"]
 _WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("fcl_lo", _F), ("g0", _F),
               ("g0_lo", _F), ("y1", _F), ("z1", _F), ("z1_lo", _F), ("y2", _F), ("p", _F), ("coef", _F),
               ("wprep", _F), ("partials", _F), ("sums", _F), ("ga", _F), ("gpp", _F), ("gpp_lo", _F),
-              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F)]
+              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("se", _F)]
 
 
 class Params(ctypes.Structure):
@@ -93,6 +94,8 @@ class _Plan:
             saved.update(fcl_lo=mp * ci)
         if self.grid_lo:
             saved.update(g0_lo=mv * ci, z1_lo=mv * co)
+        if desc.with_se:
+            saved.update(se=b * (7 * co + desc.cout // 8))
         for k, v in saved.items():
             # activations needed by the backward belong to this call; in inference they are scratch
             alloc[k] = f(v) if need_backward else _scratch("fwd_" + k, v, device)
@@ -136,7 +139,8 @@ def _module_tensors(m):
 
 class _PVConvFused(Function):
     @staticmethod
-    def forward(ctx, features, coords, module, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep):
+    def forward(ctx, features, coords, module, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1=None,
+                se_w2=None):
         dev = features.device
         if dev.type != "cuda":
             raise RuntimeError("features must be a CUDA tensor")  # utils.hpp:7 semantics: no CPU path
@@ -146,19 +150,20 @@ class _PVConvFused(Function):
         training = bool(module.training)
         vox = module.voxelization
         desc = Desc(b, n, cin, module.out_channels, int(module.resolution), int(bool(vox.normalize)), float(vox.eps),
-                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1)
+                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1, int(se_w1 is not None))
         bns = [module.voxel_layers[1], module.voxel_layers[4], module.point_features.layers[1]]
         desc.bn_eps_vox = float(bns[0].eps)
         desc.bn_eps_pt = float(bns[2].eps)
         desc.momentum = float(bns[0].momentum if bns[0].momentum is not None else 0.1)
         desc.slope = float(module.voxel_layers[2].negative_slope)
         need_bwd = training and torch.is_grad_enabled() and any(
-            t.requires_grad for t in (features, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep))
+            t.requires_grad for t in (features, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1, se_w2)
+            if t is not None)
         plan = _Plan(desc, dev, need_bwd)
         prm = Params()
         vals = dict(w1=w1, b1=b1, g1=g1, be1=be1, rm1=bns[0].running_mean, rv1=bns[0].running_var,
                     w2=w2, b2=b2, g2=g2, be2=be2, rm2=bns[1].running_mean, rv2=bns[1].running_var,
-                    wp=wp, bp=bp, gp=gp, bep=bep, rmp=bns[2].running_mean, rvp=bns[2].running_var)
+                    wp=wp, bp=bp, gp=gp, bep=bep, rmp=bns[2].running_mean, rvp=bns[2].running_var, se_w1=se_w1, se_w2=se_w2)
         keep = []
         for k in _PARAM_FIELDS:
             t = vals[k]
@@ -177,7 +182,8 @@ class _PVConvFused(Function):
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
         ctx.plan, ctx.prm, ctx.keep, ctx.desc = plan, prm, keep, desc
-        ctx.shapes = [t.shape for t in (w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep)]
+        ctx.shapes = [None if t is None else t.shape
+                      for t in (w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1, se_w2)]
         ctx.in_shape = features.shape
         return out
 
@@ -189,7 +195,7 @@ class _PVConvFused(Function):
         dev = grad_out.device
         grad_out = grad_out.contiguous().float()
         plan.add_backward_scratch()
-        grads = [torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        grads = [None if s is None else torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
         gs = Grads()
         for k, t in zip(_GRAD_FIELDS, grads):
             setattr(gs, k, _ptr(t))
@@ -197,12 +203,14 @@ class _PVConvFused(Function):
         ws = plan.struct()
         _lib.call("pvcnn_pvconv_backward", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm), ctypes.byref(ws),
                   gfeat, ctypes.byref(gs), device=dev)
-        return (gfeat, None, None, *grads)
+        nparam = 14 if ctx.shapes[12] is not None else 12  # SE weights are optional inputs of forward()
+        return (gfeat, None, None, *grads[:nparam])
 
 
 def pvconv_fused(module, features, coords):
     """features [B,Cin,N], coords [B,3,N] -> fused features [B,Cout,N] (module: pvcnn_b200.nn.PVConv)."""
-    if module.with_se:
-        raise NotImplementedError("fused PVConv with SE3d")
     params, _ = _module_tensors(module)
+    if module.with_se:
+        se = module.voxel_layers[6]
+        params = params + [se.fc[0].weight, se.fc[2].weight]
     return _PVConvFused.apply(features, coords, module, *params)

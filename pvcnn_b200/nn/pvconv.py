@@ -57,9 +57,7 @@ class PVConv(nn.Module):
     def forward(self, inputs):
         features, coords = inputs
         mode = os.environ.get("PVCNN_B200_PVCONV", "fused")
-        # SE3d is not folded into the fused pipeline yet (round-2 item): those blocks chain the
-        # stand-alone sm_100a ops around torch's dense layers.
-        if mode == "composed" or self.with_se:
+        if mode == "composed":
             return self._forward_composed(features, coords)
         from ..fused import pvconv_fused
         return pvconv_fused(self, features, coords), coords

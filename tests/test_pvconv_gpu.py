@@ -135,3 +135,27 @@ def test_precision_modes(monkeypatch):
         errs[mode] = rel_err(out.cpu().numpy(), ref["out"])
     assert errs["fp32"] < 1e-5
     assert 1e-5 < errs["tf32"] < 5e-3
+
+
+@pytest.mark.parametrize("b,n,c,r,normalize", [(2, 1024, 16, 8, True), (3, 2048, 32, 16, False)])
+def test_pvconv_fused_with_se(b, n, c, r, normalize, monkeypatch):
+    """SE3d folded into the fused block (ShapeNet / PVCNN++ configuration)."""
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
+    g = rng(34)
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n) * (1.0 if normalize else 0.3)
+    go = g.standard_normal((b, c, n), dtype=np.float32)
+    m = make_block(c, c, r, with_se=True, normalize=normalize).cuda().train()
+    ref = run_oracle(m, f, co, go, r, dtype="float64", with_se=True, normalize=normalize)
+    ft = torch.from_numpy(f).cuda().requires_grad_(True)
+    out, _ = m((ft, torch.from_numpy(co).cuda()))
+    out.backward(torch.from_numpy(go).cuda())
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) < 1e-5
+    assert rel_err(ft.grad.cpu().numpy(), ref["grad_features"]) < 2e-5
+    for name, p in m.named_parameters():
+        got, want = p.grad.cpu().numpy(), ref["grads"][name]
+        if name in ("voxel_layers.0.bias", "voxel_layers.3.bias", "point_features.layers.0.bias"):
+            scale = np.abs(ref["grads"][name.replace("bias", "weight")]).max()
+            assert np.abs(got - want).max() < 1e-4 * scale, name
+        else:
+            assert rel_err(got, want) < 5e-5, name
