@@ -188,10 +188,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
               for (int ks = 0; ks < HC_KC / 8; ++ks) {
                 const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
                 const uint32_t first = (t9 == 0 && ks == 0) ? 1u : 0u;
-                mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
                 if (three) {
-                  mma_tf32_lo32(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+                  if (p.exp & 2) {  // experiment: A_hi fetched once, reused from the collector
+                    mma_tf32_lo32_c<kCollFill>(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
+                    mma_tf32_lo32_c<kCollLastUse>(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+                  } else {
+                    mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
+                    mma_tf32_lo32(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+                  }
                   if (!(p.exp & 4)) mma_tf32_lo32(d_corr, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
+                } else {
+                  mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
                 }
               }
             }

@@ -128,6 +128,35 @@ __device__ __forceinline__ void mma_tf32_lo32(uint32_t tmem_d, uint32_t a_lo32, 
       "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Variant with an A-operand collector hint: FILL keeps A in the tensor core's collector after this MMA,
+// LASTUSE consumes the kept A (no shared-memory fetch of A for that MMA).  Used for the (A_hi,B_hi),(A_hi,B_lo)
+// pair of the 3xTF32 scheme: the kernels are bound by the shared-memory operand pipe, A is 2/3 of an MMA's bytes.
+enum : int { kCollNone = 0, kCollFill = 1, kCollLastUse = 2 };
+template <int COLL>
+__device__ __forceinline__ void mma_tf32_lo32_c(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32,
+                                                uint32_t idesc, uint32_t accumulate) {
+  if constexpr (COLL == kCollFill) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (COLL == kCollLastUse) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    mma_tf32_lo32(tmem_d, a_lo32, b_lo32, desc_hi32, idesc, accumulate);
+  }
+}
 // low / high words of a shared-memory descriptor (see make_smem_desc)
 __device__ __forceinline__ uint32_t desc_lo32(uint32_t smem_addr, uint32_t lbo_bytes) {
   return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);

@@ -15,7 +15,7 @@ x = torch.randn(b, r, r, r, c, device="cuda")
 w = torch.randn(c, c, 3, 3, 3, device="cuda") * 0.05
 w_hi, w_lo = dense.prep_weight(w)
 ref = None
-for exp in (0, 57):
+for exp in (0, 2, 0, 2):
     os.environ["PVCNN_HALO_EXP"] = str(exp)
     out = dense.igemm_conv(x, x, w_hi, w_lo, None, npass=3)
     if exp == 0: ref = out.clone()
