@@ -196,12 +196,14 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
   float *gfpt;              /* Mp*ci */
   float *d2;                /* Mv*max(ci,co) */
   float *gy2, *gy2_lo, *gy1, *gy1_lo; /* Mv*co */
+  int *sparse;              /* pvcnn_pvconv_sparse_ints(): activity lists for tile skipping (NULL = dense) */
   float *se;                /* with_se: b*(7*co + cout/8)  (pooled sums, mean, hidden, gate, d gate, dense term) */
 } pvcnn_pvconv_ws;
 
 /* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided (3xTF32 mode: the weight-
  * gradient kernel TMA-loads them); otherwise those pointers may be NULL. */
 PVCNN_API int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d);
+PVCNN_API long long pvcnn_pvconv_sparse_ints(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d);
 /* features [b,cin,n], coords [b,3,n] -> out [b,cout,n] */

@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(log)
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                    "-Xcompiler", "-fPIC"]
+                                                    "-Xcompiler", "-fPIC", "-Xlinker", "--no-undefined"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))

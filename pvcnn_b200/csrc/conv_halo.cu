@@ -45,6 +45,8 @@ struct HaloParams {
   const float *bias;
   float *out;
   int *err;
+  const int4 *unit_list;          // optional compact list of (x0, y0, b, -) units to compute; others are skipped
+  const int *unit_count;          //   (device count) -- activity-driven tile skipping, see pvconv_pipeline.cu
   int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 4 skip MMA3, 8 no A loads, 16 no B loads, 32 no epilogue stores
 };
 
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
   const int nphases = 3 * p.kchunks;
   const int half_phase = (nphases + 1) / 2;
   const uint32_t tmem_cols = 512;  // 2 tiles x (main0, main1, corr) x block_n <= 384 -> allocate all
+  const int num_units = p.unit_list ? __ldg(p.unit_count) : p.num_units;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
@@ -94,11 +97,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     if (elect_one()) {
       int abuf = 0;
       uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-        int u = unit;
-        const int y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
-        const int x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
-        const int b = u;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        int x0, y0, b;
+        if (p.unit_list) {
+          const int4 uc = __ldg(p.unit_list + unit);
+          x0 = uc.x; y0 = uc.y; b = uc.z;
+        } else {
+          int u = unit;
+          y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
+          x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
+          b = u;
+        }
         int dz = -1, cc = 0;
         for (int ph = 0; ph < nphases; ++ph) {
           mbar_wait(&a_empty[abuf], aphase ^ 1, p.err, 21);
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     if (elect_one()) {
       int bst = 0;
       uint32_t bphase = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
         int dz = -1, cc = 0;
         for (int ph = 0; ph < nphases; ++ph) {
 #pragma unroll
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
       const uint32_t bn = (uint32_t)p.block_n;
       int abuf = 0, bst = 0, it = 0;
       uint32_t aphase = 0, bphase = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
         mbar_wait(&acc_empty, (uint32_t)((it & 1) ^ 1), p.err, 23);
         tc_fence_after();
         for (int ph = 0; ph < nphases; ++ph) {
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
                 const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
                 const uint32_t first = (t9 == 0 && ks == 0) ? 1u : 0u;
                 if (three) {
-                  if (p.exp & 2) {  // experiment: A_hi fetched once, reused from the collector
+                  if (!(p.exp & 2)) {  // A_hi is fetched from shared memory once and reused from the collector (-3 %)
                     mma_tf32_lo32_c<kCollFill>(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
                     mma_tf32_lo32_c<kCollLastUse>(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
                   } else {
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     const int tid = threadIdx.x - 8 * 32;  // 0..127
     int abuf = 0;
     uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       for (int ph = 0; ph < nphases; ++ph) {
         mbar_wait(&a_full[abuf], aphase, p.err, 26);
         if (three && !(p.exp & 1)) {
@@ -245,11 +254,17 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     const int m = we * 32 + lane;
     const int lz = m % p.sz, ly = m / p.sz;
     int it = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
-      int u = unit;
-      const int y = (u % p.tiles_y) * p.ty + ly; u /= p.tiles_y;
-      const int x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
-      const int b = u;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      int x0, y, b;
+      if (p.unit_list) {
+        const int4 uc = __ldg(p.unit_list + unit);
+        x0 = uc.x; y = uc.y + ly; b = uc.z;
+      } else {
+        int u = unit;
+        y = (u % p.tiles_y) * p.ty + ly; u /= p.tiles_y;
+        x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
+        b = u;
+      }
       mbar_wait(&acc_full, (uint32_t)(it & 1), p.err, 27);
       tc_fence_after();
 #pragma unroll
@@ -315,7 +330,8 @@ static int *g_halo_err = nullptr;
 
 // Returns PVCNN_E_UNSUPPORTED when the shape is outside this kernel's envelope (caller falls back to v1).
 int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
-                     const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream) {
+                     const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream,
+                     const int4 *unit_list, const int *unit_count) {
   if (!conv_halo_supported(sx, sy, sz, cout)) return PVCNN_E_UNSUPPORTED;
   PVB_CHECK_ARG(a && w_hi && out && (npass == 1 || w_lo) && lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0);
   if (!g_halo_err) {
@@ -337,6 +353,7 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
   p.a_bytes = p.a_rows * HC_KC * 4;
   p.b_bytes = (uint32_t)p.block_n * HC_KC * 4;
   p.bias = bias; p.out = out; p.err = g_halo_err;
+  p.unit_list = unit_list; p.unit_count = unit_count;
   { const char *e = getenv("PVCNN_HALO_EXP"); p.exp = e ? atoi(e) : 0; }
   if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
 

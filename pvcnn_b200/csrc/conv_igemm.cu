@@ -340,7 +340,7 @@ int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsign
 
 int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
                      const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass,
-                     cudaStream_t stream);  // conv_halo.cu
+                     cudaStream_t stream, const int4 *unit_list, const int *unit_count);  // conv_halo.cu
 
 // Optional device buffer [8] of stall-cycle counters written by CTA 0 of the tensor-core kernels when
 // PVCNN_STALL_PROFILE=1 (tools/stall_profile.py reads it back through pvcnn_stall_profile_read).
@@ -409,7 +409,8 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
     const char *e_conv = getenv("PVCNN_B200_CONV");
     const bool force_v1 = e_conv && e_conv[0] == 'v' && e_conv[1] == '1';
     if (!force_v1) {
-      const int rc = conv_halo_launch(nb, sx, sy, sz, k, cout, a_hi, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream);
+      const int rc = conv_halo_launch(nb, sx, sy, sz, k, cout, a_hi, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream,
+                                      nullptr, nullptr);
       if (rc != PVCNN_E_UNSUPPORTED) return rc;
     }
   }

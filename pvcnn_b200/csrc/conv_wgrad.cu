@@ -48,6 +48,8 @@ struct WgradParams {
   int lo_in_kernel;               // 1: converter warps derive lo from hi in shared memory; 0: lo tensors are TMA-loaded
   float *dw;                // [cout][cin][ntaps], zero-initialised by the launcher
   int *err;
+  const int4 *ktile_list;   // optional compact list of (z0, y0, x0, b) k-tiles that can contribute (activity skipping)
+  const int *ktile_count;
   long long *dbg;           // optional [8] stall-cycle counters of CTA 0 (PVCNN_STALL_PROFILE)
 };
 
@@ -88,9 +90,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t tmem_base = tmem_base_smem;
 
   // contiguous range of k-tiles walked by this CTA (coordinates advance incrementally: no div/mod per stage)
-  const long long per_cta = (p.num_ktiles + p.ksplit - 1) / p.ksplit;
+  const long long num_ktiles = p.ktile_list ? (long long)__ldg(p.ktile_count) : p.num_ktiles;
+  const long long per_cta = (num_ktiles + p.ksplit - 1) / p.ksplit;
   const long long kt_begin = (long long)split * per_cta;
-  const long long my_tiles = max(0LL, min(p.num_ktiles, kt_begin + per_cta) - kt_begin);
+  const long long my_tiles = max(0LL, min(num_ktiles, kt_begin + per_cta) - kt_begin);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -118,7 +121,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       int x0 = kt % p.sx; kt /= p.sx;
       int b = kt;
       for (long long t = 0; t < my_tiles; ++t) {
-        const int z0 = tzi * p.bz, y0 = tyi * p.by;
+        int z0 = tzi * p.bz, y0 = tyi * p.by;
+        if (p.ktile_list) {
+          const int4 kc = __ldg(p.ktile_list + kt_begin + t);
+          z0 = kc.x; y0 = kc.y; x0 = kc.z; b = kc.w;
+        }
         mbar_wait_t(&empty_bar[stage], phase ^ 1, p.err, 11, stall);
         uint8_t *st = smem + (size_t)stage * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -315,7 +322,8 @@ static int *g_wg_err = nullptr;
 
 // x: layer input [nb,sx,sy,sz,ldx] (cin valid), g: output gradient [nb,sx,sy,sz,ldg] (cout valid)
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
-                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s) {
+                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
+                 const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
   PVB_CHECK_ARG(x_hi && g_hi && dw && ldx % 4 == 0 && ldg % 4 == 0);
   if (cout > 128) return PVCNN_E_UNSUPPORTED;  // TODO(round 2): N tiling for wide SharedMLPs
@@ -358,6 +366,9 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   p.dw = dw;
   p.err = g_wg_err;
   p.dbg = pvb::stall_profile_buffer();
+  p.ktile_list = ktile_list; p.ktile_count = ktile_count;
+  if (bz_out) *bz_out = p.bz;
+  if (by_out) *by_out = p.by;
   p.stages = min(WG_MAX_STAGES, (int)((227 * 1024 - 2048) / p.stage_bytes));
   PVB_CHECK_ARG(p.stages >= 2 && p.num_ktiles < (1LL << 31));
   PVB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)cout * cin * ntaps, s));
@@ -385,5 +396,5 @@ extern "C" int pvcnn_conv_wgrad(int nb, int sx, int sy, int sz, int cin, int cou
                                 const float *x_lo, int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw,
                                 int npass, void *stream) {
   return pvb::wgrad_launch(nb, sx, sy, sz, cin, cout, ntaps, x_hi, x_lo, ldx, g_hi, g_lo, ldg, dw, npass,
-                           (cudaStream_t)stream);
+                           (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr);
 }

@@ -831,6 +831,170 @@ int launch_bwd_final(int b, int n, int c, int cp, int r3, const int *ind, const 
   return 0;
 }
 
+
+// --------------------------------------------------------------------------------------------
+// Activity (sparsity) bookkeeping.  Voxelization(normalize=True) maps every cloud into the sphere of diameter 1
+// inscribed in the unit cube (modules/voxelization.py:19), so at most pi/6 of the grid can ever be occupied -- in practice
+// 10-20 %.  conv1's input is exactly zero elsewhere, conv2's input is a per-channel constant there.  We therefore build
+// compact lists of the tiles that can differ from that closed form and let the tensor-core kernels walk only those.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colocc_kernel(int r, long long ncols, const int *__restrict__ cnt,
+                                                     unsigned char *__restrict__ occ) {
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const int *c = cnt + col * r;
+  int any = 0;
+  for (int z = 0; z < r; ++z) any |= c[z];
+  occ[col] = any != 0;
+}
+
+__device__ __forceinline__ bool occ_any(const unsigned char *occ, int b, int r, int xa, int xb, int ya, int yb) {
+  xa = max(xa, 0); ya = max(ya, 0); xb = min(xb, r - 1); yb = min(yb, r - 1);
+  for (int x = xa; x <= xb; ++x)
+    for (int y = ya; y <= yb; ++y)
+      if (occ[((size_t)b * r + x) * r + y]) return true;
+  return false;
+}
+
+// counts: [0] conv1-forward units, [1] conv1-dgrad units, [2] conv2-forward units, [3] conv1-wgrad k-tiles
+__global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
+                                                          const unsigned char *__restrict__ occ, int *counts,
+                                                          unsigned char *__restrict__ act1, int4 *fwd1, int4 *dgrad1,
+                                                          int4 *wg1) {
+  const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
+  const int n_units = nb * pairs_x * tiles_y;
+  const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
+  const int n_kt = nb * r * wg_ty * wg_tz;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_units) {
+    int u = t;
+    const int yt = u % tiles_y; u /= tiles_y;
+    const int xp = u % pairs_x; u /= pairs_x;
+    const int b = u, x0 = xp * 2, y0 = yt * ty;
+    const bool a_fwd = occ_any(occ, b, r, x0 - 1, x0 + 2, y0 - 1, y0 + ty);   // halo of the two tiles
+    const bool a_dg = occ_any(occ, b, r, x0, x0 + 1, y0, y0 + ty - 1);        // the tiles themselves
+    act1[t] = a_fwd;
+    if (a_fwd) fwd1[atomicAdd(counts + 0, 1)] = make_int4(x0, y0, b, 0);
+    if (a_dg) dgrad1[atomicAdd(counts + 1, 1)] = make_int4(x0, y0, b, 0);
+  }
+  if (t < n_kt) {
+    int u = t;
+    const int tz = u % wg_tz; u /= wg_tz;
+    const int tyi = u % wg_ty; u /= wg_ty;
+    const int x = u % r; u /= r;
+    const int b = u, y0 = tyi * wg_by;
+    // X shifted by (dx,dy) in [-1,1] must be non-zero somewhere in the tile's rows (occupancy is per (x,y) column)
+    if (occ_any(occ, b, r, x - 1, x + 1, y0 - 1, y0 + wg_by)) wg1[atomicAdd(counts + 3, 1)] = make_int4(tz * wg_bz, y0, x, b);
+  }
+}
+
+// conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
+// voxel of a conv1-active unit
+__global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty, const unsigned char *__restrict__ act1,
+                                                          int *counts, int4 *fwd2) {
+  const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * pairs_x * tiles_y) return;
+  int u = t;
+  const int yt = u % tiles_y; u /= tiles_y;
+  const int xp = u % pairs_x; u /= pairs_x;
+  const int b = u, x0 = xp * 2, y0 = yt * ty;
+  const int xpa = max(0, (x0 - 1) / 2), xpb = min(pairs_x - 1, (x0 + 2) / 2);
+  const int yta = max(0, (y0 - 1) / ty), ytb = min(tiles_y - 1, (y0 + ty) / ty);
+  bool a = false;
+  for (int i = xpa; i <= xpb; ++i)
+    for (int j = yta; j <= ytb; ++j) a = a || act1[((size_t)b * pairs_x + i) * tiles_y + j];
+  if (a) fwd2[atomicAdd(counts + 2, 1)] = make_int4(x0, y0, b, 0);
+}
+
+int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts, unsigned char *occ,
+                          unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1, cudaStream_t s) {
+  PVB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), s));
+  const long long ncols = (long long)nb * r * r;
+  PVB_LAUNCH(colocc_kernel, ceil_div(ncols, 256), 256, 0, s, r, ncols, cnt, occ);
+  const int n_units = nb * ((r + 1) / 2) * ((r + ty - 1) / ty);
+  const int n_kt = nb * r * ((r + wg_by - 1) / wg_by) * ((r + wg_bz - 1) / wg_bz);
+  PVB_LAUNCH(build_lists_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, counts, act1,
+             fwd1, dgrad1, wg1);
+  PVB_LAUNCH(build_list2_kernel, ceil_div(n_units, 256), 256, 0, s, nb, r, ty, act1, counts, fwd2);
+  return 0;
+}
+
+// out[row][c] = bias[c]   (conv of an all-zero neighbourhood)
+__global__ void __launch_bounds__(256) fill_bias_rows_kernel(long long total4, int c, int cp,
+                                                             const float *__restrict__ bias, float *__restrict__ out) {
+  const int cp4 = cp >> 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(t % cp4) * 4;
+    float4 v;
+    v.x = c0 + 0 < c ? __ldg(bias + c0 + 0) : 0.f;
+    v.y = c0 + 1 < c ? __ldg(bias + c0 + 1) : 0.f;
+    v.z = c0 + 2 < c ? __ldg(bias + c0 + 2) : 0.f;
+    v.w = c0 + 3 < c ? __ldg(bias + c0 + 3) : 0.f;
+    stg_stream4(out + t * 4, v);
+  }
+}
+
+int launch_fill_bias_rows(long long rows, int c, int cp, const float *bias, float *out, cudaStream_t s) {
+  const long long total4 = rows * (cp / 4);
+  PVB_LAUNCH(fill_bias_rows_kernel, grid_for(total4, 256 * 4, kNumSMs * 8), 256, 0, s, total4, c, cp, bias, out);
+  return 0;
+}
+
+// conv of a per-channel constant input c1[ci] = leaky(bn1(b1[ci])): 27 boundary classes (lo edge / interior / hi edge
+// per axis decide which taps fall inside the grid).  classsum[cls][co] = b2[co] + sum_{valid taps} sum_ci w[co][ci][tap] c1[ci]
+__global__ void __launch_bounds__(128) conv_const_classes_kernel(int cin, int cout, int cp_out, float slope,
+                                                                 const float *__restrict__ w /*[co][ci][27]*/,
+                                                                 const float *__restrict__ bias2,
+                                                                 const float *__restrict__ bias1, BnCoef bn1,
+                                                                 float *__restrict__ classsum) {
+  extern __shared__ float c1[];
+  for (int i = threadIdx.x; i < cin; i += blockDim.x) c1[i] = leaky(fmaf(bias1[i], bn1.scale[i], bn1.shift[i]), slope);
+  __syncthreads();
+  const int cls = blockIdx.x, cx = cls / 9, cy = (cls / 3) % 3, cz = cls % 3;
+  for (int co = threadIdx.x; co < cp_out; co += blockDim.x) {
+    float acc = 0.f;
+    if (co < cout) {
+      acc = bias2[co];
+      for (int tap = 0; tap < 27; ++tap) {
+        const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
+        const bool ok = !(cx == 0 && dx < 0) && !(cx == 2 && dx > 0) && !(cy == 0 && dy < 0) && !(cy == 2 && dy > 0) &&
+                        !(cz == 0 && dz < 0) && !(cz == 2 && dz > 0);
+        if (!ok) continue;
+        float t = 0.f;
+        for (int ci = 0; ci < cin; ++ci) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], c1[ci], t);
+        acc += t;
+      }
+    }
+    classsum[(size_t)cls * cp_out + co] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_class_rows_kernel(long long total4, int r, int cp,
+                                                              const float *__restrict__ classsum,
+                                                              float *__restrict__ out) {
+  const int cp4 = cp >> 2;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % cp4);
+    long long v = t / cp4;
+    const int z = (int)(v % r); v /= r;
+    const int y = (int)(v % r); v /= r;
+    const int x = (int)(v % r);
+    const int cls = ((x == 0 ? 0 : (x == r - 1 ? 2 : 1)) * 3 + (y == 0 ? 0 : (y == r - 1 ? 2 : 1))) * 3 +
+                    (z == 0 ? 0 : (z == r - 1 ? 2 : 1));
+    stg_stream4(out + t * 4, ld4(classsum + (size_t)cls * cp + c4 * 4));
+  }
+}
+
+int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
+                           const float *bias1, BnCoef bn1, float *classsum, float *out, cudaStream_t s) {
+  PVB_LAUNCH(conv_const_classes_kernel, 27, 128, cin * sizeof(float), s, cin, cout, cp_out, slope, w, bias2, bias1, bn1,
+             classsum);
+  const long long total4 = (long long)nb * r * r * r * (cp_out / 4);
+  PVB_LAUNCH(fill_class_rows_kernel, grid_for(total4, 256 * 4, kNumSMs * 8), 256, 0, s, total4, r, cp_out, classsum, out);
+  return 0;
+}
+
 int launch_memset_f32(float *p, long long n, cudaStream_t s) {
   PVB_CUDA(cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, s));
   return 0;

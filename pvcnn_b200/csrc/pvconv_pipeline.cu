@@ -10,8 +10,12 @@ namespace pvb {
 int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
                  int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                  int npass, cudaStream_t stream);
+int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
+                     const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream,
+                     const int4 *unit_list, const int *unit_count);
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
-                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s);
+                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
+                 const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out);
 
 bool conv_halo_supported(int sx, int sy, int sz, int cout);  // conv_halo.cu
 
@@ -19,6 +23,46 @@ bool conv_halo_supported(int sx, int sy, int sz, int cout);  // conv_halo.cu
 // bound and runs 1.6x faster when it TMA-loads lo instead of converting it in the kernel; the v1 conv kernel
 // (odd resolutions, > 64 channels) needs them too.  The halo conv kernel ignores them.
 static bool needs_grid_lo(const pvcnn_pvconv_desc *d) { return d->npass > 1; }
+
+// ---- activity-driven skipping: layout of ws->sparse (ints) --------------------------------------------
+struct SparseBuf {
+  int *counts;               // [8]
+  unsigned char *occ, *act1;
+  int4 *fwd1, *dgrad1, *fwd2, *wg1;
+  float *classsum;           // [27][co]
+  int ty, wg_bz, wg_by;
+  long long total_ints;
+};
+static inline long long up4(long long x) { return (x + 3) / 4 * 4; }
+static SparseBuf sparse_at(int *base, int b, int r, int co) {
+  SparseBuf v{};
+  v.ty = 128 / r > 0 ? 128 / r : 1;
+  v.wg_bz = ((r < 32 ? r : 32) + 7) / 8 * 8;   // must mirror conv_wgrad.cu's k-tile box
+  v.wg_by = 32 / v.wg_bz > 0 ? 32 / v.wg_bz : 1;
+  if (v.wg_by > r) v.wg_by = r;
+  const long long units = (long long)b * ((r + 1) / 2) * ((r + v.ty - 1) / v.ty);
+  const long long kt = (long long)b * r * ((r + v.wg_by - 1) / v.wg_by) * ((r + v.wg_bz - 1) / v.wg_bz);
+  long long o = 0;
+  v.counts = base + o; o += 8;
+  v.occ = reinterpret_cast<unsigned char *>(base + o); o += up4((long long)b * r * r) / 4 + 4;
+  v.act1 = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  o = up4(o);
+  v.fwd1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
+  v.dgrad1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
+  v.fwd2 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
+  v.wg1 = reinterpret_cast<int4 *>(base + o); o += 4 * kt;
+  v.classsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
+  v.total_ints = o;
+  return v;
+}
+// Skipping applies when every 3x3x3 conv of the block runs on the halo kernel (its unit geometry) and r >= 4.
+static bool sparse_enabled(const pvcnn_pvconv_desc *d) {
+  const char *e = getenv("PVCNN_B200_SPARSE");
+  if (e && e[0] == '0') return false;
+  const char *v = getenv("PVCNN_B200_CONV");
+  if (v && v[0] == 'v' && v[1] == '1') return false;
+  return d->r >= 4 && conv_halo_supported(d->r, d->r, d->r, d->cout) && conv_halo_supported(d->r, d->r, d->r, d->cin);
+}
 
 static inline int pad4(int x) { return (x + 3) / 4 * 4; }
 static inline int ld32(int x) { return (x + 31) / 32 * 32; }
@@ -85,6 +129,10 @@ long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d) { return wprep_l
 
 int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d) { return needs_grid_lo(d) ? 1 : 0; }
 
+long long pvcnn_pvconv_sparse_ints(const pvcnn_pvconv_desc *d) {
+  return sparse_at(nullptr, d->b, d->r, (d->cout + 3) / 4 * 4).total_ints;
+}
+
 long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d) {
   const long long co = pad4(d->cout > d->cin ? d->cout : d->cin);
   const long long blocks_pts = (long long)d->b * ((d->n + 31) / 32);
@@ -111,6 +159,13 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   // 1. coordinates -> voxel indices                               (modules/voxelization.py:17-24, vox.cu:18-34)
   PVB_TRY(pvcnn_voxelize_coords(b, n, r, d->normalize, d->eps, coords, ws->nc, ws->vc, stream));
   PVB_TRY(launch_vox_index_count(b, n, r, ws->vc, ws->ind, ws->cnt, s));
+  const bool sparse = sparse_enabled(d) && ws->sparse != nullptr;
+  SparseBuf sp{};
+  if (sparse) {  // which tiles can differ from the closed form (zero / constant input)?
+    sp = sparse_at(ws->sparse, b, r, co);
+    PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.fwd1, sp.dgrad1,
+                                  sp.fwd2, sp.wg1, s));
+  }
   // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
   PVB_TRY(launch_memset_f32(ws->g0, Mv * ci, s));
@@ -126,8 +181,14 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
 
   BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
   // 4. conv1 -> BN1 -> LeakyReLU                                   (modules/pvconv.py:21-23)
-  PVB_TRY(igemm_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, wp + W.w1f, wp + W.w1f + W.n1f,
-                       ld32(d->cin), prm->b1, ws->y1, co, d->npass, s));
+  if (sparse) {  // zero neighbourhood -> conv1 = bias; only the listed units run on the tensor cores
+    PVB_TRY(launch_fill_bias_rows(Mv, d->cout, co, prm->b1, ws->y1, s));
+    PVB_TRY(conv_halo_launch(b, r, r, r, d->cin, d->cout, ws->g0, ci, wp + W.w1f, wp + W.w1f + W.n1f, ld32(d->cin), prm->b1,
+                             ws->y1, co, d->npass, s, sp.fwd1, sp.counts + 0));
+  } else {
+    PVB_TRY(igemm_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, wp + W.w1f, wp + W.w1f + W.n1f,
+                         ld32(d->cin), prm->b1, ws->y1, co, d->npass, s));
+  }
   if (d->training) {
     PVB_TRY(launch_bn_stats(Mv, co, ws->y1, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g1, prm->be1,
@@ -137,8 +198,14 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   }
   PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, glo ? ws->z1_lo : nullptr, s));
   // 5. conv2 -> BN2 statistics (BN2-apply + LeakyReLU are folded into the devoxelize gather)
-  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, wp + W.w2f, wp + W.w2f + W.n2f,
-                       ld32(d->cout), prm->b2, ws->y2, co, d->npass, s));
+  if (sparse) {  // constant neighbourhood -> conv2 = one of 27 boundary-class constants
+    PVB_TRY(launch_fill_const_conv(b, r, d->cout, d->cout, co, d->slope, prm->w2, prm->b2, prm->b1, bn1, sp.classsum, ws->y2, s));
+    PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cout, ws->z1, co, wp + W.w2f, wp + W.w2f + W.n2f, ld32(d->cout),
+                             prm->b2, ws->y2, co, d->npass, s, sp.fwd2, sp.counts + 2));
+  } else {
+    PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, wp + W.w2f, wp + W.w2f + W.n2f,
+                         ld32(d->cout), prm->b2, ws->y2, co, d->npass, s));
+  }
   if (d->training) {
     PVB_TRY(launch_bn_stats(Mv, co, ws->y2, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g2, prm->be2,
@@ -184,6 +251,9 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   const WPrep W = wprep_layout(d);
   float *wp = ws->wprep;
   BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
+  const bool sparse = sparse_enabled(d) && ws->sparse != nullptr;  // lists were built by the forward pass
+  SparseBuf sp{};
+  if (sparse) sp = sparse_at(ws->sparse, b, r, co);
   float *S = ws->sums;  // [16][co]: 0 S1, 1 S2, 2 T1, 3 T2, 4 U1, 5 U2, 6.. column sums
   int nblk = 0;
   const size_t cb = sizeof(float) * (size_t)d->cout;
@@ -228,10 +298,10 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(igemm_launch(1, 1, 1, (int)Mp, d->cout, d->cin, 1, ws->gpp, ws->gpp_lo, co, wp + W.wpd, wp + W.wpd + W.npd,
                        ld32(d->cout), nullptr, ws->gfpt, ci, d->npass, s));
   PVB_TRY(wgrad_launch(1, 1, 1, (int)Mp, d->cin, d->cout, 1, ws->fcl, ws->fcl_lo, ci, ws->gpp, ws->gpp_lo, co, gr->wp,
-                       d->npass, s));
+                       d->npass, s, nullptr, nullptr, nullptr, nullptr));
   // 5. conv2: wgrad (needs z1, gy2) then dgrad into the d2 buffer (d2 was consumed in step 2)
   PVB_TRY(wgrad_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, ws->gy2, ws->gy2_lo, co, gr->w2,
-                       d->npass, s));
+                       d->npass, s, nullptr, nullptr, nullptr, nullptr));
   float *gz1 = ws->d2;
   PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->gy2, ws->gy2_lo, co, wp + W.w2d, wp + W.w2d + W.n2d,
                        ld32(d->cout), nullptr, gz1, co, d->npass, s));
@@ -245,11 +315,20 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 8 * co, s));
   PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
   // 7. conv1: wgrad, dgrad (into the d2 buffer again: gz1 is dead)
+  // conv1: its input G0 is zero outside the occupied columns -> only the listed k-tiles contribute to dW1, and the
+  // data gradient is only consumed at occupied voxels -> only the listed units are produced (the rest of gg0 is never read)
+  int wbz = 0, wby = 0;
   PVB_TRY(wgrad_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, ws->gy1, ws->gy1_lo, co, gr->w1,
-                       d->npass, s));
+                       d->npass, s, sparse ? sp.wg1 : nullptr, sparse ? sp.counts + 3 : nullptr, &wbz, &wby));
+  if (sparse) PVB_CHECK_ARG(wbz == sp.wg_bz && wby == sp.wg_by);
   float *gg0 = ws->d2;
-  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cin, 27, ws->gy1, ws->gy1_lo, co, wp + W.w1d, wp + W.w1d + W.n1d,
-                       ld32(d->cout), nullptr, gg0, ci, d->npass, s));
+  if (sparse) {
+    PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cin, ws->gy1, co, wp + W.w1d, wp + W.w1d + W.n1d, ld32(d->cout),
+                             nullptr, gg0, ci, d->npass, s, sp.dgrad1, sp.counts + 1));
+  } else {
+    PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cin, 27, ws->gy1, ws->gy1_lo, co, wp + W.w1d, wp + W.w1d + W.n1d,
+                         ld32(d->cout), nullptr, gg0, ci, d->npass, s));
+  }
   // 8. avg_voxelize backward + point-branch gradient              (vox.cu:86-110)
   PVB_TRY(launch_bwd_final(b, n, d->cin, ci, r3, ws->ind, ws->cnt, gg0, ws->gfpt, grad_features, s));
   return 0;

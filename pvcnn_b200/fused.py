@@ -31,7 +31,7 @@ _GRAD_FIELDS = ["w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "wp", "bp", "g
 _WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("fcl_lo", _F), ("g0", _F),
               ("g0_lo", _F), ("y1", _F), ("z1", _F), ("z1_lo", _F), ("y2", _F), ("p", _F), ("coef", _F),
               ("wprep", _F), ("partials", _F), ("sums", _F), ("ga", _F), ("gpp", _F), ("gpp_lo", _F),
-              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("se", _F)]
+              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("sparse", _I), ("se", _F)]
 
 
 class Params(ctypes.Structure):
@@ -80,6 +80,7 @@ class _Plan:
         lib = _lib.load()
         lib.pvcnn_pvconv_wprep_floats.restype = ctypes.c_longlong
         lib.pvcnn_pvconv_partials_floats.restype = ctypes.c_longlong
+        lib.pvcnn_pvconv_sparse_ints.restype = ctypes.c_longlong
         b, n, r = desc.b, desc.n, desc.r
         ci, co = _pad4(desc.cin), _pad4(desc.cout)
         mv, mp = b * r ** 3, b * n
@@ -106,6 +107,8 @@ class _Plan:
         alloc["wprep"] = _scratch("wprep", lib.pvcnn_pvconv_wprep_floats(ctypes.byref(desc)), device)
         alloc["partials"] = _scratch("partials", lib.pvcnn_pvconv_partials_floats(ctypes.byref(desc)), device)
         alloc["sums"] = _scratch("sums", 16 * max(ci, co), device)
+        nsp = lib.pvcnn_pvconv_sparse_ints(ctypes.byref(desc))  # activity lists: built in forward, reused in backward
+        alloc["sparse"] = i(nsp) if need_backward else _scratch("sparse", nsp, device, torch.int32)
         self.t = alloc
         self.desc = desc
         self.device = device

@@ -159,3 +159,38 @@ def test_pvconv_fused_with_se(b, n, c, r, normalize, monkeypatch):
             assert np.abs(got - want).max() < 1e-4 * scale, name
         else:
             assert rel_err(got, want) < 5e-5, name
+
+
+@pytest.mark.parametrize("spread", ["ball", "full_cube", "single_voxel"])
+def test_activity_skipping_equals_dense(spread, monkeypatch):
+    """Tile skipping (zero / constant neighbourhoods in closed form) must reproduce the dense computation,
+    whatever the occupancy: normalised ball (10-20 % occupied), the whole cube, or a single voxel."""
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
+    g = rng(35)
+    b, n, c, r = 2, 2048, 32, 16
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    go = g.standard_normal((b, c, n), dtype=np.float32)
+    normalize = spread == "ball"
+    if spread == "ball":
+        co = s3dis_like_coords(g, b, n)
+    elif spread == "full_cube":   # normalize=False: (x - mean + 1) / 2 covers [0,1]^3
+        co = g.random((b, 3, n), dtype=np.float32) * 2.0 - 1.0
+    else:
+        co = np.zeros((b, 3, n), np.float32) + 1e-3 * g.random((b, 3, n), dtype=np.float32)
+    m = make_block(c, c, r, normalize=normalize).cuda().train()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PVCNN_B200_SPARSE", mode)
+        for p in m.parameters():
+            p.grad = None
+        ft = torch.from_numpy(f).cuda().requires_grad_(True)
+        out, _ = m((ft, torch.from_numpy(co).cuda()))
+        out.backward(torch.from_numpy(go).cuda())
+        res[mode] = (out.detach().cpu().numpy(), ft.grad.cpu().numpy(),
+                     {k: p.grad.cpu().numpy() for k, p in m.named_parameters()})
+    assert rel_err(res["1"][0], res["0"][0]) < 2e-6
+    assert rel_err(res["1"][1], res["0"][1]) < 5e-6
+    for k in res["0"][2]:
+        if k.endswith("0.bias") or k.endswith("3.bias"):
+            continue  # exactly-zero gradients (summation noise only)
+        assert rel_err(res["1"][2][k], res["0"][2][k]) < 2e-5, k
