@@ -890,10 +890,27 @@ __global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty,
 
 // conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
 // voxel of a conv1-active unit
-__global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty, const unsigned char *__restrict__ act1,
-                                                          int *counts, int4 *fwd2) {
+__global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
+                                                          const unsigned char *__restrict__ act1, int *counts,
+                                                          int4 *fwd2, int4 *wg2, unsigned char *__restrict__ wg2_flag) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  {  // conv2 weight gradient: k-tile is "active" iff a tap-shifted row can see a voxel where Z1 is not the constant
+    const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
+    if (t < nb * r * wg_ty * wg_tz) {
+      int u = t;
+      const int tz = u % wg_tz; u /= wg_tz;
+      const int tyi = u % wg_ty; u /= wg_ty;
+      const int x = u % r; u /= r;
+      const int b = u, y0 = tyi * wg_by;
+      bool a = false;
+      for (int xx = max(0, x - 1); xx <= min(r - 1, x + 1); ++xx)
+        for (int yy = max(0, y0 - 1); yy <= min(r - 1, y0 + wg_by); ++yy)
+          a = a || act1[((size_t)b * pairs_x + xx / 2) * tiles_y + yy / ty];
+      wg2_flag[t] = a;
+      if (a) wg2[atomicAdd(counts + 4, 1)] = make_int4(tz * wg_bz, y0, x, b);
+    }
+  }
   if (t >= nb * pairs_x * tiles_y) return;
   int u = t;
   const int yt = u % tiles_y; u /= tiles_y;
@@ -908,7 +925,8 @@ __global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty,
 }
 
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts, unsigned char *occ,
-                          unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1, cudaStream_t s) {
+                          unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1, int4 *wg2,
+                          unsigned char *wg2_flag, cudaStream_t s) {
   PVB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), s));
   const long long ncols = (long long)nb * r * r;
   PVB_LAUNCH(colocc_kernel, ceil_div(ncols, 256), 256, 0, s, r, ncols, cnt, occ);
@@ -916,7 +934,8 @@ int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int
   const int n_kt = nb * r * ((r + wg_by - 1) / wg_by) * ((r + wg_bz - 1) / wg_bz);
   PVB_LAUNCH(build_lists_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, counts, act1,
              fwd1, dgrad1, wg1);
-  PVB_LAUNCH(build_list2_kernel, ceil_div(n_units, 256), 256, 0, s, nb, r, ty, act1, counts, fwd2);
+  PVB_LAUNCH(build_list2_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, counts, fwd2,
+             wg2, wg2_flag);
   return 0;
 }
 
@@ -942,56 +961,141 @@ int launch_fill_bias_rows(long long rows, int c, int cp, const float *bias, floa
 }
 
 // conv of a per-channel constant input c1[ci] = leaky(bn1(b1[ci])): 27 boundary classes (lo edge / interior / hi edge
-// per axis decide which taps fall inside the grid).  classsum[cls][co] = b2[co] + sum_{valid taps} sum_ci w[co][ci][tap] c1[ci]
-__global__ void __launch_bounds__(128) conv_const_classes_kernel(int cin, int cout, int cp_out, float slope,
-                                                                 const float *__restrict__ w /*[co][ci][27]*/,
-                                                                 const float *__restrict__ bias2,
-                                                                 const float *__restrict__ bias1, BnCoef bn1,
-                                                                 float *__restrict__ classsum) {
+// per axis decide which taps fall inside the grid).  classsum[cls][co] = b2[co] + sum_{valid taps} T[tap][co],
+// T[tap][co] = sum_ci w[co][ci][tap] c1[ci]
+__device__ __forceinline__ bool tap_valid_in_class(int tap, int cls) {
+  const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
+  const int cx = cls / 9, cy = (cls / 3) % 3, cz = cls % 3;
+  return !(cx == 0 && dx < 0) && !(cx == 2 && dx > 0) && !(cy == 0 && dy < 0) && !(cy == 2 && dy > 0) &&
+         !(cz == 0 && dz < 0) && !(cz == 2 && dz > 0);
+}
+
+__global__ void __launch_bounds__(128) conv_const_taps_kernel(int cin, int cout, float slope,
+                                                              const float *__restrict__ w /*[co][ci][27]*/,
+                                                              const float *__restrict__ bias1, BnCoef bn1,
+                                                              float *__restrict__ tapsum /*[27][cout]*/) {
   extern __shared__ float c1[];
   for (int i = threadIdx.x; i < cin; i += blockDim.x) c1[i] = leaky(fmaf(bias1[i], bn1.scale[i], bn1.shift[i]), slope);
   __syncthreads();
-  const int cls = blockIdx.x, cx = cls / 9, cy = (cls / 3) % 3, cz = cls % 3;
+  const int tap = blockIdx.x;
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    float t = 0.f;
+    for (int ci = 0; ci < cin; ++ci) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], c1[ci], t);
+    tapsum[(size_t)tap * cout + co] = t;
+  }
+}
+
+__global__ void __launch_bounds__(128) conv_const_classes_kernel(int cout, int cp_out, const float *__restrict__ bias2,
+                                                                 const float *__restrict__ tapsum,
+                                                                 float *__restrict__ classsum) {
+  const int cls = blockIdx.x;
   for (int co = threadIdx.x; co < cp_out; co += blockDim.x) {
     float acc = 0.f;
     if (co < cout) {
       acc = bias2[co];
-      for (int tap = 0; tap < 27; ++tap) {
-        const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
-        const bool ok = !(cx == 0 && dx < 0) && !(cx == 2 && dx > 0) && !(cy == 0 && dy < 0) && !(cy == 2 && dy > 0) &&
-                        !(cz == 0 && dz < 0) && !(cz == 2 && dz > 0);
-        if (!ok) continue;
-        float t = 0.f;
-        for (int ci = 0; ci < cin; ++ci) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], c1[ci], t);
-        acc += t;
-      }
+      for (int tap = 0; tap < 27; ++tap)
+        if (tap_valid_in_class(tap, cls)) acc += tapsum[(size_t)tap * cout + co];
     }
     classsum[(size_t)cls * cp_out + co] = acc;
   }
 }
 
-__global__ void __launch_bounds__(256) fill_class_rows_kernel(long long total4, int r, int cp,
-                                                              const float *__restrict__ classsum,
+// one CTA per (b, x, y) line of r voxels: the boundary class only varies with z inside the line
+__global__ void __launch_bounds__(256) fill_class_rows_kernel(int r, int cp, const float *__restrict__ classsum,
                                                               float *__restrict__ out) {
   const int cp4 = cp >> 2;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % cp4);
-    long long v = t / cp4;
-    const int z = (int)(v % r); v /= r;
-    const int y = (int)(v % r); v /= r;
-    const int x = (int)(v % r);
-    const int cls = ((x == 0 ? 0 : (x == r - 1 ? 2 : 1)) * 3 + (y == 0 ? 0 : (y == r - 1 ? 2 : 1))) * 3 +
-                    (z == 0 ? 0 : (z == r - 1 ? 2 : 1));
-    stg_stream4(out + t * 4, ld4(classsum + (size_t)cls * cp + c4 * 4));
+  long long line = blockIdx.x;
+  const int y = (int)(line % r), x = (int)((line / r) % r);
+  const int cxy = ((x == 0 ? 0 : (x == r - 1 ? 2 : 1)) * 3 + (y == 0 ? 0 : (y == r - 1 ? 2 : 1))) * 3;
+  float *dst = out + (size_t)line * r * cp;
+  for (int t = threadIdx.x; t < r * cp4; t += blockDim.x) {
+    const int z = t / cp4, c4 = t - z * cp4;
+    const int cls = cxy + (z == 0 ? 0 : (z == r - 1 ? 2 : 1));
+    stg_stream4(dst + (size_t)t * 4, ld4(classsum + (size_t)cls * cp + c4 * 4));
   }
 }
 
 int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
-                           const float *bias1, BnCoef bn1, float *classsum, float *out, cudaStream_t s) {
-  PVB_LAUNCH(conv_const_classes_kernel, 27, 128, cin * sizeof(float), s, cin, cout, cp_out, slope, w, bias2, bias1, bn1,
-             classsum);
-  const long long total4 = (long long)nb * r * r * r * (cp_out / 4);
-  PVB_LAUNCH(fill_class_rows_kernel, grid_for(total4, 256 * 4, kNumSMs * 8), 256, 0, s, total4, r, cp_out, classsum, out);
+                           const float *bias1, BnCoef bn1, float *classsum, float *tapsum, float *out, cudaStream_t s) {
+  PVB_LAUNCH(conv_const_taps_kernel, 27, 128, cin * sizeof(float), s, cin, cout, slope, w, bias1, bn1, tapsum);
+  PVB_LAUNCH(conv_const_classes_kernel, 27, 128, 0, s, cout, cp_out, bias2, tapsum, classsum);
+  PVB_LAUNCH(fill_class_rows_kernel, nb * r * r, 256, 0, s, r, cp_out, classsum, out);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// Weight gradient of conv2 over the region where its input is the constant c1 (k-tiles whose whole tap
+// neighbourhood is constant):  dW2[co][ci][tap] += c1[ci] * sum_{v inactive, tap valid at v} gY2[v][co].
+// Pass 1 reduces gY2 over the inactive k-tiles into the 27 boundary classes; pass 2 is the rank-1 update.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) class_colsum_inactive_kernel(int r, int cp, int by, int bz, long long n_kt,
+                                                                    const unsigned char *__restrict__ kt_active,
+                                                                    const float *__restrict__ g,
+                                                                    float *__restrict__ classsum /*[27][cp], zeroed*/) {
+  extern __shared__ float acc[];  // [27][cp]
+  for (int i = threadIdx.x; i < 27 * cp; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int cp4 = cp >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int tz_n = (r + bz - 1) / bz, ty_n = (r + by - 1) / by;
+  for (long long kt = (long long)blockIdx.x * nwarp + warp; kt < n_kt; kt += (long long)gridDim.x * nwarp) {
+    if (kt_active[kt]) continue;
+    long long u = kt;
+    const int tz = (int)(u % tz_n); u /= tz_n;
+    const int tyi = (int)(u % ty_n); u /= ty_n;
+    const int x = (int)(u % r); u /= r;
+    const int b = (int)u;
+    const int cx = x == 0 ? 0 : (x == r - 1 ? 2 : 1);
+    for (int yy = 0; yy < by; ++yy) {
+      const int y = tyi * by + yy;
+      if (y >= r) break;
+      const int cy = y == 0 ? 0 : (y == r - 1 ? 2 : 1);
+      for (int c4 = lane; c4 < cp4; c4 += 32) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+        for (int zz = 0; zz < bz; ++zz) {
+          const int z = tz * bz + zz;
+          if (z >= r) break;
+          const float4 v = ld4(g + ((((size_t)b * r + x) * r + y) * r + z) * cp + c4 * 4);
+          float4 &d = z == 0 ? s0 : (z == r - 1 ? s2 : s1);
+          d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+        }
+        float *a0 = acc + (size_t)((cx * 3 + cy) * 3 + 0) * cp + c4 * 4;
+        float *a1 = a0 + cp, *a2 = a0 + 2 * cp;
+        atomicAdd(a0 + 0, s0.x); atomicAdd(a0 + 1, s0.y); atomicAdd(a0 + 2, s0.z); atomicAdd(a0 + 3, s0.w);
+        atomicAdd(a1 + 0, s1.x); atomicAdd(a1 + 1, s1.y); atomicAdd(a1 + 2, s1.z); atomicAdd(a1 + 3, s1.w);
+        atomicAdd(a2 + 0, s2.x); atomicAdd(a2 + 1, s2.y); atomicAdd(a2 + 2, s2.z); atomicAdd(a2 + 3, s2.w);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * cp; i += blockDim.x)
+    if (acc[i] != 0.f) atomicAdd(classsum + i, acc[i]);
+}
+
+__global__ void __launch_bounds__(256) wgrad_const_update_kernel(int cin, int cout, int cp, float slope,
+                                                                 const float *__restrict__ classsum,
+                                                                 const float *__restrict__ bias1, BnCoef bn1,
+                                                                 float *__restrict__ dw /*[co][ci][27]*/) {
+  const int tap = blockIdx.x;
+  for (int t = threadIdx.x; t < cout * cin; t += blockDim.x) {
+    const int co = t / cin, ci = t - co * cin;
+    float r = 0.f;
+    for (int cls = 0; cls < 27; ++cls)
+      if (tap_valid_in_class(tap, cls)) r += classsum[(size_t)cls * cp + co];
+    const float c1 = leaky(fmaf(bias1[ci], bn1.scale[ci], bn1.shift[ci]), slope);
+    dw[((size_t)co * cin + ci) * 27 + tap] += c1 * r;
+  }
+}
+
+int launch_wgrad_const_region(int nb, int r, int cin, int cout, int cp, int by, int bz, float slope,
+                              const unsigned char *kt_active, const float *g, const float *bias1, BnCoef bn1,
+                              float *classsum_g, float *dw, cudaStream_t s) {
+  PVB_CUDA(cudaMemsetAsync(classsum_g, 0, sizeof(float) * 27 * (size_t)cp, s));
+  const long long n_kt = (long long)nb * r * ((r + by - 1) / by) * ((r + bz - 1) / bz);
+  const size_t smem = sizeof(float) * 27 * (size_t)cp;
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(class_colsum_inactive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(class_colsum_inactive_kernel, kNumSMs * 2, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum_g);
+  PVB_LAUNCH(wgrad_const_update_kernel, 27, 256, 0, s, cin, cout, cp, slope, classsum_g, bias1, bn1, dw);
   return 0;
 }
 

@@ -81,10 +81,15 @@ int launch_se_backward(int nb, int c, int cp, int hid, long long rows_per_sample
 // ---- activity-driven tile skipping (see fused_ops.cu "Activity bookkeeping") ----
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts /*[8]*/,
                           unsigned char *occ /*[nb*r*r]*/, unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2,
-                          int4 *wg1, cudaStream_t s);
+                          int4 *wg1, int4 *wg2, unsigned char *wg2_flag, cudaStream_t s);
+// dW2 contribution of the k-tiles whose conv2 input is the constant c1 (rank-1, via 27 boundary-class sums of g)
+int launch_wgrad_const_region(int nb, int r, int cin, int cout, int cp, int by, int bz, float slope,
+                              const unsigned char *kt_active, const float *g, const float *bias1, BnCoef bn1,
+                              float *classsum_g /*[27][cp]*/, float *dw, cudaStream_t s);
 int launch_fill_bias_rows(long long rows, int c, int cp, const float *bias, float *out, cudaStream_t s);
 int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
-                           const float *bias1, BnCoef bn1, float *classsum /*[27][cp_out]*/, float *out, cudaStream_t s);
+                           const float *bias1, BnCoef bn1, float *classsum /*[27][cp_out]*/, float *tapsum /*[27][cout]*/, float *out,
+                           cudaStream_t s);
 
 // small helpers
 int launch_memset_f32(float *p, long long n, cudaStream_t s);

@@ -28,8 +28,11 @@ static bool needs_grid_lo(const pvcnn_pvconv_desc *d) { return d->npass > 1; }
 struct SparseBuf {
   int *counts;               // [8]
   unsigned char *occ, *act1;
-  int4 *fwd1, *dgrad1, *fwd2, *wg1;
-  float *classsum;           // [27][co]
+  int4 *fwd1, *dgrad1, *fwd2, *wg1, *wg2;
+  unsigned char *wg2_flag;   // per k-tile: conv2-wgrad tile is computed on the tensor cores (else closed form)
+  float *classsum;           // [27][co]  conv2 forward constants
+  float *tapsum;             // [27][co]
+  float *classsum_g;         // [27][co]  class sums of gY2 over the constant region
   int ty, wg_bz, wg_by;
   long long total_ints;
 };
@@ -51,7 +54,12 @@ static SparseBuf sparse_at(int *base, int b, int r, int co) {
   v.dgrad1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
   v.fwd2 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
   v.wg1 = reinterpret_cast<int4 *>(base + o); o += 4 * kt;
+  v.wg2 = reinterpret_cast<int4 *>(base + o); o += 4 * kt;
+  v.wg2_flag = reinterpret_cast<unsigned char *>(base + o); o += up4(kt) / 4 + 4;
+  o = up4(o);
   v.classsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
+  v.tapsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
+  v.classsum_g = reinterpret_cast<float *>(base + o); o += 27LL * co;
   v.total_ints = o;
   return v;
 }
@@ -164,7 +172,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   if (sparse) {  // which tiles can differ from the closed form (zero / constant input)?
     sp = sparse_at(ws->sparse, b, r, co);
     PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.fwd1, sp.dgrad1,
-                                  sp.fwd2, sp.wg1, s));
+                                  sp.fwd2, sp.wg1, sp.wg2, sp.wg2_flag, s));
   }
   // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
@@ -199,7 +207,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, glo ? ws->z1_lo : nullptr, s));
   // 5. conv2 -> BN2 statistics (BN2-apply + LeakyReLU are folded into the devoxelize gather)
   if (sparse) {  // constant neighbourhood -> conv2 = one of 27 boundary-class constants
-    PVB_TRY(launch_fill_const_conv(b, r, d->cout, d->cout, co, d->slope, prm->w2, prm->b2, prm->b1, bn1, sp.classsum, ws->y2, s));
+    PVB_TRY(launch_fill_const_conv(b, r, d->cout, d->cout, co, d->slope, prm->w2, prm->b2, prm->b1, bn1, sp.classsum, sp.tapsum, ws->y2, s));
     PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cout, ws->z1, co, wp + W.w2f, wp + W.w2f + W.n2f, ld32(d->cout),
                              prm->b2, ws->y2, co, d->npass, s, sp.fwd2, sp.counts + 2));
   } else {
@@ -300,8 +308,13 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(wgrad_launch(1, 1, 1, (int)Mp, d->cin, d->cout, 1, ws->fcl, ws->fcl_lo, ci, ws->gpp, ws->gpp_lo, co, gr->wp,
                        d->npass, s, nullptr, nullptr, nullptr, nullptr));
   // 5. conv2: wgrad (needs z1, gy2) then dgrad into the d2 buffer (d2 was consumed in step 2)
+  // conv2 weight gradient: tensor cores only on the k-tiles that can see a non-constant input voxel; the rest of
+  // the grid (input == c1) contributes a rank-1 term computed from 27 boundary-class sums of gY2
   PVB_TRY(wgrad_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, ws->gy2, ws->gy2_lo, co, gr->w2,
-                       d->npass, s, nullptr, nullptr, nullptr, nullptr));
+                       d->npass, s, sparse ? sp.wg2 : nullptr, sparse ? sp.counts + 4 : nullptr, nullptr, nullptr));
+  if (sparse)
+    PVB_TRY(launch_wgrad_const_region(b, r, d->cout, d->cout, co, sp.wg_by, sp.wg_bz, d->slope, sp.wg2_flag, ws->gy2,
+                                      prm->b1, bn1, sp.classsum_g, gr->w2, s));
   float *gz1 = ws->d2;
   PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->gy2, ws->gy2_lo, co, wp + W.w2d, wp + W.w2d + W.n2d,
                        ld32(d->cout), nullptr, gz1, co, d->npass, s));
