@@ -26,6 +26,14 @@ __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.0f ?
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
+#define PVB_TRY_LAUNCH(expr)     \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s);
+
 static inline int grid_for(long long work_items, int per_block, int max_blocks) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g > max_blocks) g = max_blocks;
@@ -859,7 +867,8 @@ __device__ __forceinline__ bool occ_any(const unsigned char *occ, int b, int r, 
 // counts: [0] conv1-forward units, [1] conv1-dgrad units, [2] conv2-forward units, [3] conv1-wgrad k-tiles
 __global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
                                                           const unsigned char *__restrict__ occ, int *counts,
-                                                          unsigned char *__restrict__ act1, int4 *fwd1, int4 *dgrad1,
+                                                          unsigned char *__restrict__ act1,
+                                                          unsigned char *__restrict__ act_dg, int4 *fwd1, int4 *dgrad1,
                                                           int4 *wg1) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int n_units = nb * pairs_x * tiles_y;
@@ -874,6 +883,7 @@ __global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty,
     const bool a_fwd = occ_any(occ, b, r, x0 - 1, x0 + 2, y0 - 1, y0 + ty);   // halo of the two tiles
     const bool a_dg = occ_any(occ, b, r, x0, x0 + 1, y0, y0 + ty - 1);        // the tiles themselves
     act1[t] = a_fwd;
+    act_dg[t] = a_dg;
     if (a_fwd) fwd1[atomicAdd(counts + 0, 1)] = make_int4(x0, y0, b, 0);
     if (a_dg) dgrad1[atomicAdd(counts + 1, 1)] = make_int4(x0, y0, b, 0);
   }
@@ -891,8 +901,10 @@ __global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty,
 // conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
 // voxel of a conv1-active unit
 __global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
-                                                          const unsigned char *__restrict__ act1, int *counts,
-                                                          int4 *fwd2, int4 *wg2, unsigned char *__restrict__ wg2_flag) {
+                                                          const unsigned char *__restrict__ act1,
+                                                          const unsigned char *__restrict__ act_dg, int *counts,
+                                                          int4 *fwd2, int4 *wg2, unsigned char *__restrict__ wg2_flag,
+                                                          int4 *dg2) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   {  // conv2 weight gradient: k-tile is "active" iff a tap-shifted row can see a voxel where Z1 is not the constant
@@ -922,20 +934,26 @@ __global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty,
   for (int i = xpa; i <= xpb; ++i)
     for (int j = yta; j <= ytb; ++j) a = a || act1[((size_t)b * pairs_x + i) * tiles_y + j];
   if (a) fwd2[atomicAdd(counts + 2, 1)] = make_int4(x0, y0, b, 0);
+  // region G: units whose gY1 is consumed (halo of a conv1-dgrad unit, rows of conv1-wgrad k-tiles) = 3x3 unit
+  // dilation of the units that contain occupied columns; conv2's data gradient and BN1-backward run on G only
+  bool gq = false;
+  for (int i = max(0, xp - 1); i <= min(pairs_x - 1, xp + 1); ++i)
+    for (int j = max(0, yt - 1); j <= min(tiles_y - 1, yt + 1); ++j) gq = gq || act_dg[((size_t)b * pairs_x + i) * tiles_y + j];
+  if (gq) dg2[atomicAdd(counts + 5, 1)] = make_int4(x0, y0, b, 0);
 }
 
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts, unsigned char *occ,
-                          unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1, int4 *wg2,
-                          unsigned char *wg2_flag, cudaStream_t s) {
+                          unsigned char *act1, unsigned char *act_dg, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1,
+                          int4 *wg2, unsigned char *wg2_flag, int4 *dg2, cudaStream_t s) {
   PVB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), s));
   const long long ncols = (long long)nb * r * r;
   PVB_LAUNCH(colocc_kernel, ceil_div(ncols, 256), 256, 0, s, r, ncols, cnt, occ);
   const int n_units = nb * ((r + 1) / 2) * ((r + ty - 1) / ty);
   const int n_kt = nb * r * ((r + wg_by - 1) / wg_by) * ((r + wg_bz - 1) / wg_bz);
   PVB_LAUNCH(build_lists_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, counts, act1,
-             fwd1, dgrad1, wg1);
-  PVB_LAUNCH(build_list2_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, counts, fwd2,
-             wg2, wg2_flag);
+             act_dg, fwd1, dgrad1, wg1);
+  PVB_LAUNCH(build_list2_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, act_dg, counts, fwd2,
+             wg2, wg2_flag, dg2);
   return 0;
 }
 
@@ -1028,17 +1046,17 @@ int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float s
 // neighbourhood is constant):  dW2[co][ci][tap] += c1[ci] * sum_{v inactive, tap valid at v} gY2[v][co].
 // Pass 1 reduces gY2 over the inactive k-tiles into the 27 boundary classes; pass 2 is the rank-1 update.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) class_colsum_inactive_kernel(int r, int cp, int by, int bz, long long n_kt,
-                                                                    const unsigned char *__restrict__ kt_active,
-                                                                    const float *__restrict__ g,
-                                                                    float *__restrict__ classsum /*[27][cp], zeroed*/) {
-  extern __shared__ float acc[];  // [27][cp]
-  for (int i = threadIdx.x; i < 27 * cp; i += blockDim.x) acc[i] = 0.f;
+__global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by, int bz, long long n_kt,
+                                                           const unsigned char *__restrict__ kt_active,
+                                                           const float *__restrict__ g,
+                                                           float *__restrict__ classsum /*[2][27][cp] zeroed: inactive, all*/) {
+  extern __shared__ float acc[];  // [2][27][cp]
+  for (int i = threadIdx.x; i < 2 * 27 * cp; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
   const int cp4 = cp >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int tz_n = (r + bz - 1) / bz, ty_n = (r + by - 1) / by;
   for (long long kt = (long long)blockIdx.x * nwarp + warp; kt < n_kt; kt += (long long)gridDim.x * nwarp) {
-    if (kt_active[kt]) continue;
+    const bool inactive = !kt_active[kt];
     long long u = kt;
     const int tz = (int)(u % tz_n); u /= tz_n;
     const int tyi = (int)(u % ty_n); u /= ty_n;
@@ -1058,17 +1076,43 @@ __global__ void __launch_bounds__(256) class_colsum_inactive_kernel(int r, int c
           float4 &d = z == 0 ? s0 : (z == r - 1 ? s2 : s1);
           d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
         }
-        float *a0 = acc + (size_t)((cx * 3 + cy) * 3 + 0) * cp + c4 * 4;
-        float *a1 = a0 + cp, *a2 = a0 + 2 * cp;
-        atomicAdd(a0 + 0, s0.x); atomicAdd(a0 + 1, s0.y); atomicAdd(a0 + 2, s0.z); atomicAdd(a0 + 3, s0.w);
-        atomicAdd(a1 + 0, s1.x); atomicAdd(a1 + 1, s1.y); atomicAdd(a1 + 2, s1.z); atomicAdd(a1 + 3, s1.w);
-        atomicAdd(a2 + 0, s2.x); atomicAdd(a2 + 1, s2.y); atomicAdd(a2 + 2, s2.z); atomicAdd(a2 + 3, s2.w);
+        for (int set = inactive ? 0 : 1; set < 2; ++set) {
+          float *a0 = acc + ((size_t)set * 27 + (cx * 3 + cy) * 3) * cp + c4 * 4;
+          float *a1 = a0 + cp, *a2 = a0 + 2 * cp;
+          atomicAdd(a0 + 0, s0.x); atomicAdd(a0 + 1, s0.y); atomicAdd(a0 + 2, s0.z); atomicAdd(a0 + 3, s0.w);
+          atomicAdd(a1 + 0, s1.x); atomicAdd(a1 + 1, s1.y); atomicAdd(a1 + 2, s1.z); atomicAdd(a1 + 3, s1.w);
+          atomicAdd(a2 + 0, s2.x); atomicAdd(a2 + 1, s2.y); atomicAdd(a2 + 2, s2.z); atomicAdd(a2 + 3, s2.w);
+        }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 27 * cp; i += blockDim.x)
+  for (int i = threadIdx.x; i < 2 * 27 * cp; i += blockDim.x)
     if (acc[i] != 0.f) atomicAdd(classsum + i, acc[i]);
+}
+
+// total[ci] = sum over ALL voxels of the data gradient conv^T(g) = sum_tap sum_co w[co][ci][tap] * S_tap[co],
+// S_tap[co] = sum_{classes where the tap stays in the grid} classsum_all[cls][co]
+__global__ void __launch_bounds__(256) conv_grad_total_kernel(int cin, int cout, int cp,
+                                                              const float *__restrict__ w /*[co][ci][27]*/,
+                                                              const float *__restrict__ classsum_all,
+                                                              float *__restrict__ total /*[cp]*/) {
+  extern __shared__ float stap[];  // [27][cout]
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    const int tap = i / cout, co = i - tap * cout;
+    float r = 0.f;
+    for (int cls = 0; cls < 27; ++cls)
+      if (tap_valid_in_class(tap, cls)) r += classsum_all[(size_t)cls * cp + co];
+    stap[i] = r;
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < cp; ci += blockDim.x) {
+    float t = 0.f;
+    if (ci < cin)
+      for (int tap = 0; tap < 27; ++tap)
+        for (int co = 0; co < cout; ++co) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], stap[tap * cout + co], t);
+    total[ci] = t;
+  }
 }
 
 __global__ void __launch_bounds__(256) wgrad_const_update_kernel(int cin, int cout, int cp, float slope,
@@ -1086,16 +1130,175 @@ __global__ void __launch_bounds__(256) wgrad_const_update_kernel(int cin, int co
   }
 }
 
-int launch_wgrad_const_region(int nb, int r, int cin, int cout, int cp, int by, int bz, float slope,
-                              const unsigned char *kt_active, const float *g, const float *bias1, BnCoef bn1,
-                              float *classsum_g, float *dw, cudaStream_t s) {
-  PVB_CUDA(cudaMemsetAsync(classsum_g, 0, sizeof(float) * 27 * (size_t)cp, s));
+int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char *kt_active, const float *g,
+                      float *classsum2 /*[2][27][cp]: inactive k-tiles, all*/, cudaStream_t s) {
+  PVB_CUDA(cudaMemsetAsync(classsum2, 0, sizeof(float) * 2 * 27 * (size_t)cp, s));
   const long long n_kt = (long long)nb * r * ((r + by - 1) / by) * ((r + bz - 1) / bz);
-  const size_t smem = sizeof(float) * 27 * (size_t)cp;
+  const size_t smem = sizeof(float) * 2 * 27 * (size_t)cp;
   if (smem > 48 * 1024)
-    PVB_CUDA(cudaFuncSetAttribute(class_colsum_inactive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PVB_LAUNCH(class_colsum_inactive_kernel, kNumSMs * 2, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum_g);
-  PVB_LAUNCH(wgrad_const_update_kernel, 27, 256, 0, s, cin, cout, cp, slope, classsum_g, bias1, bn1, dw);
+    PVB_CUDA(cudaFuncSetAttribute(class_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(class_colsum_kernel, kNumSMs * 2, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum2);
+  return 0;
+}
+
+int launch_wgrad_const_update(int cin, int cout, int cp, float slope, const float *classsum_inactive,
+                              const float *bias1, BnCoef bn1, float *dw, cudaStream_t s) {
+  PVB_LAUNCH(wgrad_const_update_kernel, 27, 256, 0, s, cin, cout, cp, slope, classsum_inactive, bias1, bn1, dw);
+  return 0;
+}
+
+int launch_conv_grad_total(int cin, int cout, int cp, const float *w, const float *classsum_all, float *total,
+                           cudaStream_t s) {
+  PVB_LAUNCH(conv_grad_total_kernel, 1, 256, 27 * cout * sizeof(float), s, cin, cout, cp, w, classsum_all, total);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// BatchNorm1 backward restricted to a list of units (region G); the rest of the grid is the constant region
+// (Y1 == b1), whose contribution is closed-form:   sum_C g = total - sum_G g,  leaky' = d_c,  xhat = xh_c.
+// A unit = HC_TX(2) x-planes x ty y-rows x r z-rows (the halo conv kernel's output unit).
+// --------------------------------------------------------------------------------------------
+template <int NSETS, typename F>
+__device__ __forceinline__ void unit_column_reduce(int r, int ty, int cp, const int4 *units, const int *count,
+                                                   float *partials, F &&body) {
+  __shared__ float4 red[NSETS][RED_THREADS];
+  const int cp4 = cp >> 2, rl = RED_THREADS / cp4;
+  const int c4 = threadIdx.x % cp4, lane_r = threadIdx.x / cp4;
+  float4 acc[NSETS];
+#pragma unroll
+  for (int k = 0; k < NSETS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((int)blockIdx.x < __ldg(count) && lane_r < rl) {
+    const int4 uc = __ldg(units + blockIdx.x);
+    for (int xx = 0; xx < 2; ++xx) {
+      const int x = uc.x + xx;
+      if (x >= r) break;
+      const int ny = min(ty, r - uc.y);
+      const long long row0 = (((long long)uc.z * r + x) * r + uc.y) * r;
+      for (int i = lane_r; i < ny * r; i += rl) body(row0 + i, c4, acc);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NSETS; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < cp4) {
+#pragma unroll
+    for (int k = 0; k < NSETS; ++k) {
+      float4 sum = red[k][threadIdx.x];
+      for (int j = 1; j < rl; ++j) {
+        const float4 v = red[k][threadIdx.x + j * cp4];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      }
+      st4(partials + ((size_t)blockIdx.x * NSETS + k) * cp + threadIdx.x * 4, sum);
+    }
+  }
+}
+
+// sets: 0 sum leaky'*g, 1 sum leaky'*g*xhat, 2 sum g, 3 number of rows
+__global__ void __launch_bounds__(RED_THREADS) bn_bwd_reduce_units_kernel(int r, int ty, int cp, float slope,
+                                                                          const int4 *__restrict__ units,
+                                                                          const int *__restrict__ count,
+                                                                          const float *__restrict__ g,
+                                                                          const float *__restrict__ y, BnCoef coef,
+                                                                          float *__restrict__ partials) {
+  unit_column_reduce<4>(r, ty, cp, units, count, partials, [&](long long row, int c4, float4 *acc) {
+    const size_t o = (size_t)row * cp + c4 * 4;
+    const float4 gv = ld4(g + o), yv = ld4(y + o);
+    const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
+    const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
+#define PVB_RU1(f)                                                             \
+  {                                                                            \
+    const float gg = gv.f * (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope);     \
+    acc[0].f += gg;                                                            \
+    acc[1].f = fmaf(gg, (yv.f - mu.f) * is.f, acc[1].f);                       \
+    acc[2].f += gv.f;                                                          \
+    acc[3].f += 1.0f;                                                          \
+  }
+    PVB_RU1(x) PVB_RU1(y) PVB_RU1(z) PVB_RU1(w)
+#undef PVB_RU1
+  });
+}
+
+// U1 = sum_G m g + d_c (total - sum_G g),  U2 = sum_G m g xhat + d_c xh_c (total - sum_G g)
+__global__ void __launch_bounds__(256) bn_bwd_combine_kernel(int c, int cp, float slope, const float *__restrict__ sums_g
+                                                             /*[4][cp]*/, const float *__restrict__ total,
+                                                             const float *__restrict__ bias_prev, BnCoef coef,
+                                                             float *__restrict__ u1, float *__restrict__ u2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cp) return;
+  if (i >= c) { u1[i] = 0.f; u2[i] = 0.f; return; }
+  const float zc = fmaf(bias_prev[i], coef.scale[i], coef.shift[i]);
+  const float dc = zc > 0.f ? 1.0f : slope;
+  const float xhc = (bias_prev[i] - coef.mean[i]) * coef.invstd[i];
+  const float rest = total[i] - sums_g[2 * cp + i];
+  u1[i] = sums_g[0 * cp + i] + dc * rest;
+  u2[i] = sums_g[1 * cp + i] + dc * xhc * rest;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) bn_bwd_apply_units_kernel(int r, int ty, int cp, float slope,
+                                                                         float inv_count,
+                                                                         const int4 *__restrict__ units,
+                                                                         const int *__restrict__ count,
+                                                                         const float *__restrict__ g,
+                                                                         const float *__restrict__ y, BnCoef coef,
+                                                                         const float *__restrict__ s1,
+                                                                         const float *__restrict__ s2,
+                                                                         float *__restrict__ out,
+                                                                         float *__restrict__ out_lo,
+                                                                         float *__restrict__ partials) {
+  unit_column_reduce<1>(r, ty, cp, units, count, partials, [&](long long row, int c4, float4 *acc) {
+    const size_t o = (size_t)row * cp + c4 * 4;
+    const float4 gv = ld4(g + o), yv = ld4(y + o);
+    const float4 sc = ld4(coef.scale + c4 * 4), sh = ld4(coef.shift + c4 * 4);
+    const float4 mu = ld4(coef.mean + c4 * 4), is = ld4(coef.invstd + c4 * 4);
+    const float4 a1 = ld4(s1 + c4 * 4), a2 = ld4(s2 + c4 * 4);
+    float4 d;
+#define PVB_AU1(f)                                                             \
+  {                                                                            \
+    const float gg = gv.f * (fmaf(yv.f, sc.f, sh.f) > 0.f ? 1.0f : slope);     \
+    const float xh = (yv.f - mu.f) * is.f;                                     \
+    d.f = sc.f * (gg - a1.f * inv_count - xh * (a2.f * inv_count));            \
+    acc[0].f += d.f;                                                           \
+  }
+    PVB_AU1(x) PVB_AU1(y) PVB_AU1(z) PVB_AU1(w)
+#undef PVB_AU1
+    st4(out + o, d);
+    if (out_lo) st4(out_lo + o, tf32_lo4(d));
+  });
+}
+
+// conv-bias gradient over the whole grid: explicit part (region G) + closed form on the constant region
+__global__ void __launch_bounds__(256) bn_bwd_bias_total_kernel(int c, int cp, float slope, float rows_total,
+                                                                const float *__restrict__ colsum_g /*sum_G dx*/,
+                                                                const float *__restrict__ sums_g /*[4][cp]*/,
+                                                                const float *__restrict__ total,
+                                                                const float *__restrict__ bias_prev, BnCoef coef,
+                                                                const float *__restrict__ u1,
+                                                                const float *__restrict__ u2, float *__restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float zc = fmaf(bias_prev[i], coef.scale[i], coef.shift[i]);
+  const float dc = zc > 0.f ? 1.0f : slope;
+  const float xhc = (bias_prev[i] - coef.mean[i]) * coef.invstd[i];
+  const float rest_g = total[i] - sums_g[2 * cp + i];
+  const float rows_c = rows_total - sums_g[3 * cp + i];
+  db[i] = colsum_g[i] + coef.scale[i] * (dc * rest_g - rows_c * (u1[i] / rows_total + xhc * (u2[i] / rows_total)));
+}
+
+int launch_bn_bwd_units(int max_units, int r, int ty, int c, int cp, float slope, long long rows_total,
+                        const int4 *units, const int *count, const float *g, const float *y, BnCoef coef,
+                        const float *total, const float *bias_prev, float *partials, float *sums_g /*[4][cp]*/,
+                        float *u1, float *u2, float *out, float *out_lo, float *colsum_g /*[cp]*/, float *db,
+                        cudaStream_t s) {
+  PVB_CHECK_ARG(cp % 4 == 0 && cp / 4 <= RED_THREADS);
+  PVB_LAUNCH(bn_bwd_reduce_units_kernel, max_units, RED_THREADS, 0, s, r, ty, cp, slope, units, count, g, y, coef,
+             partials);
+  PVB_TRY_LAUNCH(launch_reduce_partials(max_units, 4 * cp, partials, sums_g, s));
+  PVB_LAUNCH(bn_bwd_combine_kernel, ceil_div(cp, 256), 256, 0, s, c, cp, slope, sums_g, total, bias_prev, coef, u1, u2);
+  PVB_LAUNCH(bn_bwd_apply_units_kernel, max_units, RED_THREADS, 0, s, r, ty, cp, slope, (float)(1.0 / (double)rows_total),
+             units, count, g, y, coef, u1, u2, out, out_lo, partials);
+  PVB_TRY_LAUNCH(launch_reduce_partials(max_units, cp, partials, colsum_g, s));
+  PVB_LAUNCH(bn_bwd_bias_total_kernel, ceil_div(c, 256), 256, 0, s, c, cp, slope, (float)rows_total, colsum_g, sums_g,
+             total, bias_prev, coef, u1, u2, db);
   return 0;
 }
 

@@ -80,12 +80,25 @@ int launch_se_backward(int nb, int c, int cp, int hid, long long rows_per_sample
 
 // ---- activity-driven tile skipping (see fused_ops.cu "Activity bookkeeping") ----
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts /*[8]*/,
-                          unsigned char *occ /*[nb*r*r]*/, unsigned char *act1, int4 *fwd1, int4 *dgrad1, int4 *fwd2,
-                          int4 *wg1, int4 *wg2, unsigned char *wg2_flag, cudaStream_t s);
-// dW2 contribution of the k-tiles whose conv2 input is the constant c1 (rank-1, via 27 boundary-class sums of g)
-int launch_wgrad_const_region(int nb, int r, int cin, int cout, int cp, int by, int bz, float slope,
-                              const unsigned char *kt_active, const float *g, const float *bias1, BnCoef bn1,
-                              float *classsum_g /*[27][cp]*/, float *dw, cudaStream_t s);
+                          unsigned char *occ /*[nb*r*r]*/, unsigned char *act1, unsigned char *act_dg, int4 *fwd1,
+                          int4 *dgrad1, int4 *fwd2, int4 *wg1, int4 *wg2, unsigned char *wg2_flag, int4 *dg2,
+                          cudaStream_t s);
+// 27 boundary-class column sums of g: [0] over the k-tiles not in kt_active, [1] over all voxels
+int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char *kt_active, const float *g,
+                      float *classsum2 /*[2][27][cp]*/, cudaStream_t s);
+// dW[co][ci][tap] += c1[ci] * sum_{classes where tap valid} classsum_inactive[cls][co]   (constant-input region)
+int launch_wgrad_const_update(int cin, int cout, int cp, float slope, const float *classsum_inactive,
+                              const float *bias1, BnCoef bn1, float *dw, cudaStream_t s);
+// total[ci] = sum over all voxels of conv^T(g)[.,ci]  (closed form from the all-voxel class sums)
+int launch_conv_grad_total(int cin, int cout, int cp, const float *w, const float *classsum_all, float *total,
+                           cudaStream_t s);
+// BatchNorm backward on a unit list (explicit) + constant region (closed form); emits u1/u2 (raw reductions =
+// dbeta/dgamma), out(+lo) on the listed units and the full conv-bias gradient db
+int launch_bn_bwd_units(int max_units, int r, int ty, int c, int cp, float slope, long long rows_total,
+                        const int4 *units, const int *count, const float *g, const float *y, BnCoef coef,
+                        const float *total, const float *bias_prev, float *partials, float *sums_g /*[4][cp]*/,
+                        float *u1, float *u2, float *out, float *out_lo, float *colsum_g /*[cp]*/, float *db,
+                        cudaStream_t s);
 int launch_fill_bias_rows(long long rows, int c, int cp, const float *bias, float *out, cudaStream_t s);
 int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
                            const float *bias1, BnCoef bn1, float *classsum /*[27][cp_out]*/, float *tapsum /*[27][cout]*/, float *out,

@@ -28,11 +28,13 @@ static bool needs_grid_lo(const pvcnn_pvconv_desc *d) { return d->npass > 1; }
 struct SparseBuf {
   int *counts;               // [8]
   unsigned char *occ, *act1;
-  int4 *fwd1, *dgrad1, *fwd2, *wg1, *wg2;
+  int4 *fwd1, *dgrad1, *fwd2, *wg1, *wg2, *dg2;
+  unsigned char *act_dg;     // per unit: contains an occupied column
+  int max_units;
   unsigned char *wg2_flag;   // per k-tile: conv2-wgrad tile is computed on the tensor cores (else closed form)
   float *classsum;           // [27][co]  conv2 forward constants
   float *tapsum;             // [27][co]
-  float *classsum_g;         // [27][co]  class sums of gY2 over the constant region
+  float *classsum_g;         // [2][27][co]  class sums of gY2: constant-region k-tiles, all voxels
   int ty, wg_bz, wg_by;
   long long total_ints;
 };
@@ -49,17 +51,20 @@ static SparseBuf sparse_at(int *base, int b, int r, int co) {
   v.counts = base + o; o += 8;
   v.occ = reinterpret_cast<unsigned char *>(base + o); o += up4((long long)b * r * r) / 4 + 4;
   v.act1 = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  v.act_dg = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  v.max_units = (int)units;
   o = up4(o);
   v.fwd1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
   v.dgrad1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
   v.fwd2 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
+  v.dg2 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
   v.wg1 = reinterpret_cast<int4 *>(base + o); o += 4 * kt;
   v.wg2 = reinterpret_cast<int4 *>(base + o); o += 4 * kt;
   v.wg2_flag = reinterpret_cast<unsigned char *>(base + o); o += up4(kt) / 4 + 4;
   o = up4(o);
   v.classsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
   v.tapsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
-  v.classsum_g = reinterpret_cast<float *>(base + o); o += 27LL * co;
+  v.classsum_g = reinterpret_cast<float *>(base + o); o += 2 * 27LL * co;
   v.total_ints = o;
   return v;
 }
@@ -144,7 +149,9 @@ long long pvcnn_pvconv_sparse_ints(const pvcnn_pvconv_desc *d) {
 long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d) {
   const long long co = pad4(d->cout > d->cin ? d->cout : d->cin);
   const long long blocks_pts = (long long)d->b * ((d->n + 31) / 32);
-  const long long blocks = blocks_pts > kNumSMs * 4 ? blocks_pts : kNumSMs * 4;
+  long long blocks = blocks_pts > kNumSMs * 4 ? blocks_pts : kNumSMs * 4;
+  const long long units = sparse_at(nullptr, d->b, d->r, (int)co).max_units;  // unit-list reductions use one block per unit
+  if (units > blocks) blocks = units;
   return blocks * 5 * co;  // 4 reduction sets + the per-sample SE gate partials
 }
 
@@ -171,8 +178,8 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   SparseBuf sp{};
   if (sparse) {  // which tiles can differ from the closed form (zero / constant input)?
     sp = sparse_at(ws->sparse, b, r, co);
-    PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.fwd1, sp.dgrad1,
-                                  sp.fwd2, sp.wg1, sp.wg2, sp.wg2_flag, s));
+    PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.act_dg, sp.fwd1,
+                                  sp.dgrad1, sp.fwd2, sp.wg1, sp.wg2, sp.wg2_flag, sp.dg2, s));
   }
   // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
@@ -310,23 +317,37 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   // 5. conv2: wgrad (needs z1, gy2) then dgrad into the d2 buffer (d2 was consumed in step 2)
   // conv2 weight gradient: tensor cores only on the k-tiles that can see a non-constant input voxel; the rest of
   // the grid (input == c1) contributes a rank-1 term computed from 27 boundary-class sums of gY2
+  if (sparse) PVB_TRY(launch_class_sums(b, r, co, sp.wg_by, sp.wg_bz, sp.wg2_flag, ws->gy2, sp.classsum_g, s));
   PVB_TRY(wgrad_launch(b, r, r, r, d->cout, d->cout, 27, ws->z1, ws->z1_lo, co, ws->gy2, ws->gy2_lo, co, gr->w2,
                        d->npass, s, sparse ? sp.wg2 : nullptr, sparse ? sp.counts + 4 : nullptr, nullptr, nullptr));
   if (sparse)
-    PVB_TRY(launch_wgrad_const_region(b, r, d->cout, d->cout, co, sp.wg_by, sp.wg_bz, d->slope, sp.wg2_flag, ws->gy2,
-                                      prm->b1, bn1, sp.classsum_g, gr->w2, s));
+    PVB_TRY(launch_wgrad_const_update(d->cout, d->cout, co, d->slope, sp.classsum_g, prm->b1, bn1, gr->w2, s));
+  // conv2 data gradient: only on region G (units whose gY1 is consumed); BN1-backward treats the rest in closed form
   float *gz1 = ws->d2;
-  PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->gy2, ws->gy2_lo, co, wp + W.w2d, wp + W.w2d + W.n2d,
-                       ld32(d->cout), nullptr, gz1, co, d->npass, s));
-  // 6. LeakyReLU' + BN1 backward
-  PVB_TRY(launch_bn_bwd_reduce(Mv, co, d->slope, gz1, ws->y1, bn1, ws->partials, &nblk, s));
-  PVB_TRY(launch_reduce_partials(nblk, 2 * co, ws->partials, S + 4 * co, s));
-  PVB_CUDA(cudaMemcpyAsync(gr->be1, S + 4 * co, cb, cudaMemcpyDeviceToDevice, s));
-  PVB_CUDA(cudaMemcpyAsync(gr->g1, S + 5 * co, cb, cudaMemcpyDeviceToDevice, s));
-  PVB_TRY(launch_bn_bwd_apply(Mv, co, 1, d->slope, gz1, ws->y1, bn1, S + 4 * co, S + 5 * co, ws->gy1,
-                              glo ? ws->gy1_lo : nullptr, ws->partials, &nblk, s));
-  PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 8 * co, s));
-  PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
+  if (sparse) {
+    PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cout, ws->gy2, co, wp + W.w2d, wp + W.w2d + W.n2d, ld32(d->cout),
+                             nullptr, gz1, co, d->npass, s, sp.dg2, sp.counts + 5));
+    PVB_TRY(launch_conv_grad_total(d->cout, d->cout, co, prm->w2, sp.classsum_g + 27 * (size_t)co, S + 13 * co, s));
+    // 6. LeakyReLU' + BN1 backward on G (explicit) + constant region (closed form)
+    PVB_TRY(launch_bn_bwd_units(sp.max_units, r, sp.ty, d->cout, co, d->slope, Mv, sp.dg2, sp.counts + 5, gz1, ws->y1, bn1,
+                                S + 13 * co, prm->b1, ws->partials, S + 9 * co, S + 4 * co, S + 5 * co, ws->gy1,
+                                glo ? ws->gy1_lo : nullptr, S + 14 * co, S + 8 * co, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->be1, S + 4 * co, cb, cudaMemcpyDeviceToDevice, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->g1, S + 5 * co, cb, cudaMemcpyDeviceToDevice, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
+  } else {
+    PVB_TRY(igemm_launch(b, r, r, r, d->cout, d->cout, 27, ws->gy2, ws->gy2_lo, co, wp + W.w2d, wp + W.w2d + W.n2d,
+                         ld32(d->cout), nullptr, gz1, co, d->npass, s));
+    // 6. LeakyReLU' + BN1 backward
+    PVB_TRY(launch_bn_bwd_reduce(Mv, co, d->slope, gz1, ws->y1, bn1, ws->partials, &nblk, s));
+    PVB_TRY(launch_reduce_partials(nblk, 2 * co, ws->partials, S + 4 * co, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->be1, S + 4 * co, cb, cudaMemcpyDeviceToDevice, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->g1, S + 5 * co, cb, cudaMemcpyDeviceToDevice, s));
+    PVB_TRY(launch_bn_bwd_apply(Mv, co, 1, d->slope, gz1, ws->y1, bn1, S + 4 * co, S + 5 * co, ws->gy1,
+                                glo ? ws->gy1_lo : nullptr, ws->partials, &nblk, s));
+    PVB_TRY(launch_reduce_partials(nblk, co, ws->partials, S + 8 * co, s));
+    PVB_CUDA(cudaMemcpyAsync(gr->b1, S + 8 * co, cb, cudaMemcpyDeviceToDevice, s));
+  }
   // 7. conv1: wgrad, dgrad (into the d2 buffer again: gz1 is dead)
   // conv1: its input G0 is zero outside the occupied columns -> only the listed k-tiles contribute to dW1, and the
   // data gradient is only consumed at occupied voxels -> only the listed units are produced (the rest of gg0 is never read)
