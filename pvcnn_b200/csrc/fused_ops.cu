@@ -864,12 +864,16 @@ __device__ __forceinline__ bool occ_any(const unsigned char *occ, int b, int r, 
   return false;
 }
 
-// counts: [0] conv1-forward units, [1] conv1-dgrad units, [2] conv2-forward units, [3] conv1-wgrad k-tiles
-__global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
-                                                          const unsigned char *__restrict__ occ, int *counts,
+// Flag kernels mark, per halo-conv unit and per wgrad k-tile, whether it has to be computed; compact_lists_kernel then
+// turns each flag array into an index-ordered coordinate list (ordered = neighbouring tiles run concurrently and share
+// their halos in L2; also makes the traversal deterministic).
+//   lists / counts: [0] conv1-forward units, [1] conv1-dgrad units, [2] conv2-forward units, [3] conv1-wgrad k-tiles,
+//                   [4] conv2-wgrad k-tiles, [5] region-G units (conv2 dgrad + BN1 backward)
+__global__ void __launch_bounds__(256) flag_stage1_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
+                                                          const unsigned char *__restrict__ occ,
                                                           unsigned char *__restrict__ act1,
-                                                          unsigned char *__restrict__ act_dg, int4 *fwd1, int4 *dgrad1,
-                                                          int4 *wg1) {
+                                                          unsigned char *__restrict__ act_dg,
+                                                          unsigned char *__restrict__ wg1_flag) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int n_units = nb * pairs_x * tiles_y;
   const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
@@ -880,38 +884,33 @@ __global__ void __launch_bounds__(256) build_lists_kernel(int nb, int r, int ty,
     const int yt = u % tiles_y; u /= tiles_y;
     const int xp = u % pairs_x; u /= pairs_x;
     const int b = u, x0 = xp * 2, y0 = yt * ty;
-    const bool a_fwd = occ_any(occ, b, r, x0 - 1, x0 + 2, y0 - 1, y0 + ty);   // halo of the two tiles
-    const bool a_dg = occ_any(occ, b, r, x0, x0 + 1, y0, y0 + ty - 1);        // the tiles themselves
-    act1[t] = a_fwd;
-    act_dg[t] = a_dg;
-    if (a_fwd) fwd1[atomicAdd(counts + 0, 1)] = make_int4(x0, y0, b, 0);
-    if (a_dg) dgrad1[atomicAdd(counts + 1, 1)] = make_int4(x0, y0, b, 0);
+    act1[t] = occ_any(occ, b, r, x0 - 1, x0 + 2, y0 - 1, y0 + ty);     // halo of the two tiles sees a point
+    act_dg[t] = occ_any(occ, b, r, x0, x0 + 1, y0, y0 + ty - 1);       // the tiles themselves contain a point
   }
   if (t < n_kt) {
     int u = t;
-    const int tz = u % wg_tz; u /= wg_tz;
+    u /= wg_tz;
     const int tyi = u % wg_ty; u /= wg_ty;
     const int x = u % r; u /= r;
     const int b = u, y0 = tyi * wg_by;
     // X shifted by (dx,dy) in [-1,1] must be non-zero somewhere in the tile's rows (occupancy is per (x,y) column)
-    if (occ_any(occ, b, r, x - 1, x + 1, y0 - 1, y0 + wg_by)) wg1[atomicAdd(counts + 3, 1)] = make_int4(tz * wg_bz, y0, x, b);
+    wg1_flag[t] = occ_any(occ, b, r, x - 1, x + 1, y0 - 1, y0 + wg_by);
   }
 }
 
-// conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
-// voxel of a conv1-active unit
-__global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
+__global__ void __launch_bounds__(256) flag_stage2_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
                                                           const unsigned char *__restrict__ act1,
-                                                          const unsigned char *__restrict__ act_dg, int *counts,
-                                                          int4 *fwd2, int4 *wg2, unsigned char *__restrict__ wg2_flag,
-                                                          int4 *dg2) {
+                                                          const unsigned char *__restrict__ act_dg,
+                                                          unsigned char *__restrict__ fwd2_flag,
+                                                          unsigned char *__restrict__ wg2_flag,
+                                                          unsigned char *__restrict__ dg2_flag) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   {  // conv2 weight gradient: k-tile is "active" iff a tap-shifted row can see a voxel where Z1 is not the constant
     const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
     if (t < nb * r * wg_ty * wg_tz) {
       int u = t;
-      const int tz = u % wg_tz; u /= wg_tz;
+      u /= wg_tz;
       const int tyi = u % wg_ty; u /= wg_ty;
       const int x = u % r; u /= r;
       const int b = u, y0 = tyi * wg_by;
@@ -920,7 +919,6 @@ __global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty,
         for (int yy = max(0, y0 - 1); yy <= min(r - 1, y0 + wg_by); ++yy)
           a = a || act1[((size_t)b * pairs_x + xx / 2) * tiles_y + yy / ty];
       wg2_flag[t] = a;
-      if (a) wg2[atomicAdd(counts + 4, 1)] = make_int4(tz * wg_bz, y0, x, b);
     }
   }
   if (t >= nb * pairs_x * tiles_y) return;
@@ -928,32 +926,94 @@ __global__ void __launch_bounds__(256) build_list2_kernel(int nb, int r, int ty,
   const int yt = u % tiles_y; u /= tiles_y;
   const int xp = u % pairs_x; u /= pairs_x;
   const int b = u, x0 = xp * 2, y0 = yt * ty;
+  // conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
+  // voxel of a conv1-active unit
   const int xpa = max(0, (x0 - 1) / 2), xpb = min(pairs_x - 1, (x0 + 2) / 2);
   const int yta = max(0, (y0 - 1) / ty), ytb = min(tiles_y - 1, (y0 + ty) / ty);
   bool a = false;
   for (int i = xpa; i <= xpb; ++i)
     for (int j = yta; j <= ytb; ++j) a = a || act1[((size_t)b * pairs_x + i) * tiles_y + j];
-  if (a) fwd2[atomicAdd(counts + 2, 1)] = make_int4(x0, y0, b, 0);
+  fwd2_flag[t] = a;
   // region G: units whose gY1 is consumed (halo of a conv1-dgrad unit, rows of conv1-wgrad k-tiles) = 3x3 unit
   // dilation of the units that contain occupied columns; conv2's data gradient and BN1-backward run on G only
   bool gq = false;
   for (int i = max(0, xp - 1); i <= min(pairs_x - 1, xp + 1); ++i)
     for (int j = max(0, yt - 1); j <= min(tiles_y - 1, yt + 1); ++j) gq = gq || act_dg[((size_t)b * pairs_x + i) * tiles_y + j];
-  if (gq) dg2[atomicAdd(counts + 5, 1)] = make_int4(x0, y0, b, 0);
+  dg2_flag[t] = gq;
+}
+
+struct CompactJob {
+  const unsigned char *flags;
+  int4 *list;
+  int n;
+  int is_ktile;
+};
+struct CompactJobs { CompactJob j[6]; };
+
+// one CTA per list: ordered stream compaction (ballot scan) of flags -> coordinates
+__global__ void __launch_bounds__(1024) compact_lists_kernel(CompactJobs jobs, int r, int ty, int wg_bz, int wg_by,
+                                                             int *__restrict__ counts) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const CompactJob jb = jobs.j[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
+  const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < jb.n; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool f = i < jb.n && jb.flags[i];
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int v = warp_tot[w];
+      if (w < warp) woff += v;
+      tot += v;
+    }
+    if (f) {
+      const int pos = base + woff + __popc(bal & ((1u << lane) - 1));
+      int u = i;
+      if (jb.is_ktile) {
+        const int tz = u % wg_tz; u /= wg_tz;
+        const int tyi = u % wg_ty; u /= wg_ty;
+        const int x = u % r; u /= r;
+        jb.list[pos] = make_int4(tz * wg_bz, tyi * wg_by, x, u);
+      } else {
+        const int yt = u % tiles_y; u /= tiles_y;
+        const int xp = u % pairs_x; u /= pairs_x;
+        jb.list[pos] = make_int4(xp * 2, yt * ty, u, 0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[blockIdx.x] = base;
 }
 
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts, unsigned char *occ,
-                          unsigned char *act1, unsigned char *act_dg, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1,
-                          int4 *wg2, unsigned char *wg2_flag, int4 *dg2, cudaStream_t s) {
-  PVB_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), s));
+                          unsigned char *act1, unsigned char *act_dg, unsigned char *fwd2_flag, unsigned char *wg1_flag,
+                          unsigned char *wg2_flag, unsigned char *dg2_flag, int4 *fwd1, int4 *dgrad1, int4 *fwd2,
+                          int4 *wg1, int4 *wg2, int4 *dg2, cudaStream_t s) {
   const long long ncols = (long long)nb * r * r;
   PVB_LAUNCH(colocc_kernel, ceil_div(ncols, 256), 256, 0, s, r, ncols, cnt, occ);
   const int n_units = nb * ((r + 1) / 2) * ((r + ty - 1) / ty);
   const int n_kt = nb * r * ((r + wg_by - 1) / wg_by) * ((r + wg_bz - 1) / wg_bz);
-  PVB_LAUNCH(build_lists_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, counts, act1,
-             act_dg, fwd1, dgrad1, wg1);
-  PVB_LAUNCH(build_list2_kernel, ceil_div(max(n_units, n_kt), 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, act_dg, counts, fwd2,
-             wg2, wg2_flag, dg2);
+  const int nmax = max(n_units, n_kt);
+  PVB_LAUNCH(flag_stage1_kernel, ceil_div(nmax, 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, act1, act_dg, wg1_flag);
+  PVB_LAUNCH(flag_stage2_kernel, ceil_div(nmax, 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, act_dg, fwd2_flag, wg2_flag,
+             dg2_flag);
+  CompactJobs jobs;
+  jobs.j[0] = CompactJob{act1, fwd1, n_units, 0};
+  jobs.j[1] = CompactJob{act_dg, dgrad1, n_units, 0};
+  jobs.j[2] = CompactJob{fwd2_flag, fwd2, n_units, 0};
+  jobs.j[3] = CompactJob{wg1_flag, wg1, n_kt, 1};
+  jobs.j[4] = CompactJob{wg2_flag, wg2, n_kt, 1};
+  jobs.j[5] = CompactJob{dg2_flag, dg2, n_units, 0};
+  PVB_LAUNCH(compact_lists_kernel, 6, 1024, 0, s, jobs, r, ty, wg_bz, wg_by, counts);
   return 0;
 }
 
@@ -1067,14 +1127,19 @@ __global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by
       const int y = tyi * by + yy;
       if (y >= r) break;
       const int cy = y == 0 ? 0 : (y == r - 1 ? 2 : 1);
-      for (int c4 = lane; c4 < cp4; c4 += 32) {
+      // lanes: (z parity, channel quad) -- 32 lanes cover two z rows of 16 quads; loads unrolled for memory-level parallelism
+      const int zpar = cp4 <= 16 ? (lane >> 4) : 0, zstep = cp4 <= 16 ? 2 : 1;
+      for (int c4 = cp4 <= 16 ? (lane & 15) : lane; c4 < cp4; c4 += (cp4 <= 16 ? 16 : 32)) {
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
-        for (int zz = 0; zz < bz; ++zz) {
+        const float *row = g + ((((size_t)b * r + x) * r + y) * r + (size_t)tz * bz) * cp + c4 * 4;
+#pragma unroll 8
+        for (int zz = zpar; zz < bz; zz += zstep) {
           const int z = tz * bz + zz;
-          if (z >= r) break;
-          const float4 v = ld4(g + ((((size_t)b * r + x) * r + y) * r + z) * cp + c4 * 4);
-          float4 &d = z == 0 ? s0 : (z == r - 1 ? s2 : s1);
-          d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+          if (z < r) {
+            const float4 v = ld4(row + (size_t)zz * cp);
+            float4 &d = z == 0 ? s0 : (z == r - 1 ? s2 : s1);
+            d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+          }
         }
         for (int set = inactive ? 0 : 1; set < 2; ++set) {
           float *a0 = acc + ((size_t)set * 27 + (cx * 3 + cy) * 3) * cp + c4 * 4;
@@ -1093,25 +1158,23 @@ __global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by
 
 // total[ci] = sum over ALL voxels of the data gradient conv^T(g) = sum_tap sum_co w[co][ci][tap] * S_tap[co],
 // S_tap[co] = sum_{classes where the tap stays in the grid} classsum_all[cls][co]
-__global__ void __launch_bounds__(256) conv_grad_total_kernel(int cin, int cout, int cp,
+__global__ void __launch_bounds__(128) conv_grad_total_kernel(int cin, int cout, int cp,
                                                               const float *__restrict__ w /*[co][ci][27]*/,
                                                               const float *__restrict__ classsum_all,
-                                                              float *__restrict__ total /*[cp]*/) {
-  extern __shared__ float stap[];  // [27][cout]
-  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
-    const int tap = i / cout, co = i - tap * cout;
+                                                              float *__restrict__ total /*[cp], zeroed*/) {
+  extern __shared__ float stap[];  // [cout]
+  const int tap = blockIdx.x;
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
     float r = 0.f;
     for (int cls = 0; cls < 27; ++cls)
       if (tap_valid_in_class(tap, cls)) r += classsum_all[(size_t)cls * cp + co];
-    stap[i] = r;
+    stap[co] = r;
   }
   __syncthreads();
-  for (int ci = threadIdx.x; ci < cp; ci += blockDim.x) {
+  for (int ci = threadIdx.x; ci < cin; ci += blockDim.x) {
     float t = 0.f;
-    if (ci < cin)
-      for (int tap = 0; tap < 27; ++tap)
-        for (int co = 0; co < cout; ++co) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], stap[tap * cout + co], t);
-    total[ci] = t;
+    for (int co = 0; co < cout; ++co) t = fmaf(w[((size_t)co * cin + ci) * 27 + tap], stap[co], t);
+    atomicAdd(total + ci, t);
   }
 }
 
@@ -1119,14 +1182,19 @@ __global__ void __launch_bounds__(256) wgrad_const_update_kernel(int cin, int co
                                                                  const float *__restrict__ classsum,
                                                                  const float *__restrict__ bias1, BnCoef bn1,
                                                                  float *__restrict__ dw /*[co][ci][27]*/) {
+  extern __shared__ float rsum[];  // [cout]: sum over the classes in which this tap stays inside the grid
   const int tap = blockIdx.x;
-  for (int t = threadIdx.x; t < cout * cin; t += blockDim.x) {
-    const int co = t / cin, ci = t - co * cin;
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
     float r = 0.f;
     for (int cls = 0; cls < 27; ++cls)
       if (tap_valid_in_class(tap, cls)) r += classsum[(size_t)cls * cp + co];
+    rsum[co] = r;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cout * cin; t += blockDim.x) {
+    const int co = t / cin, ci = t - co * cin;
     const float c1 = leaky(fmaf(bias1[ci], bn1.scale[ci], bn1.shift[ci]), slope);
-    dw[((size_t)co * cin + ci) * 27 + tap] += c1 * r;
+    dw[((size_t)co * cin + ci) * 27 + tap] += c1 * rsum[co];
   }
 }
 
@@ -1143,13 +1211,15 @@ int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char
 
 int launch_wgrad_const_update(int cin, int cout, int cp, float slope, const float *classsum_inactive,
                               const float *bias1, BnCoef bn1, float *dw, cudaStream_t s) {
-  PVB_LAUNCH(wgrad_const_update_kernel, 27, 256, 0, s, cin, cout, cp, slope, classsum_inactive, bias1, bn1, dw);
+  PVB_LAUNCH(wgrad_const_update_kernel, 27, 256, cout * sizeof(float), s, cin, cout, cp, slope, classsum_inactive, bias1,
+             bn1, dw);
   return 0;
 }
 
 int launch_conv_grad_total(int cin, int cout, int cp, const float *w, const float *classsum_all, float *total,
                            cudaStream_t s) {
-  PVB_LAUNCH(conv_grad_total_kernel, 1, 256, 27 * cout * sizeof(float), s, cin, cout, cp, w, classsum_all, total);
+  PVB_CUDA(cudaMemsetAsync(total, 0, sizeof(float) * (size_t)cp, s));
+  PVB_LAUNCH(conv_grad_total_kernel, 27, 128, cout * sizeof(float), s, cin, cout, cp, w, classsum_all, total);
   return 0;
 }
 

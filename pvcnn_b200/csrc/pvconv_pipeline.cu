@@ -30,6 +30,7 @@ struct SparseBuf {
   unsigned char *occ, *act1;
   int4 *fwd1, *dgrad1, *fwd2, *wg1, *wg2, *dg2;
   unsigned char *act_dg;     // per unit: contains an occupied column
+  unsigned char *fwd2_flag, *dg2_flag, *wg1_flag;
   int max_units;
   unsigned char *wg2_flag;   // per k-tile: conv2-wgrad tile is computed on the tensor cores (else closed form)
   float *classsum;           // [27][co]  conv2 forward constants
@@ -52,6 +53,9 @@ static SparseBuf sparse_at(int *base, int b, int r, int co) {
   v.occ = reinterpret_cast<unsigned char *>(base + o); o += up4((long long)b * r * r) / 4 + 4;
   v.act1 = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
   v.act_dg = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  v.fwd2_flag = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  v.dg2_flag = reinterpret_cast<unsigned char *>(base + o); o += up4(units) / 4 + 4;
+  v.wg1_flag = reinterpret_cast<unsigned char *>(base + o); o += up4(kt) / 4 + 4;
   v.max_units = (int)units;
   o = up4(o);
   v.fwd1 = reinterpret_cast<int4 *>(base + o); o += 4 * units;
@@ -178,8 +182,8 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   SparseBuf sp{};
   if (sparse) {  // which tiles can differ from the closed form (zero / constant input)?
     sp = sparse_at(ws->sparse, b, r, co);
-    PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.act_dg, sp.fwd1,
-                                  sp.dgrad1, sp.fwd2, sp.wg1, sp.wg2, sp.wg2_flag, sp.dg2, s));
+    PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.act_dg, sp.fwd2_flag,
+                                  sp.wg1_flag, sp.wg2_flag, sp.dg2_flag, sp.fwd1, sp.dgrad1, sp.fwd2, sp.wg1, sp.wg2, sp.dg2, s));
   }
   // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));
