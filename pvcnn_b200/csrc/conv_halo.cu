@@ -25,7 +25,7 @@
 namespace pvb {
 using namespace umma;
 
-constexpr int HC_THREADS = 384;   // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-7 epilogue, w8-11 converters
+constexpr int HC_THREADS = 512;   // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-11 epilogue (one tile per 4 warps), w12-15 converters
 constexpr int HC_KC = 16;         // channels per phase (64-byte rows, SWIZZLE_64B)
 constexpr int HC_TX = 2;          // output x-planes (tiles) per CTA iteration
 constexpr int HC_BSTAGES = 4;     // weight-tile ring
@@ -47,6 +47,7 @@ struct HaloParams {
   int *err;
   const int4 *unit_list;          // optional compact list of (x0, y0, b, -) units to compute; others are skipped
   const int *unit_count;          //   (device count) -- activity-driven tile skipping, see pvconv_pipeline.cu
+  long long *dbg;                 // optional stall counters of CTA 0 (PVCNN_STALL_PROFILE=1)
   int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 4 skip MMA3, 8 no A loads, 16 no B loads, 32 no epilogue stores
 };
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     }
     for (int i = 0; i < HC_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 128);
+    mbar_init(&acc_empty, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -164,11 +165,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
       const uint32_t bn = (uint32_t)p.block_n;
       int abuf = 0, bst = 0, it = 0;
       uint32_t aphase = 0, bphase = 0;
+      long long st_acc = 0, st_a = 0, st_b = 0;
+      const long long t_begin = clock64();
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-        mbar_wait(&acc_empty, (uint32_t)((it & 1) ^ 1), p.err, 23);
+        mbar_wait_t(&acc_empty, (uint32_t)((it & 1) ^ 1), p.err, 23, st_acc);
         tc_fence_after();
         for (int ph = 0; ph < nphases; ++ph) {
-          mbar_wait(&a_ready[abuf], aphase, p.err, 24);
+          mbar_wait_t(&a_ready[abuf], aphase, p.err, 24, st_a);
           tc_fence_after();
           const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)abuf * a_buf_bytes), 0);
           const uint32_t a_lo = a_hi + (p.a_bytes >> 4);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
           bool b_ready = mbar_try_wait(&b_full[bst], bphase);
 #pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {
-            if (!b_ready) mbar_wait(&b_full[bst], bphase, p.err, 25);
+            if (!b_ready) mbar_wait_t(&b_full[bst], bphase, p.err, 25, st_b);
             {
               const int nst = (bst + 1 == HC_BSTAGES) ? 0 : bst + 1;
               const uint32_t nph = (bst + 1 == HC_BSTAGES) ? (bphase ^ 1) : bphase;
@@ -219,10 +222,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         }
         mma_commit(&acc_full);
       }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = it; }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ================================ converters: lo = x - trunc_tf32(x) ================================
-    const int tid = threadIdx.x - 8 * 32;  // 0..127
+    const int tid = threadIdx.x - 12 * 32;  // 0..127
     int abuf = 0;
     uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
@@ -250,10 +254,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int we = warp - 4;
+    const int we = (warp - 4) & 3;   // TMEM lane quarter
+    const int my_t = (warp - 4) >> 2;  // the output tile (x-plane) this warp drains: the two tiles drain in parallel
     const int m = we * 32 + lane;
     const int lz = m % p.sz, ly = m / p.sz;
     int it = 0;
+    long long st_full = 0;
+    const long long t_begin = clock64();
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       int x0, y, b;
       if (p.unit_list) {
@@ -265,10 +272,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
         b = u;
       }
-      mbar_wait(&acc_full, (uint32_t)(it & 1), p.err, 27);
+      mbar_wait_t(&acc_full, (uint32_t)(it & 1), p.err, 27, st_full);
       tc_fence_after();
-#pragma unroll
-      for (int t = 0; t < HC_TX; ++t) {
+      {
+        const int t = my_t;
         const int x = x0 + t;
         const bool valid = x < p.sx && y < p.sy;
         float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + lz) * p.ldo;
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
       tc_fence_before();
       mbar_arrive(&acc_empty);
     }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 4 * 32) { p.dbg[5] = st_full; p.dbg[6] = clock64() - t_begin; }
   }
   tc_fence_before();
   __syncthreads();
@@ -325,6 +333,8 @@ bool conv_halo_supported(int sx, int sy, int sz, int cout) {
   const size_t smem = 2 * a_bytes * 2 + (size_t)HC_BSTAGES * bn * HC_KC * 4 * 2 + 1024;
   return a_bytes % 1024 == 0 && smem <= 227 * 1024 - 512;
 }
+
+long long *stall_profile_buffer();  // conv_igemm.cu
 
 static int *g_halo_err = nullptr;
 
@@ -354,6 +364,7 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
   p.b_bytes = (uint32_t)p.block_n * HC_KC * 4;
   p.bias = bias; p.out = out; p.err = g_halo_err;
   p.unit_list = unit_list; p.unit_count = unit_count;
+  p.dbg = stall_profile_buffer();
   { const char *e = getenv("PVCNN_HALO_EXP"); p.exp = e ? atoi(e) : 0; }
   if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
 

@@ -898,15 +898,18 @@ __global__ void __launch_bounds__(256) flag_stage1_kernel(int nb, int r, int ty,
   }
 }
 
+// Y1 (conv1 output) equals its bias exactly wherever no occupied voxel lies within one voxel, so Z1 = leaky(bn1(Y1)) is
+// the constant c1 outside the occupancy dilated by 1, and conv2 / its weight gradient only need the tiles that can see
+// the occupancy dilated by 2 (column granularity; occupancy is tracked per (x,y) column).
 __global__ void __launch_bounds__(256) flag_stage2_kernel(int nb, int r, int ty, int wg_bz, int wg_by,
-                                                          const unsigned char *__restrict__ act1,
+                                                          const unsigned char *__restrict__ occ,
                                                           const unsigned char *__restrict__ act_dg,
                                                           unsigned char *__restrict__ fwd2_flag,
                                                           unsigned char *__restrict__ wg2_flag,
                                                           unsigned char *__restrict__ dg2_flag) {
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  {  // conv2 weight gradient: k-tile is "active" iff a tap-shifted row can see a voxel where Z1 is not the constant
+  {  // conv2 weight gradient: a tap-shifted row (+-1) can see a non-constant Z1 voxel (occupancy dilated by 1)
     const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
     if (t < nb * r * wg_ty * wg_tz) {
       int u = t;
@@ -914,11 +917,7 @@ __global__ void __launch_bounds__(256) flag_stage2_kernel(int nb, int r, int ty,
       const int tyi = u % wg_ty; u /= wg_ty;
       const int x = u % r; u /= r;
       const int b = u, y0 = tyi * wg_by;
-      bool a = false;
-      for (int xx = max(0, x - 1); xx <= min(r - 1, x + 1); ++xx)
-        for (int yy = max(0, y0 - 1); yy <= min(r - 1, y0 + wg_by); ++yy)
-          a = a || act1[((size_t)b * pairs_x + xx / 2) * tiles_y + yy / ty];
-      wg2_flag[t] = a;
+      wg2_flag[t] = occ_any(occ, b, r, x - 2, x + 2, y0 - 2, y0 + wg_by + 1);
     }
   }
   if (t >= nb * pairs_x * tiles_y) return;
@@ -926,14 +925,8 @@ __global__ void __launch_bounds__(256) flag_stage2_kernel(int nb, int r, int ty,
   const int yt = u % tiles_y; u /= tiles_y;
   const int xp = u % pairs_x; u /= pairs_x;
   const int b = u, x0 = xp * 2, y0 = yt * ty;
-  // conv2 forward: a unit must be computed iff its halo touches a voxel whose Z1 differs from the constant, i.e. a
-  // voxel of a conv1-active unit
-  const int xpa = max(0, (x0 - 1) / 2), xpb = min(pairs_x - 1, (x0 + 2) / 2);
-  const int yta = max(0, (y0 - 1) / ty), ytb = min(tiles_y - 1, (y0 + ty) / ty);
-  bool a = false;
-  for (int i = xpa; i <= xpb; ++i)
-    for (int j = yta; j <= ytb; ++j) a = a || act1[((size_t)b * pairs_x + i) * tiles_y + j];
-  fwd2_flag[t] = a;
+  // conv2 forward: the unit's halo (+-1) touches a non-constant Z1 voxel (occupancy dilated by 1)
+  fwd2_flag[t] = occ_any(occ, b, r, x0 - 2, x0 + 3, y0 - 2, y0 + ty + 1);
   // region G: units whose gY1 is consumed (halo of a conv1-dgrad unit, rows of conv1-wgrad k-tiles) = 3x3 unit
   // dilation of the units that contain occupied columns; conv2's data gradient and BN1-backward run on G only
   bool gq = false;
@@ -1004,7 +997,7 @@ int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int
   const int n_kt = nb * r * ((r + wg_by - 1) / wg_by) * ((r + wg_bz - 1) / wg_bz);
   const int nmax = max(n_units, n_kt);
   PVB_LAUNCH(flag_stage1_kernel, ceil_div(nmax, 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, act1, act_dg, wg1_flag);
-  PVB_LAUNCH(flag_stage2_kernel, ceil_div(nmax, 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, act1, act_dg, fwd2_flag, wg2_flag,
+  PVB_LAUNCH(flag_stage2_kernel, ceil_div(nmax, 256), 256, 0, s, nb, r, ty, wg_bz, wg_by, occ, act_dg, fwd2_flag, wg2_flag,
              dg2_flag);
   CompactJobs jobs;
   jobs.j[0] = CompactJob{act1, fwd1, n_units, 0};
