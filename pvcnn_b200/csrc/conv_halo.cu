@@ -280,29 +280,46 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
         const bool valid = x < p.sx && y < p.sy;
         float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + lz) * p.ldo;
         const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(t * 3 * p.block_n);
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          float v[16], w[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld16(taddr + p.block_n + c0, w);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          // all three partial accumulators of a 32-column slab are requested before a single wait
+          uint32_t ra[32], rb[32], rc[32];
+          float v[32];
+          if (c0 + 32 <= p.block_n) {
+            tmem_ld32_nowait(taddr + c0, ra);
+            tmem_ld32_nowait(taddr + p.block_n + c0, rb);
+            if (three) tmem_ld32_nowait(taddr + 2 * p.block_n + c0, rc);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += w[i];
-          if (three) {
-            tmem_ld16(taddr + 2 * p.block_n + c0, w);
+            for (int i = 0; i < 32; ++i) {
+              v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+              if (three) v[i] += __uint_as_float(rc[i]);
+            }
+          } else {  // block_n == 16 or 48: 16-column tail
+            float w[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld16(taddr + p.block_n + c0, w);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += w[i];
+            if (three) {
+              tmem_ld16(taddr + 2 * p.block_n + c0, w);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += w[i];
+            }
+#pragma unroll
+            for (int i = 16; i < 32; ++i) v[i] = 0.f;
           }
-          if (valid && c0 < p.cout && !(p.exp & 32)) {
+          if (valid && c0 < p.cout) {
             if (p.bias) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
+              for (int i = 0; i < 32; ++i)
                 if (c0 + i < p.cout) v[i] += __ldg(p.bias + c0 + i);
             }
-            if (c0 + 16 <= p.cout) {
+            if (c0 + 32 <= p.cout) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
+              for (int i = 0; i < 32; i += 4)
                 *reinterpret_cast<float4 *>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
-              for (int i = 0; i < 16 && c0 + i < p.cout; ++i) orow[c0 + i] = v[i];
+              for (int i = 0; i < 32 && c0 + i < p.cout; ++i) orow[c0 + i] = v[i];
             }
           }
         }
