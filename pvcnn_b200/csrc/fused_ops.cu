@@ -226,12 +226,26 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(int nblocks, int ncols, const float *__restrict__ partials,
                                                               float *__restrict__ sums) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (c >= ncols) return;
-  double s = 0.0;
-  for (int k = lane; k < nblocks; k += 32) s += (double)partials[(size_t)k * ncols + c];
-  s = warp_sum_d(s);
-  if (lane == 0) sums[c] = (float)s;
+  // one CTA per column: 256 threads stride over the partial rows (4 independent fp64 accumulators for MLP)
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = threadIdx.x;
+  for (; k + 768 < nblocks; k += 1024) {
+    s0 += (double)partials[(size_t)k * ncols + c];
+    s1 += (double)partials[(size_t)(k + 256) * ncols + c];
+    s2 += (double)partials[(size_t)(k + 512) * ncols + c];
+    s3 += (double)partials[(size_t)(k + 768) * ncols + c];
+  }
+  for (; k < nblocks; k += 256) s0 += (double)partials[(size_t)k * ncols + c];
+  double s = warp_sum_d((s0 + s1) + (s2 + s3));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    sums[c] = (float)t;
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, int cp, double rows, float eps,
@@ -239,20 +253,24 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
                                                           const float *__restrict__ gamma,
                                                           const float *__restrict__ beta, float *running_mean,
                                                           float *running_var, BnCoef coef) {
-  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per channel
-  if (ch >= cp) return;
+  __shared__ double red[2][8];
+  const int ch = blockIdx.x;  // one CTA per channel
   if (ch >= c) {
-    if (lane == 0) { coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f; }
+    if (threadIdx.x == 0) { coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f; }
     return;
   }
   double s = 0.0, ss = 0.0;
-  for (int k = lane; k < nblocks; k += 32) {
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) {
     s += (double)partials[((size_t)k * 2 + 0) * cp + ch];
     ss += (double)partials[((size_t)k * 2 + 1) * cp + ch];
   }
   s = warp_sum_d(s);
   ss = warp_sum_d(ss);
-  if (lane != 0) return;
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  s = 0.0; ss = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += red[0][w]; ss += red[1][w]; }
   const double mean = s / rows;
   double var = ss / rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
 int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
                        const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
                        cudaStream_t s) {
-  PVB_LAUNCH(bn_finalize_kernel, ceil_div(cp, 8), 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
+  PVB_LAUNCH(bn_finalize_kernel, cp, 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
              gamma, beta, running_mean, running_var, coef);
   return 0;
 }
@@ -546,7 +564,7 @@ int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const flo
 }
 
 int launch_reduce_partials(int nblocks, int ncols, const float *partials, float *sums, cudaStream_t s) {
-  PVB_LAUNCH(reduce_partials_kernel, ceil_div(ncols, 8), 256, 0, s, nblocks, ncols, partials, sums);
+  PVB_LAUNCH(reduce_partials_kernel, ncols, 256, 0, s, nblocks, ncols, partials, sums);
   return 0;
 }
 
