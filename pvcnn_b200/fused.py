@@ -73,6 +73,16 @@ def _scratch(name, numel, device, dtype=torch.float32):
     return t
 
 
+def _poison(tensors):
+    """PVCNN_B200_POISON=1 (debug): fill every workspace buffer with NaN / INT_MAX before use, so that a kernel
+    reading memory it never wrote shows up as NaN instead of depending on what the allocator handed out."""
+    if os.environ.get("PVCNN_B200_POISON", "0") != "1":
+        return
+    for t in tensors:
+        if t is not None:
+            t.fill_(float("nan") if t.is_floating_point() else 2 ** 31 - 1)
+
+
 class _Plan:
     """Buffers of one forward pass (kept alive for the backward)."""
 
@@ -112,6 +122,8 @@ class _Plan:
         self.t = alloc
         self.desc = desc
         self.device = device
+        self.private = bool(need_backward)
+        _poison(alloc.values())
 
     def add_backward_scratch(self):
         d = self.desc
@@ -125,6 +137,7 @@ class _Plan:
             sizes.update(gy2_lo=mv * co, gy1_lo=mv * co)
         for k, v in sizes.items():
             self.t[k] = _scratch("bwd_" + k, v, self.device)
+        _poison(self.t[k] for k in sizes)
 
     def struct(self):
         ws = Workspace()
@@ -142,7 +155,7 @@ def _module_tensors(m):
 
 class _PVConvFused(Function):
     @staticmethod
-    def forward(ctx, features, coords, module, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1=None,
+    def forward(ctx, features, coords, module, need_bwd, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1=None,
                 se_w2=None):
         dev = features.device
         if dev.type != "cuda":
@@ -159,10 +172,8 @@ class _PVConvFused(Function):
         desc.bn_eps_pt = float(bns[2].eps)
         desc.momentum = float(bns[0].momentum if bns[0].momentum is not None else 0.1)
         desc.slope = float(module.voxel_layers[2].negative_slope)
-        need_bwd = training and torch.is_grad_enabled() and any(
-            t.requires_grad for t in (features, w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1, se_w2)
-            if t is not None)
-        plan = _Plan(desc, dev, need_bwd)
+        # need_bwd is decided by the caller: grad mode is always off inside Function.forward
+        plan = _Plan(desc, dev, bool(need_bwd) and training)
         prm = Params()
         vals = dict(w1=w1, b1=b1, g1=g1, be1=be1, rm1=bns[0].running_mean, rv1=bns[0].running_var,
                     w2=w2, b2=b2, g2=g2, be2=be2, rm2=bns[1].running_mean, rv2=bns[1].running_var,
@@ -177,6 +188,7 @@ class _PVConvFused(Function):
             keep.append(t)
             setattr(prm, k, _ptr(t))
         out = torch.empty((b, module.out_channels, n), dtype=torch.float32, device=dev)
+        _poison([out])
         ws = plan.struct()
         _lib.call("pvcnn_pvconv_forward", ctypes.byref(desc), features, coords, ctypes.byref(prm), ctypes.byref(ws),
                   out, device=dev)
@@ -195,6 +207,8 @@ class _PVConvFused(Function):
         plan, desc = ctx.plan, ctx.desc
         if not desc.training:
             raise RuntimeError("PVConv backward requires training mode (batch statistics)")
+        if not plan.private:
+            raise RuntimeError("PVConv forward ran without saving activations (no_grad / eval); cannot run backward")
         dev = grad_out.device
         grad_out = grad_out.contiguous().float()
         plan.add_backward_scratch()
@@ -203,11 +217,12 @@ class _PVConvFused(Function):
         for k, t in zip(_GRAD_FIELDS, grads):
             setattr(gs, k, _ptr(t))
         gfeat = torch.empty(ctx.in_shape, dtype=torch.float32, device=dev)
+        _poison([gfeat] + grads)
         ws = plan.struct()
         _lib.call("pvcnn_pvconv_backward", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm), ctypes.byref(ws),
                   gfeat, ctypes.byref(gs), device=dev)
         nparam = 14 if ctx.shapes[12] is not None else 12  # SE weights are optional inputs of forward()
-        return (gfeat, None, None, *grads[:nparam])
+        return (gfeat, None, None, None, *grads[:nparam])
 
 
 def pvconv_fused(module, features, coords):
@@ -216,4 +231,7 @@ def pvconv_fused(module, features, coords):
     if module.with_se:
         se = module.voxel_layers[6]
         params = params + [se.fc[0].weight, se.fc[2].weight]
-    return _PVConvFused.apply(features, coords, module, *params)
+    # activations saved for the backward must be private to this call; otherwise they live in shared scratch
+    need_bwd = module.training and torch.is_grad_enabled() and (
+        features.requires_grad or any(p.requires_grad for p in params))
+    return _PVConvFused.apply(features, coords, module, need_bwd, *params)
