@@ -74,6 +74,19 @@ PVCNN_API int pvcnn_trilinear_devoxelize_grad(int b, int c, int n, int r3, const
 PVCNN_API int pvcnn_ball_query(int b, int n, int m, float r2, int u, const float *centers_coords,
                      const float *points_coords, int *neighbors_indices, void *stream);
 
+/* ---- fused BallQuery grouping: replaces the sequence of modules/ball_query.py:16-30
+ *      (grouping(points_coords) - centers_coords, grouping(points_features), torch.cat) built on
+ *      grouping/grouping.cuh:4-7.  out [B,3+C,M,U]: channels 0..2 = neighbour xyz - centre xyz,
+ *      channels 3.. = neighbour features (c may be 0, then features may be NULL).
+ *      _grad: grad_y [B,3+C,M,U] -> grad_features [B,C,N]; grad_points_coords [B,3,N] and
+ *      grad_centers_coords [B,3,M] are optional (NULL = not needed).  Outputs are zeroed here. */
+PVCNN_API int pvcnn_group_concat(int b, int c, int n, int m, int u, const float *points_coords,
+                       const float *centers_coords, const float *features, const int *indices,
+                       float *out, void *stream);
+PVCNN_API int pvcnn_group_concat_grad(int b, int c, int n, int m, int u, const float *grad_y,
+                            const int *indices, float *grad_features, float *grad_points_coords,
+                            float *grad_centers_coords, void *stream);
+
 /* ---- replaces grouping(...) / grouping_grad(...)  grouping/grouping.cuh:4-7 */
 PVCNN_API int pvcnn_grouping(int b, int c, int n, int m, int u, const float *features, const int *indices,
                    float *out, void *stream);

@@ -18,7 +18,7 @@ _SO = os.path.join(_HERE, "_build", "libpvcnn_oracle.so")
 
 __all__ = [
     "build", "num_threads", "voxelize_coords", "avg_voxelize", "avg_voxelize_grad",
-    "trilinear_devoxelize", "trilinear_devoxelize_grad", "ball_query", "grouping", "grouping_grad",
+    "trilinear_devoxelize", "trilinear_devoxelize_grad", "ball_query", "grouping", "grouping_grad", "group_concat", "group_concat_grad",
     "gather", "gather_grad", "furthest_point_sampling", "three_nn", "three_nn_interpolate",
     "three_nn_interpolate_grad", "pvconv_forward_backward",
 ]
@@ -137,6 +137,20 @@ def grouping_grad(grad_y, idx, n):
     gx = np.empty((b, c, n), np.float32)
     lib().oracle_grouping_grad(_ci(b), _ci(c), _ci(n), _ci(m), _ci(u), _p(grad_y), _p(idx), _p(gx))
     return gx
+
+
+def group_concat(points_coords, centers_coords, feat, idx):
+    """modules/ball_query.py:16-30 restated on the oracle's grouping: cat([grouping(coords) - centres, grouping(feat)])."""
+    rel = grouping(points_coords, idx) - _f(centers_coords)[:, :, :, None]
+    return rel if feat is None else np.concatenate([rel, grouping(feat, idx)], axis=1)
+
+
+def group_concat_grad(grad_y, idx, n):
+    """-> (grad_features [B,C,N] | None, grad_points_coords [B,3,N], grad_centers_coords [B,3,M])"""
+    grad_y = _f(grad_y)
+    gxyz = np.ascontiguousarray(grad_y[:, :3])
+    gf = grouping_grad(np.ascontiguousarray(grad_y[:, 3:]), idx, n) if grad_y.shape[1] > 3 else None
+    return gf, grouping_grad(gxyz, idx, n), -gxyz.sum(axis=3, dtype=np.float64).astype(np.float32)
 
 
 def gather(feat, idx):

@@ -60,6 +60,12 @@ def _arg(a):
     return a
 
 
+def _raw_stream(index):
+    import torch
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    return get(index) if get is not None else torch.cuda.current_stream(index).cuda_stream
+
+
 def call(name, *args, device=None):
     """Invoke `name(*args, stream)` on the current CUDA stream of `device`; raise on error."""
     import torch
@@ -71,8 +77,12 @@ def call(name, *args, device=None):
                 break
     if device is None or device.type != "cuda":
         raise PvcnnError("%s: tensors must live on a CUDA device (the hot path has no CPU implementation)" % name)
-    with torch.cuda.device(device):
-        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        rc = fn(*[_arg(a) for a in args], stream)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    cargs = [_arg(a) for a in args]
+    if index == torch.cuda.current_device():   # common case: no device switch, ~10 us less host overhead per call
+        rc = fn(*cargs, ctypes.c_void_p(_raw_stream(index)))
+    else:
+        with torch.cuda.device(index):
+            rc = fn(*cargs, ctypes.c_void_p(_raw_stream(index)))
     if rc != 0:
         raise PvcnnError("%s failed with code %d" % (name, rc))

@@ -563,6 +563,73 @@ static int launch_fps(int b, int n, int m, const float *coords, int *indices, cu
   return 0;
 }
 
+// =====================================================================================
+// BallQuery grouping in one pass  (modules/ball_query.py:16-30: grouping(coords) - centre, grouping(features), cat)
+// out [B, 3+C, M, U]: channels 0..2 = neighbour coordinate - centre coordinate, channels 3.. = neighbour features.
+// The reference materialises [B,3,M,U] twice and [B,C,M,U] once before writing the concatenation.
+// =====================================================================================
+template <int CT>
+__global__ void __launch_bounds__(256) group_concat_kernel(int c, int n, int m, int u, const float *__restrict__ coords,
+                                                           const float *__restrict__ centers,
+                                                           const float *__restrict__ feat, const int *__restrict__ idx,
+                                                           float *__restrict__ out) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, mu = m * u, ct = c + 3;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= mu) return;
+  const int src = idx[(size_t)b * mu + e];
+  const int ctr = e / u;
+  float *o = out + ((size_t)b * ct + c0) * mu + e;
+  const int cmax = min(CT, ct - c0);
+#pragma unroll 4
+  for (int j = 0; j < cmax; ++j) {
+    const int ch = c0 + j;
+    float v;
+    if (ch < 3)
+      v = __fsub_rn(__ldg(coords + ((size_t)b * 3 + ch) * n + src), __ldg(centers + ((size_t)b * 3 + ch) * m + ctr));
+    else
+      v = __ldg(feat + ((size_t)b * c + (ch - 3)) * n + src);
+    o[(size_t)j * mu] = v;
+  }
+}
+
+// grad_y [B,3+C,M,U] -> grad_features [B,C,N] (+)= channels 3.., grad_coords [B,3,N] (+)= channels 0..2 (optional),
+// grad_centers [B,3,M] = - sum_u channels 0..2 (optional; one warp-segment reduction per centre via atomics)
+template <int CT>
+__global__ void __launch_bounds__(256) group_concat_grad_kernel(int c, int n, int m, int u,
+                                                                const float *__restrict__ grad_y,
+                                                                const int *__restrict__ idx,
+                                                                float *__restrict__ grad_feat,
+                                                                float *__restrict__ grad_coords,
+                                                                float *__restrict__ grad_centers) {
+  const int b = blockIdx.z, c0 = blockIdx.y * CT, lane = threadIdx.x & 31, mu = m * u, ct = c + 3;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e < mu;
+  const int dst = valid ? idx[(size_t)b * mu + e] : -1 - lane;
+  const int ctr = valid ? e / u : -1 - lane;
+  const unsigned grp = __match_any_sync(0xffffffffu, dst);
+  const bool leader = (__ffs(grp) - 1) == lane;
+  const bool multi = __any_sync(0xffffffffu, grp != (1u << lane));
+  const unsigned cgrp = __match_any_sync(0xffffffffu, ctr);
+  const bool cleader = (__ffs(cgrp) - 1) == lane;
+  const float *gy = grad_y + ((size_t)b * ct + c0) * mu + e;
+  const int cmax = min(CT, ct - c0);
+  for (int j = 0; j < cmax; ++j) {
+    const int ch = c0 + j;
+    const float g = valid ? gy[(size_t)j * mu] : 0.0f;
+    float *base = ch < 3 ? grad_coords : grad_feat;   // warp-uniform
+    if (base) {
+      float v = g;
+      if (multi) v = group_sum_ordered(grp, v);
+      const size_t off = ch < 3 ? ((size_t)b * 3 + ch) * n : ((size_t)b * c + (ch - 3)) * n;
+      if (valid && leader) atomicAdd(base + off + dst, v);
+    }
+    if (ch < 3 && grad_centers) {
+      const float v = group_sum_ordered(cgrp, g);
+      if (valid && cleader) atomicAdd(grad_centers + ((size_t)b * 3 + ch) * m + ctr, -v);
+    }
+  }
+}
+
 extern "C" {
 
 int pvcnn_abi_version(void) { return PVCNN_B200_ABI_VERSION; }
@@ -649,6 +716,32 @@ int pvcnn_grouping_grad(int b, int c, int n, int m, int u, const float *grad_y, 
   constexpr int CT = 8;
   PVB_LAUNCH(grouping_grad_kernel<CT>, dim3(ceil_div((long long)m * u, 256), ceil_div(c, CT), b), 256, 0, s, c, n,
              m * u, grad_y, indices, grad_x);
+  return 0;
+}
+
+int pvcnn_group_concat(int b, int c, int n, int m, int u, const float *points_coords, const float *centers_coords,
+                       const float *features, const int *indices, float *out, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c >= 0 && n > 0 && m > 0 && u > 0 && points_coords && centers_coords && indices && out);
+  PVB_CHECK_ARG(c == 0 || features != nullptr);
+  constexpr int CT = 8;
+  PVB_LAUNCH(group_concat_kernel<CT>, dim3(ceil_div((long long)m * u, 256), ceil_div(c + 3, CT), b), 256, 0, stream, c,
+             n, m, u, points_coords, centers_coords, features, indices, out);
+  return 0;
+}
+
+int pvcnn_group_concat_grad(int b, int c, int n, int m, int u, const float *grad_y, const int *indices,
+                            float *grad_features, float *grad_points_coords, float *grad_centers_coords,
+                            void *stream) {
+  PVB_CHECK_ARG(b > 0 && c >= 0 && n > 0 && m > 0 && u > 0 && grad_y && indices);
+  PVB_CHECK_ARG(c == 0 || grad_features != nullptr);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c > 0) PVB_CUDA(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)b * c * n, s));
+  if (grad_points_coords) PVB_CUDA(cudaMemsetAsync(grad_points_coords, 0, sizeof(float) * (size_t)b * 3 * n, s));
+  if (grad_centers_coords) PVB_CUDA(cudaMemsetAsync(grad_centers_coords, 0, sizeof(float) * (size_t)b * 3 * m, s));
+  constexpr int CT = 8;
+  // channel tiles: tile 0 holds the 3 coordinate channels (+ the first 5 feature channels)
+  PVB_LAUNCH(group_concat_grad_kernel<CT>, dim3(ceil_div((long long)m * u, 256), ceil_div(c + 3, CT), b), 256, 0, s, c,
+             n, m, u, grad_y, indices, c > 0 ? grad_features : nullptr, grad_points_coords, grad_centers_coords);
   return 0;
 }
 

@@ -96,6 +96,33 @@ def grouping_backward(grad_y, indices, n):
     return grad_x
 
 
+def group_concat_forward(points_coords, centers_coords, features, indices):
+    """Fused modules/ball_query.py:16-30 -> [B,3+C,M,U] (features may be None: C = 0)."""
+    check_f(points_coords, "points_coords"); check_f(centers_coords, "centers_coords"); check_i(indices, "indices")
+    if features is not None:
+        check_f(features, "features")
+    b, _, n = points_coords.shape
+    _, m, u = indices.shape
+    c = 0 if features is None else features.shape[1]
+    out = torch.empty((b, 3 + c, m, u), dtype=torch.float32, device=points_coords.device)
+    _lib.call("pvcnn_group_concat", b, c, n, m, u, points_coords, centers_coords, features, indices, out)
+    return out
+
+
+def group_concat_backward(grad_y, indices, n, need_features=True, need_points=False, need_centers=False):
+    """-> (grad_features [B,C,N] | None, grad_points_coords [B,3,N] | None, grad_centers_coords [B,3,M] | None)"""
+    check_f(grad_y, "grad_y"); check_i(indices, "indices")
+    b, ct = grad_y.shape[:2]
+    _, m, u = indices.shape
+    c = ct - 3
+    dev = grad_y.device
+    gf = torch.empty((b, c, int(n)), dtype=torch.float32, device=dev) if c > 0 else None
+    gp = torch.empty((b, 3, int(n)), dtype=torch.float32, device=dev) if need_points else None
+    gc = torch.empty((b, 3, m), dtype=torch.float32, device=dev) if need_centers else None
+    _lib.call("pvcnn_group_concat_grad", b, c, int(n), m, u, grad_y, indices, gf, gp, gc)
+    return (gf if need_features else None), gp, gc
+
+
 def gather_features_forward(features, indices):
     """sampling/sampling.cpp:6-23 -> [B,C,M]"""
     check_f(features, "features"); check_i(indices, "indices")

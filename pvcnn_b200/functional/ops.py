@@ -82,6 +82,37 @@ class _Grouping(Function):
 grouping = _Grouping.apply
 
 
+class _GroupConcat(Function):
+    """One-pass replacement for the tensor sequence of modules/ball_query.py:16-30
+    (grouping(coords) - centres, grouping(features), cat): same values, same gradients."""
+
+    @staticmethod
+    def forward(ctx, points_coords, centers_coords, points_features, indices):
+        points_coords = points_coords.contiguous()
+        centers_coords = centers_coords.contiguous()
+        indices = indices.contiguous()
+        if points_features is not None:
+            points_features = points_features.contiguous()
+        ctx.save_for_backward(indices)
+        ctx.num_points = points_coords.size(-1)
+        ctx.has_features = points_features is not None
+        return _backend.group_concat_forward(points_coords, centers_coords, points_features, indices)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (indices,) = ctx.saved_tensors
+        need_p, need_c, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gf, gp, gc = _backend.group_concat_backward(grad_output.contiguous(), indices, ctx.num_points,
+                                                    need_features=need_f and ctx.has_features, need_points=need_p,
+                                                    need_centers=need_c)
+        return gp, gc, gf, None
+
+
+def group_concat(points_coords, centers_coords, points_features, indices):
+    """[B,3,N], [B,3,M], [B,C,N] | None, Int[B,M,U] -> [B,3+C,M,U]"""
+    return _GroupConcat.apply(points_coords, centers_coords, points_features, indices)
+
+
 class _Gather(Function):
     """modules/functional/sampling.py:10-32"""
 

@@ -1,4 +1,3 @@
-import torch
 import torch.nn as nn
 
 from .. import functional as F
@@ -20,12 +19,13 @@ class BallQuery(nn.Module):
         points_coords = points_coords.contiguous()
         centers_coords = centers_coords.contiguous()
         idx = F.ball_query(centers_coords, points_coords, self.radius, self.num_neighbors)
-        rel = F.grouping(points_coords, idx) - centers_coords.unsqueeze(-1)
         if points_features is None:
             assert self.include_coordinates, "No Features For Grouping"
-            return rel
-        grouped = F.grouping(points_features, idx)
-        return torch.cat([rel, grouped], dim=1) if self.include_coordinates else grouped
+            return F.group_concat(points_coords, centers_coords, None, idx)
+        if not self.include_coordinates:
+            return F.grouping(points_features, idx)
+        # one kernel writes [B,3+C,M,U] directly (the reference materialises three intermediates and a cat)
+        return F.group_concat(points_coords, centers_coords, points_features, idx)
 
     def extra_repr(self):
         return "radius={}, num_neighbors={}{}".format(

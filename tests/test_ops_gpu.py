@@ -187,3 +187,52 @@ def test_autograd_wrappers():
     out = F.trilinear_devoxelize(grid, nc, r, True)
     out.sum().backward()
     assert f.grad is not None and f.grad.shape == f.shape and torch.isfinite(f.grad).all()
+
+
+@pytest.mark.parametrize("b,c,n,m,u", [(2, 32, 1024, 256, 32), (8, 9, 8192, 1024, 32), (1, 0, 50, 7, 3), (2, 5, 300, 33, 16)])
+def test_group_concat(b, c, n, m, u):
+    """Fused BallQuery grouping (modules/ball_query.py:16-30) == grouping(coords) - centres ++ grouping(features):
+    forward bit-exact (copies and one fp32 subtraction), backward to features / point coords / centre coords."""
+    g = rng(21)
+    p = s3dis_like_coords(g, b, n)
+    ce = np.ascontiguousarray(p[:, :, :m])
+    f = g.standard_normal((b, c, n), dtype=np.float32) if c else None
+    idx = oracle.ball_query(ce, p, 0.3, u)
+    out = B.group_concat_forward(cu(p), cu(ce), None if f is None else cu(f), cu(idx))
+    assert out.shape == (b, 3 + c, m, u)
+    assert np.array_equal(npy(out), oracle.group_concat(p, ce, f, idx))
+    # the composition the reference performs, on our stand-alone ops
+    rel = F.grouping(cu(p), cu(idx)) - cu(ce).unsqueeze(-1)
+    comp = rel if f is None else torch.cat([rel, F.grouping(cu(f), cu(idx))], dim=1)
+    assert torch.equal(out, comp)
+    gy = g.standard_normal((b, 3 + c, m, u), dtype=np.float32)
+    gf, gp, gc = B.group_concat_backward(cu(gy), cu(idx), n, need_features=True, need_points=True, need_centers=True)
+    of, op, oc = oracle.group_concat_grad(gy, idx, n)
+    if c:
+        assert rel_err(npy(gf), of) < TOL
+    else:
+        assert gf is None
+    assert rel_err(npy(gp), op) < TOL
+    assert rel_err(npy(gc), oc) < TOL
+
+
+def test_ball_query_module_autograd():
+    """BallQuery module (fused grouping) against the reference's tensor sequence under autograd."""
+    import modules
+    g = rng(22)
+    b, c, n, m, u = 2, 16, 2048, 256, 32
+    p = cu(s3dis_like_coords(g, b, n)).requires_grad_(True)
+    ce = p.detach()[:, :, :m].clone().requires_grad_(True)
+    f = cu(g.standard_normal((b, c, n), dtype=np.float32)).requires_grad_(True)
+    gy = cu(g.standard_normal((b, 3 + c, m, u), dtype=np.float32))
+    out = modules.BallQuery(0.25, u)(p, ce, f)
+    out.backward(gy)
+    got = [t.grad.clone() for t in (p, ce, f)]
+    for t in (p, ce, f):
+        t.grad = None
+    idx = F.ball_query(ce.detach(), p.detach(), 0.25, u)
+    ref = torch.cat([F.grouping(p, idx) - ce.unsqueeze(-1), F.grouping(f, idx)], dim=1)
+    assert torch.equal(out, ref)
+    ref.backward(gy)
+    for a, t in zip(got, (p, ce, f)):
+        assert rel_err(npy(a), npy(t.grad)) < TOL

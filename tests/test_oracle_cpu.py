@@ -171,3 +171,28 @@ def test_degenerate_voxelization():
     out, ind, cnt = oracle.avg_voxelize(f, vc, 8)
     assert (cnt > 0).sum() <= 2 * 27
     assert cnt.sum() == 2 * 256
+
+
+def test_group_concat_oracle_matches_indexing():
+    """oracle.group_concat / group_concat_grad (modules/ball_query.py:16-30) against plain numpy indexing."""
+    g = np.random.default_rng(9)
+    b, c, n, m, u = 2, 5, 40, 6, 4
+    p = g.standard_normal((b, 3, n)).astype(np.float32)
+    ce = g.standard_normal((b, 3, m)).astype(np.float32)
+    f = g.standard_normal((b, c, n)).astype(np.float32)
+    idx = g.integers(0, n, size=(b, m, u)).astype(np.int32)
+    out = oracle.group_concat(p, ce, f, idx)
+    for bi in range(b):
+        assert np.array_equal(out[bi, :3], p[bi][:, idx[bi]] - ce[bi][:, :, None])
+        assert np.array_equal(out[bi, 3:], f[bi][:, idx[bi]])
+    assert oracle.group_concat(p, ce, None, idx).shape == (b, 3, m, u)
+    gy = g.standard_normal((b, 3 + c, m, u)).astype(np.float32)
+    gf, gp, gc = oracle.group_concat_grad(gy, idx, n)
+    ref_f = np.zeros((b, c, n)); ref_p = np.zeros((b, 3, n))
+    for bi in range(b):
+        for mi in range(m):
+            for ui in range(u):
+                ref_f[bi, :, idx[bi, mi, ui]] += gy[bi, 3:, mi, ui]
+                ref_p[bi, :, idx[bi, mi, ui]] += gy[bi, :3, mi, ui]
+    assert np.allclose(gf, ref_f, atol=1e-5) and np.allclose(gp, ref_p, atol=1e-5)
+    assert np.allclose(gc, -gy[:, :3].sum(-1), atol=1e-5)

@@ -67,6 +67,17 @@ add("grouping fwd", "B8 C32 N8192 M1024 U32", lambda: B.grouping_forward(pf, bq)
     4 * b * (c * m * u + m * u + c * m * u))
 ggy = torch.randn(b, c, m, u, device="cuda", generator=g)
 add("grouping bwd", "B8 C32 N8192 M1024 U32", lambda: B.grouping_backward(ggy, bq, n), lambda: R.grouping_backward(ggy, bq, n))
+# fused BallQuery grouping (SA0 of PVCNN++: 9 -> 32 channels carried, 3 coordinate channels prepended)
+def _ref_group_concat():
+    rel = R.grouping_forward(p, bq) - ce.unsqueeze(-1)
+    return torch.cat([rel, R.grouping_forward(pf, bq)], dim=1)
+add("BallQuery grouping+centre+cat fwd (fused)", "B8 C32+3 N8192 M1024 U32", lambda: B.group_concat_forward(p, ce, pf, bq),
+    _ref_group_concat, 4 * b * ((c + 3) * m * u + m * u + (c + 3) * m * u))
+cgy = torch.randn(b, c + 3, m, u, device="cuda", generator=g)
+def _ref_group_concat_bwd():
+    return R.grouping_backward(cgy[:, 3:].contiguous(), bq, n)
+add("BallQuery grouping+centre+cat bwd (features only)", "B8 C32+3 N8192 M1024 U32",
+    lambda: B.group_concat_backward(cgy, bq, n), _ref_group_concat_bwd)
 cf = torch.randn(b, 64, m, device="cuda", generator=g)
 add("three_nn_interpolate fwd", "B8 C64 N8192 M1024", lambda: B.three_nearest_neighbors_interpolate_forward(p, ce, cf),
     lambda: R.three_nearest_neighbors_interpolate_forward(p, ce, cf))
