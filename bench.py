@@ -6,7 +6,7 @@ features ~ N(0,1) [16,64,4096], coords ~ U(0,1.5)xU(0,1.5)xU(0,3.0) [16,3,4096],
 seed 1588147245.  A "step" = zero grads, forward, backward (+ one NCCL all-reduce of the flat parameter
 gradients when N > 1).  Weak scaling: B=16 per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tf32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|tf32] [--scaling weak|strong]
 
 `--impl reference`: the reference has NO CPU implementation of this path (modules/functional/src/utils.hpp:7),
 so the reference arm is the CPU oracle (oracle/: C restatement of the reference kernels + the same torch dense
@@ -119,7 +119,12 @@ def run_ours(args):
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
-    feats_h, coords_h, gout_h = [t.pin_memory() for t in make_inputs(torch, dev)]
+    strong = args.scaling == "strong"
+    if strong and B % world:
+        raise SystemExit("--scaling strong needs the global batch (%d) divisible by the number of GPUs" % B)
+    bl = B // world if strong else B     # clouds per GPU: strong = global B=16 sharded, weak = B=16 on every GPU
+    full = make_inputs(torch, dev)
+    feats_h, coords_h, gout_h = [(t[rank * bl:(rank + 1) * bl] if strong else t).contiguous().pin_memory() for t in full]
     feats = feats_h.to(dev).requires_grad_(True)
     coords, gout = coords_h.to(dev), gout_h.to(dev)
     from pvcnn_b200.parallel import GradBucket
@@ -164,13 +169,13 @@ def run_ours(args):
     # pinned host memory; the copies run on a second stream with two buffer sets, so step i+1's upload and step i's
     # download overlap step i+1's compute (ordering by CUDA events; nothing is skipped or reused across steps).
     nbuf = 2
-    out_h = [torch.empty(B, C, N).pin_memory() for _ in range(nbuf)]
-    gfe_h = [torch.empty(B, C, N).pin_memory() for _ in range(nbuf)]
-    f_d = [torch.empty(B, C, N, device=dev, requires_grad=True) for _ in range(nbuf)]
-    c_d = [torch.empty(B, 3, N, device=dev) for _ in range(nbuf)]
-    g_d = [torch.empty(B, C, N, device=dev) for _ in range(nbuf)]
-    res_o = [torch.empty(B, C, N, device=dev) for _ in range(nbuf)]
-    res_g = [torch.empty(B, C, N, device=dev) for _ in range(nbuf)]
+    out_h = [torch.empty(bl, C, N).pin_memory() for _ in range(nbuf)]
+    gfe_h = [torch.empty(bl, C, N).pin_memory() for _ in range(nbuf)]
+    f_d = [torch.empty(bl, C, N, device=dev, requires_grad=True) for _ in range(nbuf)]
+    c_d = [torch.empty(bl, 3, N, device=dev) for _ in range(nbuf)]
+    g_d = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
+    res_o = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
+    res_g = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     up_done = [torch.cuda.Event() for _ in range(nbuf)]
@@ -229,17 +234,18 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         line = {
-            "metric": "PVConv fwd+bwd points/sec (B=16,N=4096,C=64,R=32)", "value": world * B * N / ms * 1e3,
+            "metric": "PVConv fwd+bwd points/sec (B=16,N=4096,C=64,R=32)", "value": world * bl * N / ms * 1e3,
             "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32 (3xTF32 error-compensated tensor-core passes)" if args.precision == "fp32" else "tf32",
             "data": "synthetic",
-            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, B=16/GPU N=4096",
+            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, B=%d/GPU N=4096%s" % (
+                           bl, " (global B=16 sharded)" if strong else ""),
                        "parallelism": "dp%d" % world, "precision": args.precision,
                        "l2": "activations (>2 GB/step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks,
-            "e2e": {"value": world * B * N / ms_e2e * 1e3, "unit": "points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 4 * (2 * B * C * N + B * 3 * N), "d2h_bytes_per_step": 4 * 2 * B * C * N},
+            "e2e": {"value": world * bl * N / ms_e2e * 1e3, "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 4 * (2 * bl * C * N + bl * 3 * N), "d2h_bytes_per_step": 4 * 2 * bl * C * N},
             "gpu_launches": int(launches),
             "peaks": pk,
         }
@@ -349,6 +355,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: B=16 clouds on every GPU (default, what the driver's scaling run uses); "
+                         "strong: the global B=16 batch sharded over the GPUs (SURVEY.md 8d reports both)")
     ap.add_argument("--precision", default=os.environ.get("PVCNN_B200_PRECISION", "fp32"), choices=["fp32", "tf32"])
     args = ap.parse_args()
     if args.warmup < 3:
