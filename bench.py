@@ -288,7 +288,7 @@ def single_gpu_extras(torch, dev, m, args):
     }
     # GPU reference arm (reference CUDA ops + cuDNN), informational
     try:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))  # checker-side tool: runs oracle/_ref (reference .so)
         import ref_gpu_time
         extra["reference_gpu"] = [ref_gpu_time.run(True, steps=10, warmup=5), ref_gpu_time.run(False, steps=5, warmup=2)]
     except Exception as e:  # noqa: BLE001

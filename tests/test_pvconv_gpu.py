@@ -215,7 +215,7 @@ def _close(a, b, tol, q, what=""):
     every run -- ours, the composed block, the reference itself -- flips a few of them, which changes the gradients of ONE
     voxel-channel by 10x and everything downstream of it (27 neighbouring voxels; one output channel of dW).  Measured
     against the fp64 oracle: L2 8e-4 on grad_features from a single flip, identical for the composed block
-    (tools/full_truth.py).  A flip in the second LeakyReLU reaches every channel of dW1 / BN1's gradients through conv2's
+    (tests/tools/full_truth.py).  A flip in the second LeakyReLU reaches every channel of dW1 / BN1's gradients through conv2's
     data gradient, so parameter gradients only get the L2 bound (tol=None); they are compared element-wise against the
     oracle at the small sizes above, where flips are rare.  So: the q-quantile of the element-wise error must be at
     rounding level (point tensors: a flip touches 27-125 voxels), and the L2 error must stay at the few-flips level."""

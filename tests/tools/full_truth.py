@@ -2,8 +2,8 @@
 import os, sys, time
 import numpy as np
 import torch
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import oracle
 from util import rng, s3dis_like_coords, rel_err
 from test_pvconv_gpu import make_block, _step

@@ -1,7 +1,7 @@
 """Stand-alone ops: ours (C ABI) vs the reference's own CUDA kernels (oracle/_ref .so) on the same B200.
 Writes gpurun_out/ops_bench.json; summarised in profiles/.  GPU box only."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from pvcnn_b200.functional import backend as B
