@@ -79,3 +79,59 @@ def test_reference_models_build_on_our_modules():
         assert isinstance(net.point_features[0], modules.PVConv)
     finally:
         sys.path.remove(added)
+
+
+def test_invalid_arguments_are_rejected_before_any_gpu_work():
+    """Every launcher validates sizes / pointers first and returns a non-zero status (the reference would launch and
+    `exit(-1)`, cuda_utils.cuh:28-37).  No CUDA call is reached, so this runs on the GPU-less box."""
+    import ctypes
+    from pvcnn_b200 import _lib
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    i = ctypes.c_int
+    f = ctypes.c_float
+    cases = {
+        "pvcnn_avg_voxelize": [i(0), i(4), i(8), i(2), i(4), i(8), null, null, null, null, null, null],
+        "pvcnn_avg_voxelize_grad": [i(1), i(4), i(8), i(8), null, null, null, null, null],
+        "pvcnn_trilinear_devoxelize": [i(1), i(4), i(8), i(2), i(4), i(8), i(1), null, null, null, null, null, null],
+        "pvcnn_trilinear_devoxelize_grad": [i(1), i(4), i(8), i(8), null, null, null, null, null],
+        "pvcnn_ball_query": [i(1), i(8), i(0), f(0.1), i(4), null, null, null, null],
+        "pvcnn_grouping": [i(1), i(4), i(8), i(2), i(4), null, null, null, null],
+        "pvcnn_grouping_grad": [i(1), i(4), i(8), i(2), i(4), null, null, null, null],
+        "pvcnn_group_concat": [i(1), i(4), i(8), i(2), i(4), null, null, null, null, null, null],
+        "pvcnn_group_concat_grad": [i(1), i(4), i(8), i(2), i(4), null, null, null, null, null, null],
+        "pvcnn_gather_features": [i(1), i(4), i(8), i(2), null, null, null, null],
+        "pvcnn_gather_features_grad": [i(1), i(4), i(8), i(2), null, null, null, null],
+        "pvcnn_furthest_point_sampling": [i(1), i(8), i(2), null, null, null, null],
+        "pvcnn_pvconv_forward": [null, null, null, null, null, null, null],
+        "pvcnn_pvconv_backward": [null, null, null, null, null, null, null],
+    }
+    bad_arg = 100001   # PVCNN_E_BADARG (include/pvcnn_b200.h:38); a CUDA failure would surface as a cudaError_t (< 1000)
+    for name, args in cases.items():
+        assert getattr(lib, name)(*args) == bad_arg, name
+
+
+def test_workspace_size_queries_are_host_only_and_consistent():
+    """pvcnn_pvconv_*_floats / _ints size the caller-owned workspace; pure host arithmetic."""
+    import ctypes
+    from pvcnn_b200 import _lib, fused
+    lib = _lib.load()
+    for fn in ("pvcnn_pvconv_wprep_floats", "pvcnn_pvconv_partials_floats", "pvcnn_pvconv_sparse_ints"):
+        getattr(lib, fn).restype = ctypes.c_longlong
+
+    def desc(b, n, cin, cout, r, npass=3):
+        return fused.Desc(b, n, cin, cout, r, 1, 0.0, 1, npass, 1e-4, 1e-5, 0.1, 0.1, 0)
+
+    d = desc(16, 4096, 64, 64, 32)
+    w = lib.pvcnn_pvconv_wprep_floats(ctypes.byref(d))
+    # 2 x (hi, lo) x [27 (w1) + 27 (w2) + 1 (wp)] x 64 x 64, forward and data-gradient operand copies
+    assert w == 2 * 2 * (27 + 27 + 1) * 64 * 64
+    assert lib.pvcnn_pvconv_needs_grid_lo(ctypes.byref(d)) == 1
+    assert lib.pvcnn_pvconv_needs_grid_lo(ctypes.byref(desc(16, 4096, 64, 64, 32, npass=1))) == 0
+    small, big = desc(2, 1024, 16, 16, 8), desc(4, 2048, 9, 64, 16)
+    for fn in ("pvcnn_pvconv_wprep_floats", "pvcnn_pvconv_partials_floats", "pvcnn_pvconv_sparse_ints"):
+        a, b_ = getattr(lib, fn)(ctypes.byref(small)), getattr(lib, fn)(ctypes.byref(big))
+        assert 0 < a <= b_, fn
+    # activity lists: 8 counters + one int4 per unit / k-tile + flags + 4 x 27 x C class sums
+    units, kt = 16 * 16 * 8, 16 * 32 * 32 * 1
+    assert lib.pvcnn_pvconv_sparse_ints(ctypes.byref(d)) >= 8 + 4 * 4 * units + 2 * 4 * kt + 4 * 27 * 64
