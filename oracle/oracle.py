@@ -3,7 +3,8 @@ dense (third-party) arithmetic of PVConv.
 
 Parity status: the reference ships no tests or golden vectors, so the oracle is
 pinned against the reference's *own CUDA kernels*, compiled unmodified into oracle/_ref/ and run
-on the GPU box (tests/test_ref_parity.py).  The dense ops (Conv3d / BatchNorm / Conv1d, which
+on a B200: golden outputs in tests/golden/ref_ops_golden.npz (tests/test_golden_cpu.py), live comparison in
+tests/test_ops_gpu.py.  The dense ops (Conv3d / BatchNorm / Conv1d, which
 the reference delegates to torch, modules/pvconv.py:21-26, modules/shared_mlp.py:10-24) are
 restated with the same torch calls on CPU in fp32 / fp64.
 """

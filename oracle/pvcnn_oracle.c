@@ -10,7 +10,7 @@
  * implementation (utils.hpp:7 rejects CPU tensors), so this file follows the
  * CUDA kernels line by line, including their quirks:
  *   - products are contracted into FMAs exactly where nvcc contracts them
- *     (verified on the sm_100a SASS of the reference build, see oracle/README.md);
+ *     (verified on the sm_100a SASS of the reference build);
  *     this file must therefore be compiled with -ffp-contract=off so that the
  *     explicit fmaf() calls below are the only fused operations;
  *   - atomics make the reference's summation order nondeterministic; the oracle
@@ -18,7 +18,10 @@
  *
  * Parity pinning: the reference has no tests / golden vectors.  The
  * oracle is pinned against the reference's own kernels, compiled unmodified into
- * oracle/_ref/ by oracle/build_ref.py and run on the GPU box (tests/test_ref_parity.py).
+ * oracle/_ref/ by oracle/build_ref.py and run on a B200: their outputs are committed as
+ * tests/golden/ref_ops_golden.npz (generator: tests/golden/make_golden.py) and checked on CPU by
+ * tests/test_golden_cpu.py; tests/test_ops_gpu.py additionally compares oracle, our kernels and the live
+ * reference .so on the GPU box.
  */
 #include <math.h>
 #include <stdint.h>
