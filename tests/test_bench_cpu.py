@@ -1,0 +1,34 @@
+"""bench.py's reference arm runs on the host cores only (CPU oracle), so its JSON contract can be checked on the
+GPU-less box: one line, the keys the driver reads, the cpu_baseline / e2e objects of the tier contract."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return [l for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = _run()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("PVConv fwd+bwd points/sec") and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "B=2" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["data"] == "synthetic"
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    """Under torchrun only rank 0 measures and prints; the other ranks exit 0 without work."""
+    assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
