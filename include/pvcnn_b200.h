@@ -47,9 +47,21 @@ PVCNN_API unsigned long long pvcnn_launch_count(void);
 /* ---- coordinate normalisation: modules/voxelization.py:16-25 (the reference runs ~9 ATen
  *      kernels here; we fuse them).  coords [B,3,N] -> norm_coords [B,3,N] fp32 (clamped to
  *      [0,r-1], NOT rounded; this is what devoxelize consumes) and vox_coords [B,3,N] int32
- *      (round-half-even).  The mean is the fp64 sum rounded once (oracle/pvcnn_oracle.c). */
+ *      (round-half-even).  Single-kernel variant: the mean is the fp64 sum rounded once (oracle/pvcnn_oracle.c),
+ *      which agrees with the reference's torch reduction except where an ulp flips a .5 rounding tie; the Python
+ *      layer therefore defaults to pvcnn_voxelize_denom/_apply below (PVCNN_B200_VOX=fused selects this one). */
 PVCNN_API int pvcnn_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords,
                           float *norm_coords, int *vox_coords, void *stream);
+
+/* ---- reference-exact coordinate normalisation (default of the Python layer).  `mean` [B,3] is produced by the same
+ *      ATen reduction the reference calls (coords.mean(2), modules/voxelization.py:18: its summation order belongs to
+ *      torch); the rest of modules/voxelization.py:19-24 is element-wise IEEE arithmetic plus an order-independent max
+ *      and is reproduced bit for bit.  pvcnn_voxelize_denom: denom[b] = max_i ||coords[b,:,i] - mean[b]||_2 * 2 + eps
+ *      (:20); pvcnn_voxelize_apply: the element-wise tail (:20-24); denom may be NULL when normalize == 0. */
+PVCNN_API int pvcnn_voxelize_denom(int b, int n, float eps, const float *coords, const float *mean, float *denom,
+                                   void *stream);
+PVCNN_API int pvcnn_voxelize_apply(int b, int n, int r, int normalize, const float *coords, const float *mean,
+                                   const float *denom, float *norm_coords, int *vox_coords, void *stream);
 
 /* ---- replaces avg_voxelize(...)       voxelization/vox.cuh:5-6  (kernels vox.cu:18-72) */
 PVCNN_API int pvcnn_avg_voxelize(int b, int c, int n, int r, int r2, int r3, const int *coords,
@@ -176,6 +188,8 @@ typedef struct {
   float momentum;     /* 0.1                                               */
   float slope;        /* LeakyReLU 0.1                                     */
   int with_se;        /* SE3d after the second conv block (modules/se.py), hidden = cout / 8 */
+  int vox_stats;      /* 0: fused fp64-mean normalisation; 1: ws->vox_mean given (reference-exact), denom computed;
+                         2: ws->vox_mean and ws->vox_denom given */
 } pvcnn_pvconv_desc;
 
 typedef struct { /* parameters in torch layouts; running stats are updated in training mode */
@@ -211,6 +225,8 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
   float *gy2, *gy2_lo, *gy1, *gy1_lo; /* Mv*co */
   int *sparse;              /* pvcnn_pvconv_sparse_ints(): activity lists for tile skipping (NULL = dense) */
   float *se;                /* with_se: b*(7*co + cout/8)  (pooled sums, mean, hidden, gate, d gate, dense term) */
+  float *vox_mean;          /* b*3   per-cloud coordinate mean (desc.vox_stats >= 1) */
+  float *vox_denom;         /* b     per-cloud normalisation denominator (desc.vox_stats >= 1, normalize) */
 } pvcnn_pvconv_ws;
 
 /* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided (3xTF32 mode: the weight-

@@ -64,12 +64,27 @@ _ci = ctypes.c_int
 _cf = ctypes.c_float
 
 
-def voxelize_coords(coords, r, normalize=True, eps=0.0):
+def torch_mean(coords):
+    """The reference's own mean: `coords.mean(2, keepdim=True)` (modules/voxelization.py:18) as torch computes it on
+    CPU.  GPU tests pass the same call's result from the device under test instead (mean=...)."""
+    import torch
+    return torch.from_numpy(_f(coords)).mean(2, keepdim=True).numpy().reshape(-1, 3)
+
+
+def voxelize_coords(coords, r, normalize=True, eps=0.0, mean=None):
+    """modules/voxelization.py:17-24.  mean: [B,3] result of the reference's `coords.mean(2)` (default: torch CPU);
+    mean="fp64" selects the round-1 definition (fp64 sum rounded once)."""
     coords = _f(coords)
     b, _, n = coords.shape
     nc = np.empty_like(coords)
     vc = np.empty(coords.shape, dtype=np.int32)
-    lib().oracle_voxelize_coords(_ci(b), _ci(n), _ci(r), _ci(int(normalize)), _cf(eps), _p(coords), _p(nc), _p(vc))
+    if isinstance(mean, str) and mean == "fp64":
+        lib().oracle_voxelize_coords(_ci(b), _ci(n), _ci(r), _ci(int(normalize)), _cf(eps), _p(coords), _p(nc), _p(vc))
+        return nc, vc
+    mean = _f(torch_mean(coords) if mean is None else np.asarray(mean).reshape(-1, 3))
+    assert mean.shape == (b, 3)
+    lib().oracle_voxelize_coords_given(_ci(b), _ci(n), _ci(r), _ci(int(normalize)), _cf(eps), _p(coords), _p(mean),
+                                       _p(nc), _p(vc))
     return nc, vc
 
 
@@ -210,7 +225,8 @@ def three_nn_interpolate_grad(grad_y, idx, w, m):
 # PVConv block oracle: modules/pvconv.py:33-39 wiring, dense ops through torch CPU.
 # ----------------------------------------------------------------------------------------------
 def pvconv_forward_backward(params, features, coords, grad_out, resolution, *, training=True, normalize=True,
-                            eps=0.0, with_se=False, dtype="float32", bn_eps=1e-4, momentum=0.1, buffers=None, threads=None):
+                            eps=0.0, with_se=False, dtype="float32", bn_eps=1e-4, momentum=0.1, buffers=None, threads=None,
+                            vox_mean=None):
     """Forward (+ backward when grad_out is not None) of one PVConv block on CPU.
 
     params: dict with the reference state_dict names:
@@ -276,7 +292,7 @@ def pvconv_forward_backward(params, features, coords, grad_out, resolution, *, t
             return gg * w.unsqueeze(1), None, None
 
     x = feats.to(td).requires_grad_(grad_out is not None)
-    nc, vc = voxelize_coords(np.asarray(coords, dtype=np.float32), r, normalize, eps)
+    nc, vc = voxelize_coords(np.asarray(coords, dtype=np.float32), r, normalize, eps, mean=vox_mean)
 
     if td == torch.float32:
         vox = _Vox.apply(x, vc)

@@ -82,6 +82,47 @@ ORACLE_API void oracle_voxelize_coords(int b, int n, int r, int normalize, float
   }
 }
 
+/* modules/voxelization.py:17-24 with the per-cloud mean GIVEN (the result of the reference's own
+ * `coords.mean(2, keepdim=True)`, :18, whose summation order is an implementation detail of torch).  Everything
+ * after the mean is element-wise IEEE arithmetic or an order-independent max:
+ *   norm = sqrt((x*x + y*y) + z*z)            (ATen's 3-element reduce: one accumulator per element, combined in order)
+ *   denom = max_N(norm) * 2 + eps             (:20)
+ *   v = (c - mean) / denom + 0.5  |  (c - mean + 1) / 2  ;  clamp(v * r, 0, r-1) ;  round-half-even -> int32   (:20-24) */
+ORACLE_API void oracle_voxelize_coords_given(int b, int n, int r, int normalize, float eps, const float *coords,
+                                             const float *mean_b3, float *norm_coords, int *vox_coords) {
+#pragma omp parallel for
+  for (int bi = 0; bi < b; ++bi) {
+    const float *c = coords + (size_t)bi * 3 * n;
+    const float *mean = mean_b3 + (size_t)bi * 3;
+    float *nc = norm_coords + (size_t)bi * 3 * n;
+    int *vc = vox_coords + (size_t)bi * 3 * n;
+    float maxnorm = -INFINITY;
+    if (normalize) {
+      for (int i = 0; i < n; ++i) {
+        float x = c[i] - mean[0], y = c[n + i] - mean[1], z = c[2 * n + i] - mean[2];
+        float s = x * x + y * y;
+        s = s + z * z;
+        float nr = sqrtf(s);
+        if (maxnorm != maxnorm) continue; /* NaN sticks, like torch.max */
+        if (nr > maxnorm || nr != nr) maxnorm = nr;
+      }
+    }
+    float denom = maxnorm * 2.0f + eps;
+    for (int a = 0; a < 3; ++a) {
+      for (int i = 0; i < n; ++i) {
+        float v = c[a * n + i] - mean[a];
+        if (normalize) v = v / denom + 0.5f;
+        else v = (v + 1.0f) / 2.0f;
+        v = v * (float)r;
+        if (v < 0.0f) v = 0.0f;
+        if (v > (float)(r - 1)) v = (float)(r - 1);
+        nc[a * n + i] = v;
+        vc[a * n + i] = (int)rintf(v);
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------
  * avg_voxelize forward: voxelization/vox.cu:18-34 (grid_stats_kernel) + :48-72
  * (avg_voxelize_kernel); allocation / zero-init rules from vox.cpp:17-43.

@@ -3,12 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/pvcnn_b200.h"
 
 namespace pvb {
 
 // Global launch counter (exported through pvcnn_launch_count()).
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -1,22 +1,26 @@
-// conv_halo.cu -- second-generation 3x3x3 implicit-GEMM convolution (forward / data gradient) for sm_100a.
+// conv_halo.cu -- third-generation 3x3x3 implicit-GEMM convolution (forward / data gradient) for sm_100a.
+// Replaces cuDNN's Conv3d forward / dgrad behind nn.Conv3d (modules/pvconv.py:21,24).
 //
-// v1 (conv_igemm.cu) fetches one [128 voxel x 32 channel] tile per (tap, chunk) and is bound by the
-// L2->SMEM pipe (ncu: 10.9 GB pulled from L2 per launch, tensor pipe 38 % active).  This kernel keeps a HALO
-// block of the input in shared memory and serves the 9 (dy,dx) taps of a z-shift from it:
+// v2 (conv_halo_v2.cu) loads one z-pre-shifted halo per (dz, 16-channel chunk): 3 TMA boxes and 3 `lo` conversions
+// per chunk, 12 short phases per unit, TMEM chains that grow with Cin and an epilogue that serialises with the
+// next unit's MMAs.  v3 moves the z shift to the OUTPUT side:
 //
-//   * a CTA produces 2 output tiles (two x-planes of [TY x BZ] = 128 voxels) per iteration;
-//   * per phase (dz in {-1,0,1}, 16-channel chunk) ONE 5-D TMA box brings the (TX+2) x (TY+2) x BZ halo
-//     (z pre-shifted by dz, out-of-bounds rows zero-filled = conv padding) into 64-byte-swizzled rows;
-//     a tap (dy,dx) of tile t is then just a row offset of the UMMA descriptor (multiples of 8 rows, so the
-//     swizzle phase is preserved) -- 18 tile-operands from one 768-row load instead of 18 loads of 128 rows;
-//   * the `lo` halves of the 3xTF32 split are computed IN the kernel by 4 converter warps
-//     (lo = x - trunc_tf32(x), generic-proxy writes + fence.proxy.async), so activations need no `lo`
-//     tensor in HBM and the A-side L2 traffic halves again;
-//   * weights stream through a 4-deep ring of [Cout x 16] tiles (hi, lo), one per tap and phase;
-//   * accumulators: per tile two main chains (phases 0-5 / 6-11: <= 108 MMAs each, the tensor core
-//     truncates when accumulating) and one chain for the correction terms; summed in fp32 RN in the epilogue.
-//
-// L2->SMEM traffic per conv at the metric shape: ~3.1 GB (v1: 10.9 GB).
+//   * per 16-channel chunk ONE 5-D TMA box brings the (TX+2) x (TY+2) x BZ halo (no z shift) into 64B-swizzled
+//     rows; all 27 taps are served from it.  A (dx,dy) tap of tile t is a row offset of the UMMA descriptor
+//     (multiple of 8 rows: swizzle phase preserved); the dz taps accumulate into three separate TMEM
+//     accumulators P_dz[row] = sum_{dx,dy,c} W[dx,dy,dz,c] X[x+dx, y+dy, row]  (row = un-shifted z);
+//   * the epilogue warps drain the three accumulators after EVERY chunk into fp32 registers and apply the shift
+//     there: out[z] += P_-1[z-1] + P_0[z] + P_+1[z+1]  (TMEM lane = z, so the shift is a warp shuffle by one
+//     lane; segment edges contribute zero = the conv's z padding).  Consequences:
+//       - L2->SMEM halo traffic and `lo` conversions drop 3x; a chunk phase carries 324 MMAs (3xTF32), so the
+//         2-deep halo ring is deeply hidden;
+//       - TMEM chains are 54 MMAs long for ANY Cin (the tensor core truncates when it accumulates; partial sums
+//         are combined in round-to-nearest fp32 registers), so Cin is unbounded;
+//       - the final store of unit i overlaps the MMAs of unit i+1 (accumulators are already in registers);
+//   * Cout > 64 runs as N-blocks of 64 (work item = (unit, n-block)); z extents that are not 8/16/32 are padded
+//     (R=12 -> BZ=16: the TMA box zero-fills rows z >= sz, the epilogue masks them).
+//   * `lo = x - trunc_tf32(x)` of the 3xTF32 split is computed in the kernel by 4 converter warps (once per chunk);
+//     in single-pass TF32 mode the freed shared memory becomes a 4-deep halo ring.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -25,49 +29,60 @@
 namespace pvb {
 using namespace umma;
 
-constexpr int HC_THREADS = 512;   // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-11 epilogue (one tile per 4 warps), w12-15 converters
-constexpr int HC_KC = 16;         // channels per phase (64-byte rows, SWIZZLE_64B)
-constexpr int HC_TX = 2;          // output x-planes (tiles) per CTA iteration
-constexpr int HC_BSTAGES = 4;     // weight-tile ring
-constexpr uint32_t kLayoutSW64 = 4;
+constexpr int H3_THREADS = 512;  // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-11 epilogue (tile = (w-4)/4), w12-15 converters
+constexpr int H3_KC = 16;        // channels per chunk (64-byte rows, SWIZZLE_64B)
+constexpr int H3_TX = 2;         // output x-planes (tiles) per work item
+constexpr int H3_MAX_A = 4;      // halo ring depth (2 in 3xTF32 mode at R=32)
+constexpr int H3_MAX_B = 8;      // weight-tile ring depth
+constexpr uint32_t kH3LayoutSW64 = 4;
 
-struct HaloParams {
-  int nb, sx, sy, sz;             // sz = BZ (full z rows), 128 % sz == 0, sz % 8 == 0
-  int ty;                         // y rows per tile = 128 / sz
-  int tiles_y, pairs_x;           // sy / ty (ceil), sx / 2 (ceil)
-  int num_units;                  // nb * pairs_x * tiles_y
+struct Halo3Params {
+  int nb, sx, sy, sz;
+  int bz;                         // z rows per line in shared memory: 8 / 16 / 32 (>= sz)
+  int ty;                         // y rows per tile = 128 / bz
+  int tiles_y, pairs_x;
+  int num_units;                  // nb * pairs_x * tiles_y (dense walk)
   int kchunks;                    // ceil(k / 16)
-  int cout, block_n;              // block_n = cout padded to 16 (<= 64)
-  int npass;
-  int ldo;
-  uint32_t a_rows, a_bytes;       // halo rows, bytes of one halo copy (rows * 64)
-  uint32_t b_bytes;               // bytes of one weight tile copy (block_n * 64)
+  int cout, nblocks, block_n;     // N-blocks of block_n (<= 64, multiple of 16) output channels
+  int npass, ldo;
+  int a_stages, b_stages;
+  uint32_t a_bytes, b_bytes;      // bytes of ONE copy (hi) of a halo / a weight tile
   const float *bias;
   float *out;
   int *err;
   const int4 *unit_list;          // optional compact list of (x0, y0, b, -) units to compute; others are skipped
   const int *unit_count;          //   (device count) -- activity-driven tile skipping, see pvconv_pipeline.cu
   long long *dbg;                 // optional stall counters of CTA 0 (PVCNN_STALL_PROFILE=1)
-  int exp;                        // experiment bits (PVCNN_HALO_EXP): 1 skip lo conversion, 4 skip MMA3, 8 no A loads, 16 no B loads, 32 no epilogue stores
 };
 
-__global__ void __launch_bounds__(HC_THREADS, 1)
+__device__ __forceinline__ void h3_decode(const Halo3Params &p, int unit, int &x0, int &y0, int &b) {
+  if (p.unit_list) {
+    const int4 uc = __ldg(p.unit_list + unit);
+    x0 = uc.x; y0 = uc.y; b = uc.z;
+  } else {
+    int u = unit;
+    y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
+    x0 = (u % p.pairs_x) * H3_TX; u /= p.pairs_x;
+    b = u;
+  }
+}
+
+__global__ void __launch_bounds__(H3_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w_hi,
-                     const __grid_constant__ CUtensorMap map_w_lo, const HaloParams p) {
+                     const __grid_constant__ CUtensorMap map_w_lo, const Halo3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t a_full[2], a_ready[2], a_empty[2], b_full[HC_BSTAGES], b_empty[HC_BSTAGES], acc_full, acc_empty;
+  __shared__ uint64_t a_full[H3_MAX_A], a_ready[H3_MAX_A], a_empty[H3_MAX_A], b_full[H3_MAX_B], b_empty[H3_MAX_B],
+      acc_full[3], acc_empty[3];
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool three = p.npass > 1;
-  // smem carve-up: [A buf0: hi, lo][A buf1: hi, lo][B ring: (hi, lo) x stages]
-  const uint32_t a_buf_bytes = p.a_bytes * 2;
-  uint8_t *smem_b = smem + 2 * a_buf_bytes;
-  const uint32_t b_stage_bytes = p.b_bytes * 2;
-  const int nphases = 3 * p.kchunks;
-  const int half_phase = (nphases + 1) / 2;
-  const uint32_t tmem_cols = 512;  // 2 tiles x (main0, main1, corr) x block_n <= 384 -> allocate all
+  const uint32_t a_stage_bytes = p.a_bytes * (three ? 2u : 1u);
+  const uint32_t b_stage_bytes = p.b_bytes * (three ? 2u : 1u);
+  uint8_t *smem_b = smem + (size_t)p.a_stages * a_stage_bytes;
+  const uint32_t tmem_cols = 512;  // 2 tiles x 3 dz x block_n <= 384 columns; one CTA per SM -> take all
   const int num_units = p.unit_list ? __ldg(p.unit_count) : p.num_units;
+  const int num_items = num_units * p.nblocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a);
@@ -75,14 +90,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     if (three) prefetch_tensormap(&map_w_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_ready[i], 128);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < HC_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(&acc_full, 1);
-    mbar_init(&acc_empty, 256);
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -92,61 +106,41 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ================================ TMA producer: activation halos ================================
-    // (own thread, so the next phase's halo is requested as soon as its buffer frees up, independent of
-    //  how far the weight ring has advanced)
+    // ================================ TMA producer: activation halos (one per chunk) ================================
     if (elect_one()) {
-      int abuf = 0;
-      uint32_t aphase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int ast = 0;
+      uint32_t aph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int x0, y0, b;
-        if (p.unit_list) {
-          const int4 uc = __ldg(p.unit_list + unit);
-          x0 = uc.x; y0 = uc.y; b = uc.z;
-        } else {
-          int u = unit;
-          y0 = (u % p.tiles_y) * p.ty; u /= p.tiles_y;
-          x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
-          b = u;
-        }
-        int dz = -1, cc = 0;
-        for (int ph = 0; ph < nphases; ++ph) {
-          mbar_wait(&a_empty[abuf], aphase ^ 1, p.err, 21);
-          if (p.exp & 8) {  // experiment: no activation traffic
-            mbar_arrive(&a_full[abuf]);
-          } else {
-            mbar_arrive_expect_tx(&a_full[abuf], p.a_bytes);
-            tma_load_5d(smem + (size_t)abuf * a_buf_bytes, &map_a, &a_full[abuf], cc * HC_KC, dz, y0 - 1, x0 - 1, b);
-          }
-          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
-          if (++cc == p.kchunks) { cc = 0; ++dz; }
+        h3_decode(p, item / p.nblocks, x0, y0, b);
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(&a_empty[ast], aph ^ 1, p.err, 21);
+          mbar_arrive_expect_tx(&a_full[ast], p.a_bytes);
+          tma_load_5d(smem + (size_t)ast * a_stage_bytes, &map_a, &a_full[ast], cc * H3_KC, 0, y0 - 1, x0 - 1, b);
+          if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 3) {
-    // ================================ TMA producer: weight tiles ================================
+    // ================================ TMA producer: weight tiles (27 per chunk) ================================
     if (elect_one()) {
       int bst = 0;
-      uint32_t bphase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        int dz = -1, cc = 0;
-        for (int ph = 0; ph < nphases; ++ph) {
+      uint32_t bph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n0 = (item % p.nblocks) * p.block_n;
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {  // taps (dx, dy) of this dz
-            const int dx = t9 / 3 - 1, dy = t9 % 3 - 1;
-            const int tap = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
-            mbar_wait(&b_empty[bst], bphase ^ 1, p.err, 22);
-            uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
-            if (p.exp & 16) {  // experiment: no weight traffic
-              mbar_arrive(&b_full[bst]);
-            } else {
-              mbar_arrive_expect_tx(&b_full[bst], three ? 2 * p.b_bytes : p.b_bytes);
-              tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * HC_KC, 0, tap);
-              if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * HC_KC, 0, tap);
+            for (int t9 = 0; t9 < 9; ++t9) {  // t9 = (dx+1)*3 + (dy+1); torch tap index = kx*9 + ky*3 + kz
+              const int tap = (t9 / 3) * 9 + (t9 % 3) * 3 + dz;
+              mbar_wait(&b_empty[bst], bph ^ 1, p.err, 22);
+              uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
+              mbar_arrive_expect_tx(&b_full[bst], b_stage_bytes);
+              tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * H3_KC, n0, tap);
+              if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * H3_KC, n0, tap);
+              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
             }
-            if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
           }
-          if (++cc == p.kchunks) { cc = 0; ++dz; }
         }
       }
     }
@@ -154,89 +148,87 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
-      constexpr uint32_t dhi = desc_hi32(512, kLayoutSW64);
-      // descriptor offsets (16-byte units) of tile t / tap t9 inside the halo: rows are (x_local, y_local, z)
-      uint32_t tap_off[9][HC_TX];
+      constexpr uint32_t dhi = desc_hi32(512, kH3LayoutSW64);
+      // descriptor offsets (16-byte units) of tile t / tap (dx,dy) inside the halo: rows are (x_local, y_local, z)
+      uint32_t tap_off[9][H3_TX];
 #pragma unroll
       for (int t9 = 0; t9 < 9; ++t9)
 #pragma unroll
-        for (int t = 0; t < HC_TX; ++t)
-          tap_off[t9][t] = (uint32_t)(((t + t9 / 3) * (p.ty + 2) + (t9 % 3)) * p.sz) * (HC_KC * 4 / 16);
+        for (int t = 0; t < H3_TX; ++t)
+          tap_off[t9][t] = (uint32_t)(((t + t9 / 3) * (p.ty + 2) + (t9 % 3)) * p.bz) * (H3_KC * 4 / 16);
       const uint32_t bn = (uint32_t)p.block_n;
-      int abuf = 0, bst = 0, it = 0;
-      uint32_t aphase = 0, bphase = 0;
+      uint64_t *a_bar = three ? a_ready : a_full;  // single pass: nothing to convert, consume the TMA data directly
+      int ast = 0, bst = 0;
+      uint32_t aph = 0, bph = 0, g = 0;  // g: chunk phases issued so far (accumulator hand-shake parity)
       long long st_acc = 0, st_a = 0, st_b = 0;
+      int items_done = 0;
       const long long t_begin = clock64();
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-        mbar_wait_t(&acc_empty, (uint32_t)((it & 1) ^ 1), p.err, 23, st_acc);
-        tc_fence_after();
-        for (int ph = 0; ph < nphases; ++ph) {
-          mbar_wait_t(&a_ready[abuf], aphase, p.err, 24, st_a);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++items_done) {
+        for (int cc = 0; cc < p.kchunks; ++cc, ++g) {
+          mbar_wait_t(&a_bar[ast], aph, p.err, 24, st_a);
           tc_fence_after();
-          const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)abuf * a_buf_bytes), 0);
+          const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)ast * a_stage_bytes), 0);
           const uint32_t a_lo = a_hi + (p.a_bytes >> 4);
-          const uint32_t slot_col = ph < half_phase ? 0u : bn;
-          const uint32_t fresh_main = ((ph == 0) || (ph == half_phase)) ? 0u : 1u;
-          const uint32_t fresh_corr = ph == 0 ? 0u : 1u;
-          // software-pipelined barrier polling: the try_wait for the NEXT weight tile is issued before this
-          // tile's MMAs, so its latency hides behind the MMA issue instead of sitting on the critical path
-          bool b_ready = mbar_try_wait(&b_full[bst], bphase);
-#pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            if (!b_ready) mbar_wait_t(&b_full[bst], bphase, p.err, 25, st_b);
-            {
-              const int nst = (bst + 1 == HC_BSTAGES) ? 0 : bst + 1;
-              const uint32_t nph = (bst + 1 == HC_BSTAGES) ? (bphase ^ 1) : bphase;
-              b_ready = mbar_try_wait(&b_full[nst], nph);
-            }
+          for (int dz = 0; dz < 3; ++dz) {
+            // the epilogue has copied the previous chunk's P_dz (both tiles) into registers
+            mbar_wait_t(&acc_empty[dz], (g & 1u) ^ 1u, p.err, 23, st_acc);
             tc_fence_after();
-            const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
-            const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
+            // software-pipelined barrier polling: the try_wait for the NEXT weight tile is issued before this
+            // tile's MMAs, so its latency hides behind the MMA issue instead of sitting on the critical path
+            bool b_ready = mbar_try_wait(&b_full[bst], bph);
 #pragma unroll
-            for (int t = 0; t < HC_TX; ++t) {
-              const uint32_t d_main = tmem_base + (uint32_t)t * 3u * bn + slot_col;
-              const uint32_t d_corr = tmem_base + (uint32_t)t * 3u * bn + 2u * bn;
+            for (int t9 = 0; t9 < 9; ++t9) {
+              if (!b_ready) mbar_wait_t(&b_full[bst], bph, p.err, 25, st_b);
+              {
+                const int nst = (bst + 1 == p.b_stages) ? 0 : bst + 1;
+                const uint32_t nph = (bst + 1 == p.b_stages) ? (bph ^ 1) : bph;
+                b_ready = mbar_try_wait(&b_full[nst], nph);
+              }
+              tc_fence_after();
+              const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
+              const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
 #pragma unroll
-              for (int ks = 0; ks < HC_KC / 8; ++ks) {
-                const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
-                const uint32_t first = (t9 == 0 && ks == 0) ? 1u : 0u;
-                if (three) {
-                  if (!(p.exp & 2)) {  // A_hi is fetched from shared memory once and reused from the collector (-3 %)
-                    mma_tf32_lo32_c<kCollFill>(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
-                    mma_tf32_lo32_c<kCollLastUse>(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+              for (int t = 0; t < H3_TX; ++t) {
+                const uint32_t d = tmem_base + (uint32_t)(t * 3 + dz) * bn;
+#pragma unroll
+                for (int ks = 0; ks < H3_KC / 8; ++ks) {
+                  const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
+                  const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;    // every chunk starts a fresh chain
+                  if (three) {
+                    // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
+                    mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                    mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_lo + ks * 2u, dhi, idesc, 1u);
+                    mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
                   } else {
-                    mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
-                    mma_tf32_lo32(d_corr, a_hi + ao, b_lo + ks * 2u, dhi, idesc, first ? fresh_corr : 1u);
+                    mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
                   }
-                  if (!(p.exp & 4)) mma_tf32_lo32(d_corr, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
-                } else {
-                  mma_tf32_lo32(d_main, a_hi + ao, b_hi + ks * 2u, dhi, idesc, first ? fresh_main : 1u);
                 }
               }
+              mma_commit(&b_empty[bst]);
+              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
             }
-            mma_commit(&b_empty[bst]);
-            if (++bst == HC_BSTAGES) { bst = 0; bphase ^= 1; }
+            mma_commit(&acc_full[dz]);
           }
-          mma_commit(&a_empty[abuf]);
-          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+          mma_commit(&a_empty[ast]);
+          if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
         }
-        mma_commit(&acc_full);
       }
-      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = it; }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = items_done; }
     }
   } else if (warp >= 12) {
     // ================================ converters: lo = x - trunc_tf32(x) ================================
-    const int tid = threadIdx.x - 12 * 32;  // 0..127
-    int abuf = 0;
-    uint32_t aphase = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      for (int ph = 0; ph < nphases; ++ph) {
-        mbar_wait(&a_full[abuf], aphase, p.err, 26);
-        if (three && !(p.exp & 1)) {
-          const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)abuf * a_buf_bytes);
-          float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)abuf * a_buf_bytes + p.a_bytes);
-          const int n16 = (int)(p.a_bytes >> 4);
+    if (three) {
+      const int tid = threadIdx.x - 12 * 32;  // 0..127
+      int ast = 0;
+      uint32_t aph = 0;
+      const int n16 = (int)(p.a_bytes >> 4);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(&a_full[ast], aph, p.err, 26);
+          const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)ast * a_stage_bytes);
+          float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)ast * a_stage_bytes + p.a_bytes);
           // elementwise on the swizzled bytes: hi and lo share the same layout
+#pragma unroll 4
           for (int i = tid; i < n16; i += 128) {
             const float4 v = src[i];
             float4 l;
@@ -247,85 +239,94 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
             dst[i] = l;
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          mbar_arrive(&a_ready[ast]);
+          if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
         }
-        mbar_arrive(&a_ready[abuf]);
-        if (++abuf == 2) { abuf = 0; aphase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
-    const int we = (warp - 4) & 3;   // TMEM lane quarter
+    // ================================ epilogue: drain per chunk, z shift, bias, store ================================
+    const int q = (warp - 4) & 3;      // TMEM lane quarter
     const int my_t = (warp - 4) >> 2;  // the output tile (x-plane) this warp drains: the two tiles drain in parallel
-    const int m = we * 32 + lane;
-    const int lz = m % p.sz, ly = m / p.sz;
-    int it = 0;
+    const int m = q * 32 + lane;
+    const int lz = m % p.bz, ly = m / p.bz;
+    const bool z_first = lz == 0, z_last = lz == p.bz - 1;
+    const int bn = p.block_n;
+    uint32_t g = 0;
     long long st_full = 0;
     const long long t_begin = clock64();
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-      int x0, y, b;
-      if (p.unit_list) {
-        const int4 uc = __ldg(p.unit_list + unit);
-        x0 = uc.x; y = uc.y + ly; b = uc.z;
-      } else {
-        int u = unit;
-        y = (u % p.tiles_y) * p.ty + ly; u /= p.tiles_y;
-        x0 = (u % p.pairs_x) * HC_TX; u /= p.pairs_x;
-        b = u;
-      }
-      mbar_wait_t(&acc_full, (uint32_t)(it & 1), p.err, 27, st_full);
-      tc_fence_after();
-      {
-        const int t = my_t;
-        const int x = x0 + t;
-        const bool valid = x < p.sx && y < p.sy;
-        float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + lz) * p.ldo;
-        const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(t * 3 * p.block_n);
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-          // all three partial accumulators of a 32-column slab are requested before a single wait
-          uint32_t ra[32], rb[32], rc[32];
-          float v[32];
-          if (c0 + 32 <= p.block_n) {
-            tmem_ld32_nowait(taddr + c0, ra);
-            tmem_ld32_nowait(taddr + p.block_n + c0, rb);
-            if (three) tmem_ld32_nowait(taddr + 2 * p.block_n + c0, rc);
-            tmem_ld_wait();
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      float acc[64];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
-              if (three) v[i] += __uint_as_float(rc[i]);
-            }
-          } else {  // block_n == 16 or 48: 16-column tail
-            float w[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld16(taddr + p.block_n + c0, w);
+      for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
+      for (int cc = 0; cc < p.kchunks; ++cc, ++g) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
-            if (three) {
-              tmem_ld16(taddr + 2 * p.block_n + c0, w);
+        for (int dz = 0; dz < 3; ++dz) {
+          mbar_wait_t(&acc_full[dz], g & 1u, p.err, 27, st_full);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((my_t * 3 + dz) * bn);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += w[i];
-            }
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            if (c0 < bn) {  // warp-uniform
+              uint32_t r[32];
+              if (c0 + 32 <= bn) {
+                tmem_ld32_nowait(taddr + c0, r);
+                tmem_ld_wait();
+              } else {  // block_n == 16 or 48: 16-column tail
+                float w[16];
+                tmem_ld16(taddr + c0, w);
 #pragma unroll
-            for (int i = 16; i < 32; ++i) v[i] = 0.f;
-          }
-          if (valid && c0 < p.cout) {
-            if (p.bias) {
+                for (int i = 0; i < 16; ++i) { r[i] = __float_as_uint(w[i]); r[16 + i] = 0u; }
+              }
+              if (c0 + 32 >= bn) {  // last slab of this accumulator is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(&acc_empty[dz]);
+              }
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.cout) v[i] += __ldg(p.bias + c0 + i);
-            }
-            if (c0 + 32 <= p.cout) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4 *>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              for (int i = 0; i < 32 && c0 + i < p.cout; ++i) orow[c0 + i] = v[i];
+              for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(r[i]);
+                if (dz == 0) {         // P_-1: out[z] takes row z-1
+                  v = __shfl_up_sync(0xffffffffu, v, 1);
+                  if (z_first) v = 0.0f;
+                } else if (dz == 2) {  // P_+1: out[z] takes row z+1
+                  v = __shfl_down_sync(0xffffffffu, v, 1);
+                  if (z_last) v = 0.0f;
+                }
+                acc[c0 + i] = __fadd_rn(acc[c0 + i], v);
+              }
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty);
+      // ---- bias + store (the MMA warp is already working on the next item)
+      int x0, y0, b;
+      const int unit = item / p.nblocks;
+      h3_decode(p, unit, x0, y0, b);
+      const int n0 = (item - unit * p.nblocks) * bn;
+      const int x = x0 + my_t, y = y0 + ly;
+      const int ncols = min(bn, p.cout - n0);
+      if (x < p.sx && y < p.sy && lz < p.sz) {
+        float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + lz) * p.ldo + n0;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          if (i < ncols) {
+            float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            if (p.bias) {
+              v.x += __ldg(p.bias + n0 + i);
+              if (i + 1 < ncols) v.y += __ldg(p.bias + n0 + i + 1);
+              if (i + 2 < ncols) v.z += __ldg(p.bias + n0 + i + 2);
+              if (i + 3 < ncols) v.w += __ldg(p.bias + n0 + i + 3);
+            }
+            if (i + 4 <= ncols) {
+              *reinterpret_cast<float4 *>(orow + i) = v;
+            } else {
+              orow[i] = v.x;
+              if (i + 1 < ncols) orow[i + 1] = v.y;
+              if (i + 2 < ncols) orow[i + 2] = v.z;
+            }
+          }
+        }
+      }
     }
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 4 * 32) { p.dbg[5] = st_full; p.dbg[6] = clock64() - t_begin; }
   }
@@ -339,51 +340,70 @@ __global__ void __launch_bounds__(HC_THREADS, 1)
 
 int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsigned long long *gdim,
                        const unsigned long long *gstride_bytes, const unsigned *box, int swizzle_kind);  // conv_igemm.cu
+long long *stall_profile_buffer();                                                                       // conv_igemm.cu
+int *device_error_flag(int slot);                                                                        // conv_igemm.cu
 
-// shape envelope of this kernel (also used by the pipeline to decide whether `lo` grids are needed at all)
-bool conv_halo_supported(int sx, int sy, int sz, int cout) {
-  (void)sy;
-  if (!(sz % 8 == 0 && sz <= 128 && 128 % sz == 0 && cout <= 64 && sx >= 2)) return false;
-  const int ty = 128 / sz;
-  const size_t a_bytes = (size_t)sz * (ty + 2) * (HC_TX + 2) * HC_KC * 4;
-  const int bn = max(16, ((cout + 15) / 16) * 16);
-  const size_t smem = 2 * a_bytes * 2 + (size_t)HC_BSTAGES * bn * HC_KC * 4 * 2 + 1024;
-  return a_bytes % 1024 == 0 && smem <= 227 * 1024 - 512;
+int conv_halo_v2_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
+                        const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream,
+                        const int4 *unit_list, const int *unit_count);  // conv_halo_v2.cu
+bool conv_halo_v2_supported(int sx, int sy, int sz, int cout);
+
+static bool halo_use_v2() {
+  const char *e = getenv("PVCNN_B200_CONV");
+  return e && e[0] == 'v' && e[1] == '2';
 }
 
-long long *stall_profile_buffer();  // conv_igemm.cu
+// z rows per shared-memory line (the tile is 128 = bz * ty rows); 0 = outside the envelope
+int conv_halo_bz(int sz) { return sz <= 8 ? 8 : (sz <= 16 ? 16 : (sz <= 32 ? 32 : 0)); }
+// y rows per output tile of the kernel that will run this shape (the activity lists are built in these units)
+int conv_halo_ty(int sz) {
+  if (halo_use_v2()) return 128 / sz > 0 ? 128 / sz : 1;
+  const int bz = conv_halo_bz(sz);
+  return bz ? 128 / bz : 1;
+}
 
-static int *g_halo_err = nullptr;
+// shape envelope of this kernel (the pipeline enables activity skipping when every 3x3x3 conv of a block is inside it)
+bool conv_halo_supported(int sx, int sy, int sz, int cout) {
+  if (halo_use_v2()) return conv_halo_v2_supported(sx, sy, sz, cout);
+  (void)sy; (void)cout;
+  return conv_halo_bz(sz) != 0 && sx >= 2;
+}
 
 // Returns PVCNN_E_UNSUPPORTED when the shape is outside this kernel's envelope (caller falls back to v1).
 int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const float *a, int lda, const float *w_hi,
                      const float *w_lo, int ldw, const float *bias, float *out, int ldo, int npass, cudaStream_t stream,
                      const int4 *unit_list, const int *unit_count) {
+  if (halo_use_v2())
+    return conv_halo_v2_launch(nb, sx, sy, sz, k, cout, a, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream, unit_list,
+                               unit_count);
   if (!conv_halo_supported(sx, sy, sz, cout)) return PVCNN_E_UNSUPPORTED;
   PVB_CHECK_ARG(a && w_hi && out && (npass == 1 || w_lo) && lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0);
-  if (!g_halo_err) {
-    PVB_CUDA(cudaMalloc((void **)&g_halo_err, sizeof(int)));
-    PVB_CUDA(cudaMemset(g_halo_err, 0, sizeof(int)));
-  }
-  HaloParams p{};
+  Halo3Params p{};
   p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
-  p.ty = 128 / sz;
+  p.bz = conv_halo_bz(sz);
+  p.ty = 128 / p.bz;
   p.tiles_y = ceil_div(sy, p.ty);
-  p.pairs_x = ceil_div(sx, HC_TX);
+  p.pairs_x = ceil_div(sx, H3_TX);
   p.num_units = nb * p.pairs_x * p.tiles_y;
-  p.kchunks = ceil_div(k, HC_KC);
+  p.kchunks = ceil_div(k, H3_KC);
   p.cout = cout;
-  p.block_n = max(16, ((cout + 15) / 16) * 16);
+  p.block_n = cout >= 64 ? 64 : max(16, ((cout + 15) / 16) * 16);
+  p.nblocks = ceil_div(cout, p.block_n);
   p.npass = npass;
   p.ldo = ldo;
-  p.a_rows = (uint32_t)(sz * (p.ty + 2) * (HC_TX + 2));
-  p.a_bytes = p.a_rows * HC_KC * 4;
-  p.b_bytes = (uint32_t)p.block_n * HC_KC * 4;
-  p.bias = bias; p.out = out; p.err = g_halo_err;
+  p.a_bytes = (uint32_t)(p.bz * (p.ty + 2) * (H3_TX + 2)) * H3_KC * 4;
+  p.b_bytes = (uint32_t)p.block_n * H3_KC * 4;
+  if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
+  const uint32_t a_stage = p.a_bytes * (npass > 1 ? 2 : 1), b_stage = p.b_bytes * (npass > 1 ? 2 : 1);
+  const int budget = 227 * 1024 - 1024 - 1024;  // alignment slack + static shared memory (barriers)
+  p.a_stages = min(H3_MAX_A, (budget - 4 * (int)b_stage) / (int)a_stage);
+  if (p.a_stages < 2) return PVCNN_E_UNSUPPORTED;
+  p.b_stages = min(H3_MAX_B, (budget - p.a_stages * (int)a_stage) / (int)b_stage);
+  p.bias = bias; p.out = out;
+  p.err = device_error_flag(1);
+  PVB_CHECK_ARG(p.err != nullptr);
   p.unit_list = unit_list; p.unit_count = unit_count;
   p.dbg = stall_profile_buffer();
-  { const char *e = getenv("PVCNN_HALO_EXP"); p.exp = e ? atoi(e) : 0; }
-  if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
 
   CUtensorMap ma, mw_hi, mw_lo;
   {
@@ -391,24 +411,23 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
                                   (unsigned long long)sx, (unsigned long long)nb};
     unsigned long long gstr[4] = {(unsigned long long)lda * 4, (unsigned long long)sz * lda * 4,
                                   (unsigned long long)sy * sz * lda * 4, (unsigned long long)sx * sy * sz * lda * 4};
-    unsigned box[5] = {(unsigned)HC_KC, (unsigned)sz, (unsigned)(p.ty + 2), (unsigned)(HC_TX + 2), 1};
+    unsigned box[5] = {(unsigned)H3_KC, (unsigned)p.bz, (unsigned)(p.ty + 2), (unsigned)(H3_TX + 2), 1};
     int rc = encode_map_generic(&ma, a, 5, gdim, gstr, box, 64);
     if (rc) return rc;
   }
   {
     unsigned long long gdim[3] = {(unsigned long long)k, (unsigned long long)cout, 27ull};
     unsigned long long gstr[2] = {(unsigned long long)ldw * 4, (unsigned long long)cout * ldw * 4};
-    unsigned box[3] = {(unsigned)HC_KC, (unsigned)p.block_n, 1};
+    unsigned box[3] = {(unsigned)H3_KC, (unsigned)p.block_n, 1};
     int rc = encode_map_generic(&mw_hi, w_hi, 3, gdim, gstr, box, 64);
     if (rc) return rc;
     rc = encode_map_generic(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box, 64);
     if (rc) return rc;
   }
-  const size_t smem = 2 * (size_t)p.a_bytes * 2 + (size_t)HC_BSTAGES * p.b_bytes * 2 + 1024;
-  if (smem > 227 * 1024 - 512) return PVCNN_E_UNSUPPORTED;
+  const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024;
   PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = min(kNumSMs, p.num_units);
-  PVB_LAUNCH(conv_halo_kernel, grid, HC_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+  const int grid = min(kNumSMs, p.num_units * p.nblocks);
+  PVB_LAUNCH(conv_halo_kernel, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
   return 0;
 }
 

@@ -344,21 +344,42 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
 
 // Optional device buffer [8] of stall-cycle counters written by CTA 0 of the tensor-core kernels when
 // PVCNN_STALL_PROFILE=1 (tools/stall_profile.py reads it back through pvcnn_stall_profile_read).
+// Per-device scratch (several GPUs may be driven from one process, e.g. nn.DataParallel in the reference's train.py:181):
+// every device gets its own error-flag ints and stall-counter buffer, created under a mutex on first use.
+static std::mutex g_dev_mu;
+static int *g_dev_flags[64][4];
+static long long *g_dev_stall[64];
+static bool g_dev_stall_init[64];
+
+int *device_error_flag(int slot) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || slot < 0 || slot >= 4) return nullptr;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev_flags[dev][slot]) {
+    int *p = nullptr;
+    if (cudaMalloc((void **)&p, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(int));
+    g_dev_flags[dev][slot] = p;
+  }
+  return g_dev_flags[dev][slot];
+}
+
 long long *stall_profile_buffer() {
-  static long long *buf = nullptr;
-  static bool init = false;
-  if (!init) {
-    init = true;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev_stall_init[dev]) {
+    g_dev_stall_init[dev] = true;
     const char *e = getenv("PVCNN_STALL_PROFILE");
+    long long *buf = nullptr;
     if (e && e[0] == '1' && cudaMalloc((void **)&buf, 8 * sizeof(long long)) == cudaSuccess)
       cudaMemset(buf, 0, 8 * sizeof(long long));
     else
       buf = nullptr;
+    g_dev_stall[dev] = buf;
   }
-  return buf;
+  return g_dev_stall[dev];
 }
-
-static int *g_err_flag = nullptr;  // device int, set by a starving mbarrier wait before it traps
 
 }  // namespace pvb
 
@@ -415,10 +436,8 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
     }
   }
   PVB_CHECK_ARG(npass == 1 || a_lo);  // the v1 kernel reads a materialised lo tensor
-  if (!g_err_flag) {
-    PVB_CUDA(cudaMalloc((void **)&g_err_flag, sizeof(int)));
-    PVB_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
-  }
+  int *g_err_flag = device_error_flag(0);
+  PVB_CHECK_ARG(g_err_flag != nullptr);
   IgemmParams p{};
   p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
   // tile box: up to 128 voxels, z fastest
@@ -501,6 +520,7 @@ int pvcnn_stall_profile_read(long long *host8) {
 /* Diagnostic: code of the mbarrier wait that starved (0 = none); readable after a trapped launch only
  * through a fresh context, so mainly useful under compute-sanitizer / in bring-up tests. */
 int pvcnn_igemm_last_error(int *host_code) {
+  int *g_err_flag = pvb::device_error_flag(0);
   if (!g_err_flag) { *host_code = 0; return 0; }
   return (int)cudaMemcpy(host_code, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
 }

@@ -318,19 +318,17 @@ int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, 
 
 long long *stall_profile_buffer();  // conv_igemm.cu
 
-static int *g_wg_err = nullptr;
+int *device_error_flag(int slot);  // conv_igemm.cu
 
-// x: layer input [nb,sx,sy,sz,ldx] (cin valid), g: output gradient [nb,sx,sy,sz,ldg] (cout valid)
-int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
+// x: layer input [nb,sx,sy,sz,ldx] (cin valid), g: output gradient [nb,sx,sy,sz,ldg] (cout <= 128 valid)
+static int wgrad_launch_block(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
                  const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out) {
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
   PVB_CHECK_ARG(x_hi && g_hi && dw && ldx % 4 == 0 && ldg % 4 == 0);
-  if (cout > 128) return PVCNN_E_UNSUPPORTED;  // TODO(round 2): N tiling for wide SharedMLPs
-  if (!g_wg_err) {
-    PVB_CUDA(cudaMalloc((void **)&g_wg_err, sizeof(int)));
-    PVB_CUDA(cudaMemset(g_wg_err, 0, sizeof(int)));
-  }
+  PVB_CHECK_ARG(cout <= 128);
+  int *g_wg_err = device_error_flag(2);
+  PVB_CHECK_ARG(g_wg_err != nullptr);
   WgradParams p{};
   p.nb = nb; p.sx = sx; p.sy = sy; p.sz = sz;
   p.bz = ((min(sz, WG_ROWS) + 7) / 8) * 8;
@@ -386,6 +384,21 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
   } else {
     PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PVB_LAUNCH(conv_wgrad_kernel<1>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+  }
+  return 0;
+}
+
+// Any cout: output channels are walked in blocks of 128 (the N extent of one TMEM accumulator set); a block reads its
+// own channel slice of g (pointer offset inside the channels-last rows) and writes its own rows of dW.
+int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
+                 int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
+                 const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out) {
+  PVB_CHECK_ARG(cout > 0 && g_hi && dw && cin > 0 && (ntaps == 1 || ntaps == 27));
+  for (int n0 = 0; n0 < cout; n0 += 128) {
+    const int nblk = min(128, cout - n0);
+    const int rc = wgrad_launch_block(nb, sx, sy, sz, cin, nblk, ntaps, x_hi, x_lo, ldx, g_hi + n0, g_lo ? g_lo + n0 : nullptr,
+                                      ldg, dw + (size_t)n0 * cin * ntaps, npass, s, ktile_list, ktile_count, bz_out, by_out);
+    if (rc != 0) return rc;
   }
   return 0;
 }

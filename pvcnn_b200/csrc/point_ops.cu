@@ -9,7 +9,7 @@
 #include "common.cuh"
 
 namespace pvb {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 // =====================================================================================
 // Coordinate normalisation  (modules/voxelization.py:16-25)
@@ -73,6 +73,51 @@ __global__ void __launch_bounds__(512) voxelize_coords_kernel(int n, int r, int 
     if (v > hi) v = hi;
     norm_coords[(size_t)b * 3 * n + idx] = v;
     vox_coords[(size_t)b * 3 * n + idx] = __float2int_rn(v);
+  }
+}
+
+// ---- reference-exact variant (default): the per-cloud mean comes from the SAME ATen reduction the reference runs
+// (coords.mean(2), modules/voxelization.py:18 -- its summation order is an implementation detail of torch), everything
+// after it is element-wise IEEE arithmetic or an order-independent max, reproduced here op by op without contraction:
+//   norm = sqrt((x*x + y*y) + z*z)  (ATen's 3-element reduce: one accumulator per element, combined left to right)
+//   denom = max_N(norm) * 2 + eps ;  v = (c - mean) / denom + 0.5  |  (c - mean + 1) * 0.5 ;  clamp(v * r, 0, r-1)
+// One CTA per cloud for the max; the element-wise tail runs over the whole chip.
+__global__ void __launch_bounds__(512) voxelize_denom_kernel(int n, float eps, const float *__restrict__ coords,
+                                                             const float *__restrict__ mean,
+                                                             float *__restrict__ denom) {
+  __shared__ float sf[32];
+  const int b = blockIdx.x;
+  const float *c = coords + (size_t)b * 3 * n;
+  const float m0 = mean[b * 3 + 0], m1 = mean[b * 3 + 1], m2 = mean[b * 3 + 2];
+  float mx = -INFINITY;  // torch.max over non-negative norms; NaN propagates
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = __fsub_rn(c[i], m0), y = __fsub_rn(c[n + i], m1), z = __fsub_rn(c[2 * n + i], m2);
+    float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    s = __fadd_rn(s, __fmul_rn(z, z));
+    mx = OpMaxNan()(__fsqrt_rn(s), mx);
+  }
+  mx = block_allreduce(mx, OpMaxNan(), sf);
+  if (threadIdx.x == 0) denom[b] = __fadd_rn(__fmul_rn(mx, 2.0f), eps);
+}
+
+__global__ void __launch_bounds__(256) voxelize_apply_kernel(int n, int r, int normalize, long long total,
+                                                             const float *__restrict__ coords,
+                                                             const float *__restrict__ mean,
+                                                             const float *__restrict__ denom,
+                                                             float *__restrict__ norm_coords,
+                                                             int *__restrict__ vox_coords) {
+  const float rf = (float)r, hi = (float)(r - 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int ba = (int)(t / n);  // b * 3 + axis
+    float v = __fsub_rn(coords[t], __ldg(mean + ba));
+    if (normalize) v = __fadd_rn(__fdiv_rn(v, __ldg(denom + ba / 3)), 0.5f);
+    else v = __fmul_rn(__fadd_rn(v, 1.0f), 0.5f);
+    v = __fmul_rn(v, rf);
+    if (v < 0.0f) v = 0.0f;   // torch.clamp: NaN stays NaN
+    if (v > hi) v = hi;
+    norm_coords[t] = v;
+    vox_coords[t] = __float2int_rn(v);  // torch.round (half to even) + .to(int32)
   }
 }
 
@@ -636,12 +681,29 @@ int pvcnn_abi_version(void) { return PVCNN_B200_ABI_VERSION; }
 const char *pvcnn_build_info(void) {
   return "pvcnn_b200 sm_100a (nvcc " __DATE__ " " __TIME__ ")";
 }
-unsigned long long pvcnn_launch_count(void) { return pvb::g_launches; }
+unsigned long long pvcnn_launch_count(void) { return pvb::g_launches.load(); }
 
 int pvcnn_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords, float *norm_coords,
                           int *vox_coords, void *stream) {
   PVB_CHECK_ARG(b > 0 && n > 0 && r > 0 && coords && norm_coords && vox_coords);
   PVB_LAUNCH(voxelize_coords_kernel, b, 512, 0, stream, n, r, normalize, eps, coords, norm_coords, vox_coords);
+  return 0;
+}
+
+int pvcnn_voxelize_denom(int b, int n, float eps, const float *coords, const float *mean, float *denom, void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && coords && mean && denom);
+  PVB_LAUNCH(voxelize_denom_kernel, b, 512, 0, stream, n, eps, coords, mean, denom);
+  return 0;
+}
+
+int pvcnn_voxelize_apply(int b, int n, int r, int normalize, const float *coords, const float *mean,
+                         const float *denom, float *norm_coords, int *vox_coords, void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && r > 0 && coords && mean && (denom || !normalize) && norm_coords && vox_coords);
+  const long long total = (long long)b * 3 * n;
+  long long grid = (total + 255) / 256;
+  if (grid > pvb::kNumSMs * 8) grid = pvb::kNumSMs * 8;
+  PVB_LAUNCH(voxelize_apply_kernel, (int)grid, 256, 0, stream, n, r, normalize, total, coords, mean, denom, norm_coords,
+             vox_coords);
   return 0;
 }
 

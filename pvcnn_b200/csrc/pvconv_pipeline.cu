@@ -18,6 +18,7 @@ int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, c
                  const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out);
 
 bool conv_halo_supported(int sx, int sy, int sz, int cout);  // conv_halo.cu
+int conv_halo_ty(int sz);                                    // conv_halo.cu
 
 // `lo` GRID tensors (x - trunc_tf32(x)) are materialised in 3xTF32 mode: the wgrad kernel is shared-memory-bandwidth
 // bound and runs 1.6x faster when it TMA-loads lo instead of converting it in the kernel; the v1 conv kernel
@@ -42,7 +43,7 @@ struct SparseBuf {
 static inline long long up4(long long x) { return (x + 3) / 4 * 4; }
 static SparseBuf sparse_at(int *base, int b, int r, int co) {
   SparseBuf v{};
-  v.ty = 128 / r > 0 ? 128 / r : 1;
+  v.ty = conv_halo_ty(r);            // y rows per halo-conv tile (conv_halo.cu)
   v.wg_bz = ((r < 32 ? r : 32) + 7) / 8 * 8;   // must mirror conv_wgrad.cu's k-tile box
   v.wg_by = 32 / v.wg_bz > 0 ? 32 / v.wg_bz : 1;
   if (v.wg_by > r) v.wg_by = r;
@@ -176,7 +177,13 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   int nblk = 0;
 
   // 1. coordinates -> voxel indices                               (modules/voxelization.py:17-24, vox.cu:18-34)
-  PVB_TRY(pvcnn_voxelize_coords(b, n, r, d->normalize, d->eps, coords, ws->nc, ws->vc, stream));
+  if (d->vox_stats >= 1) {  // reference-exact: the mean is torch's own reduction result
+    PVB_CHECK_ARG(ws->vox_mean && (ws->vox_denom || !d->normalize));
+    if (d->normalize && d->vox_stats == 1) PVB_TRY(pvcnn_voxelize_denom(b, n, d->eps, coords, ws->vox_mean, ws->vox_denom, stream));
+    PVB_TRY(pvcnn_voxelize_apply(b, n, r, d->normalize, coords, ws->vox_mean, ws->vox_denom, ws->nc, ws->vc, stream));
+  } else {
+    PVB_TRY(pvcnn_voxelize_coords(b, n, r, d->normalize, d->eps, coords, ws->nc, ws->vc, stream));
+  }
   PVB_TRY(launch_vox_index_count(b, n, r, ws->vc, ws->ind, ws->cnt, s));
   const bool sparse = sparse_enabled(d) && ws->sparse != nullptr;
   SparseBuf sp{};

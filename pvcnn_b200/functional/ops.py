@@ -1,6 +1,8 @@
 """autograd.Function wrappers -- same contracts as the reference's
 modules/functional/{voxelization,devoxelization,ball_query,grouping,sampling,interpolatation}.py."""
 import numpy as np
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -191,12 +193,45 @@ class _NeighborInterpolate(Function):
 nearest_neighbor_interpolate = _NeighborInterpolate.apply
 
 
+def vox_stats_mode():
+    """PVCNN_B200_VOX = exact (default) | aten | fused.
+    exact: per-cloud mean by the reference's own ATen call (coords.mean(2), modules/voxelization.py:18), the
+           max-norm and the element-wise tail in our kernels (bit-identical to the reference's op sequence);
+    aten:  mean AND denominator by the reference's ATen calls (:18-20), element-wise tail in our kernel;
+    fused: single kernel with an fp64 mean (differs from torch's reduction by an ulp on rare .5 ties)."""
+    m = os.environ.get("PVCNN_B200_VOX", "exact").lower()
+    return m if m in ("exact", "aten", "fused") else "exact"
+
+
+def voxel_stats(coords, normalize, eps, mode=None):
+    """(vox_stats flag, mean [B,3], denom [B] or None) for pvcnn_voxelize_* / the fused block."""
+    mode = mode or vox_stats_mode()
+    if mode == "fused":
+        return 0, None, None
+    mean = coords.mean(2, keepdim=True)                                     # modules/voxelization.py:18
+    if not normalize:
+        return 1, mean.reshape(-1, 3).contiguous(), None
+    if mode == "aten":
+        nc = coords - mean
+        denom = nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps   # :20
+        return 2, mean.reshape(-1, 3).contiguous(), denom.reshape(-1).contiguous()
+    denom = torch.empty(coords.shape[0], dtype=torch.float32, device=coords.device)
+    return 1, mean.reshape(-1, 3).contiguous(), denom
+
+
 def voxelize_coords(coords, resolution, normalize=True, eps=0.0):
-    """Fused replacement for the tensor ops of modules/voxelization.py:17-24: returns
-    (norm_coords float [B,3,N] clamped to [0,r-1], vox_coords int32 [B,3,N])."""
+    """Replacement for the tensor ops of modules/voxelization.py:17-24: returns
+    (norm_coords float [B,3,N] clamped to [0,r-1], vox_coords int32 [B,3,N]); bit-identical to the reference's
+    op sequence on the same device (see vox_stats_mode)."""
     coords = coords.detach().contiguous().float()
     b, _, n = coords.shape
     nc = torch.empty_like(coords)
     vc = torch.empty(coords.shape, dtype=torch.int32, device=coords.device)
-    _lib.call("pvcnn_voxelize_coords", b, n, int(resolution), bool(normalize), float(eps), coords, nc, vc)
+    flag, mean, denom = voxel_stats(coords, normalize, eps)
+    if flag == 0:
+        _lib.call("pvcnn_voxelize_coords", b, n, int(resolution), bool(normalize), float(eps), coords, nc, vc)
+        return nc, vc
+    if normalize and flag == 1:
+        _lib.call("pvcnn_voxelize_denom", b, n, float(eps), coords, mean, denom)
+    _lib.call("pvcnn_voxelize_apply", b, n, int(resolution), bool(normalize), coords, mean, denom, nc, vc)
     return nc, vc

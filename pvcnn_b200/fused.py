@@ -22,7 +22,7 @@ class Desc(ctypes.Structure):
                 ("r", ctypes.c_int), ("normalize", ctypes.c_int), ("eps", ctypes.c_float),
                 ("training", ctypes.c_int), ("npass", ctypes.c_int), ("bn_eps_vox", ctypes.c_float),
                 ("bn_eps_pt", ctypes.c_float), ("momentum", ctypes.c_float), ("slope", ctypes.c_float),
-                ("with_se", ctypes.c_int)]
+                ("with_se", ctypes.c_int), ("vox_stats", ctypes.c_int)]
 
 
 _PARAM_FIELDS = ["w1", "b1", "g1", "be1", "rm1", "rv1", "w2", "b2", "g2", "be2", "rm2", "rv2",
@@ -31,7 +31,8 @@ _GRAD_FIELDS = ["w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "wp", "bp", "g
 _WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("fcl_lo", _F), ("g0", _F),
               ("g0_lo", _F), ("y1", _F), ("z1", _F), ("z1_lo", _F), ("y2", _F), ("p", _F), ("coef", _F),
               ("wprep", _F), ("partials", _F), ("sums", _F), ("ga", _F), ("gpp", _F), ("gpp_lo", _F),
-              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("sparse", _I), ("se", _F)]
+              ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("sparse", _I), ("se", _F),
+              ("vox_mean", _F), ("vox_denom", _F)]
 
 
 class Params(ctypes.Structure):
@@ -166,14 +167,18 @@ class _PVConvFused(Function):
         training = bool(module.training)
         vox = module.voxelization
         desc = Desc(b, n, cin, module.out_channels, int(module.resolution), int(bool(vox.normalize)), float(vox.eps),
-                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1, int(se_w1 is not None))
+                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1, int(se_w1 is not None), 0)
         bns = [module.voxel_layers[1], module.voxel_layers[4], module.point_features.layers[1]]
         desc.bn_eps_vox = float(bns[0].eps)
         desc.bn_eps_pt = float(bns[2].eps)
         desc.momentum = float(bns[0].momentum if bns[0].momentum is not None else 0.1)
         desc.slope = float(module.voxel_layers[2].negative_slope)
         # need_bwd is decided by the caller: grad mode is always off inside Function.forward
+        # per-cloud coordinate mean from the reference's own ATen reduction (bit-exact voxel indices)
+        from .functional.ops import voxel_stats
+        desc.vox_stats, vmean, vdenom = voxel_stats(coords, bool(vox.normalize), float(vox.eps))
         plan = _Plan(desc, dev, bool(need_bwd) and training)
+        plan.t["vox_mean"], plan.t["vox_denom"] = vmean, vdenom
         prm = Params()
         vals = dict(w1=w1, b1=b1, g1=g1, be1=be1, rm1=bns[0].running_mean, rv1=bns[0].running_var,
                     w2=w2, b2=b2, g2=g2, be2=be2, rm2=bns[1].running_mean, rv2=bns[1].running_var,

@@ -56,7 +56,8 @@ def test_hw_rounding_probe(capsys):
 
 @pytest.mark.parametrize("npass,tol", [(1, 3e-3), (3, 1e-5)])
 @pytest.mark.parametrize("b,r,cin,cout", [(2, 8, 16, 16), (1, 16, 64, 64), (2, 32, 64, 64), (1, 12, 64, 128),
-                                          (1, 16, 9, 64), (1, 8, 128, 256)])
+                                          (1, 16, 9, 64), (1, 8, 128, 256), (2, 12, 4, 64), (1, 16, 128, 128),
+                                          (1, 8, 256, 256), (1, 32, 32, 48), (1, 12, 64, 64), (1, 20, 24, 40)])
 def test_conv3d_forward(npass, tol, b, r, cin, cout):
     torch.manual_seed(2)
     cp = (cin + 3) // 4 * 4
@@ -72,7 +73,8 @@ def test_conv3d_forward(npass, tol, b, r, cin, cout):
     assert relerr(got, ref) < tol
 
 
-@pytest.mark.parametrize("b,r,cin,cout", [(1, 8, 16, 32), (1, 16, 64, 64)])
+@pytest.mark.parametrize("b,r,cin,cout", [(1, 8, 16, 32), (1, 16, 64, 64), (1, 12, 64, 128), (1, 8, 256, 256),
+                                          (2, 32, 9, 64)])
 def test_conv3d_dgrad(b, r, cin, cout):
     torch.manual_seed(3)
     x = torch.randn(b, cin, r, r, r, dtype=torch.float64, requires_grad=True)
@@ -115,7 +117,7 @@ def test_conv_linearity_full_size():
 
 @pytest.mark.parametrize("npass,tol", [(1, 3e-3), (3, 2e-5)])
 @pytest.mark.parametrize("b,r,cin,cout", [(1, 8, 16, 16), (2, 16, 64, 64), (1, 12, 64, 128), (1, 16, 9, 64),
-                                          (4, 32, 64, 64)])
+                                          (4, 32, 64, 64), (2, 8, 256, 256), (1, 8, 128, 192)])
 def test_conv3d_wgrad(npass, tol, b, r, cin, cout):
     torch.manual_seed(5)
     x = torch.randn(b, cin, r, r, r, device="cuda")
@@ -134,7 +136,8 @@ def test_conv3d_wgrad(npass, tol, b, r, cin, cout):
     assert relerr(dw.cpu(), ref) < tol
 
 
-@pytest.mark.parametrize("m,cin,cout", [(4096, 64, 64), (65536, 64, 64), (2048, 16, 32), (5000, 9, 64)])
+@pytest.mark.parametrize("m,cin,cout", [(4096, 64, 64), (65536, 64, 64), (2048, 16, 32), (5000, 9, 64), (4096, 1472, 512),
+                                        (3000, 128, 1024)])
 def test_pointwise_wgrad(m, cin, cout):
     torch.manual_seed(6)
     cp = (cin + 3) // 4 * 4

@@ -26,15 +26,46 @@ def npy(t):
 COORD_GENS = {"s3dis": s3dis_like_coords, "surface": surface_coords, "degenerate": degenerate_coords}
 
 
-@pytest.mark.parametrize("b,n,r,normalize,eps", [(2, 1024, 8, True, 0.0), (16, 4096, 32, True, 0.0),
-                                                 (3, 777, 12, False, 0.0), (4, 2048, 16, True, 1e-15)])
-def test_voxelize_coords(b, n, r, normalize, eps):
+VOX_CASES = [(2, 1024, 8, True, 0.0), (16, 4096, 32, True, 0.0), (3, 777, 12, False, 0.0), (4, 2048, 16, True, 1e-15),
+             (32, 1024, 12, True, 0.0), (8, 8192, 32, True, 0.0), (5, 999, 12, True, 0.0)]
+
+
+@pytest.mark.parametrize("mode", ["exact", "aten"])
+@pytest.mark.parametrize("b,n,r,normalize,eps", VOX_CASES)
+def test_voxelize_coords_bit_exact_vs_reference_program(mode, b, n, r, normalize, eps, monkeypatch):
+    """North-star: integer voxel indices bit-exact with the reference.  Compared with the LITERAL tensor program of
+    modules/voxelization.py:17-24 run by torch on the same GPU (cfg 1, the metric config, R=12 cases)."""
+    from util import reference_voxelization
+    monkeypatch.setenv("PVCNN_B200_VOX", mode)
+    g = rng(10)
+    for dist in ("s3dis", "surface"):
+        c = COORD_GENS[dist](g, b, n) - (0.4 if not normalize else 0.0)
+        ct = cu(c)
+        nc_ref, vc_ref = reference_voxelization(ct, r, normalize, eps)
+        nc, vc = F.voxelize_coords(ct, r, normalize, eps)
+        assert torch.equal(vc, vc_ref)
+        assert torch.equal(nc, nc_ref)
+
+
+@pytest.mark.parametrize("b,n,r,normalize,eps", VOX_CASES[:4])
+def test_voxelize_coords_vs_oracle(b, n, r, normalize, eps):
+    from util import device_mean
     g = rng(10)
     c = s3dis_like_coords(g, b, n) - (0.4 if not normalize else 0.0)
-    nc0, vc0 = oracle.voxelize_coords(c, r, normalize, eps)
+    nc0, vc0 = oracle.voxelize_coords(c, r, normalize, eps, mean=device_mean(c))
     nc, vc = F.voxelize_coords(cu(c), r, normalize, eps)
     assert np.array_equal(npy(vc), vc0)          # integer voxel indices: bit-exact
     assert np.array_equal(npy(nc), nc0)          # same arithmetic -> identical floats
+
+
+def test_voxelize_coords_fused_variant(monkeypatch):
+    """PVCNN_B200_VOX=fused: single kernel, fp64 mean (round-1 definition) == oracle's mean="fp64"."""
+    monkeypatch.setenv("PVCNN_B200_VOX", "fused")
+    g = rng(10)
+    c = s3dis_like_coords(g, 4, 2048)
+    nc0, vc0 = oracle.voxelize_coords(c, 16, True, 0.0, mean="fp64")
+    nc, vc = F.voxelize_coords(cu(c), 16, True, 0.0)
+    assert np.array_equal(npy(vc), vc0) and np.array_equal(npy(nc), nc0)
 
 
 @pytest.mark.parametrize("dist", ["s3dis", "surface", "degenerate"])

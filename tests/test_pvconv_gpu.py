@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle
-from util import rng, s3dis_like_coords, rel_err
+from util import rng, s3dis_like_coords, rel_err, device_mean
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,8 @@ def run_oracle(m, f, co, go, r, training=True, dtype="float32", **kw):
     params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()
               if "running" not in k and "num_batches" not in k}
     buffers = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items() if "running" in k}
+    # the per-cloud mean is the reference's own torch reduction ON THE DEVICE UNDER TEST (modules/voxelization.py:18)
+    kw.setdefault("vox_mean", device_mean(co))
     # small problems: a handful of threads beats oversubscribing every host core
     return oracle.pvconv_forward_backward(params, f, co, go, r, training=training, dtype=dtype,
                                           buffers=None if training else buffers, threads=16, **kw)

@@ -38,3 +38,26 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def device_mean(coords):
+    """`coords.mean(2, keepdim=True)` (modules/voxelization.py:18) evaluated by torch on the device under test -> [B,3].
+    The summation order of that reduction belongs to torch; oracle and product both take its result."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float32))
+    if torch.cuda.is_available():
+        t = t.cuda()
+    return t.mean(2, keepdim=True).cpu().numpy().reshape(-1, 3)
+
+
+def reference_voxelization(coords_t, r, normalize=True, eps=0.0):
+    """The literal tensor program of modules/voxelization.py:17-24 on whatever device `coords_t` lives."""
+    import torch
+    coords_t = coords_t.detach()
+    norm_coords = coords_t - coords_t.mean(2, keepdim=True)
+    if normalize:
+        norm_coords = norm_coords / (norm_coords.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps) + 0.5
+    else:
+        norm_coords = (norm_coords + 1) / 2.0
+    norm_coords = torch.clamp(norm_coords * r, 0, r - 1)
+    return norm_coords, torch.round(norm_coords).to(torch.int32)
