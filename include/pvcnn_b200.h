@@ -244,6 +244,45 @@ PVCNN_API int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *gra
                                     const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws,
                                     float *grad_features, const pvcnn_pvconv_grads *grads, void *stream);
 
+/* =====================================================================================================
+ * SharedMLP on the tensor-core path: replaces nn.Conv1d/Conv2d(k=1) + nn.BatchNorm1d/2d + nn.ReLU of
+ * modules/shared_mlp.py:6-33 (cuDNN + ATen in the reference) layer by layer, on channels-last rows
+ * [rows, pad4(C)] (rows = B*N for dim=1, B*M*U for dim=2).  See pvcnn_b200/csrc/mlp_pipeline.cu.
+ * ===================================================================================================== */
+/* layout converters at the module boundary: [b,c,n] <-> [b*n, pad4(c)] (xcl_lo = x - trunc_tf32(x), may be NULL) */
+PVCNN_API int pvcnn_points_to_cl(int b, int c, int n, const float *x, float *xcl, float *xcl_lo, void *stream);
+PVCNN_API int pvcnn_cl_to_points(int b, int c, int n, const float *xcl, float *x, void *stream);
+/* workspace sizes (floats) and the row-segment count of the pooled variant */
+PVCNN_API long long pvcnn_mlp_partials_floats(int cout);
+PVCNN_API long long pvcnn_mlp_wprep_floats(int cin, int cout);
+PVCNN_API int pvcnn_mlp_pool_segments(long long groups, int u);
+/* one layer forward: y = x W^T + bias (saved), BatchNorm (batch statistics + running update when training, running
+ * statistics otherwise; coef[4*pad4(cout)] = mean, invstd, scale, shift), then either z (+ z_lo) = relu(bn(y)) or, with
+ * pool_u > 0, pooled/argmax [rows/pool_u, pad4(cout)] = max over groups of pool_u consecutive rows
+ * (modules/pointnet.py:87 `.max(dim=-1).values`); pool_tmp: 2*segments*(rows/pool_u)*pad4(cout) floats if segments > 1 */
+PVCNN_API int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int npass, float bn_eps,
+                                      float momentum, const float *x, const float *x_lo, const float *w,
+                                      const float *bias, const float *gamma, const float *beta, float *running_mean,
+                                      float *running_var, float *wprep, float *partials, float *coef, float *y, float *z,
+                                      float *z_lo, int pool_u, float *pooled, int *argmax, float *pool_tmp, void *stream);
+/* dense gradient gz [groups*u, pad4(cout)] of a pooled output */
+PVCNN_API int pvcnn_mlp_pool_backward(long long groups, int u, int cout, const float *gpool, const int *argmax,
+                                      float *gz, void *stream);
+/* one layer backward: gz = d relu(bn(y)); writes dgamma/dbeta/dbias [cout], dw [cout,cin], gx [rows,pad4(cin)] (NULL to
+ * skip); gy (+gy_lo) [rows,pad4(cout)] and sums [4*pad4(cout)] are scratch */
+PVCNN_API int pvcnn_mlp_layer_backward(long long rows, int cin, int cout, int npass, const float *gz, const float *x,
+                                       const float *x_lo, const float *w, const float *y, const float *coef,
+                                       float *wprep, float *partials, float *sums, float *gy, float *gy_lo, float *gx,
+                                       float *dw, float *dbias, float *dgamma, float *dbeta, void *stream);
+/* modules/ball_query.py:16-30 (grouping + centre subtraction + concat) with channels-last output rows
+ * [b*m*u, pad4(3+c)] feeding pvcnn_mlp_layer_forward directly: the reference's [B,3+C,M,U] is never materialised */
+PVCNN_API int pvcnn_group_concat_cl(int b, int c, int n, int m, int u, const float *points_coords,
+                                    const float *centers_coords, const float *features, const int *indices,
+                                    float *out, float *out_lo, void *stream);
+PVCNN_API int pvcnn_group_concat_cl_grad(int b, int c, int n, int m, int u, const float *grad_rows, const int *indices,
+                                         float *grad_features, float *grad_points_coords, float *grad_centers_coords,
+                                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,7 @@ __device__ __forceinline__ void h3_decode(const Halo3Params &p, int unit, int &x
   }
 }
 
+template <int ORDER>
 __global__ void __launch_bounds__(H3_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w_hi,
                      const __grid_constant__ CUtensorMap map_w_lo, const Halo3Params p) {
@@ -187,21 +188,22 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
               tc_fence_after();
               const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
               const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
+              // Issue order inside a tap: consecutive MMAs into the SAME accumulator serialise on the accumulate
+              // dependency, so the two tiles' chains are interleaved (ORDER 1: k-step outer, tile inner).
 #pragma unroll
-              for (int t = 0; t < H3_TX; ++t) {
+              for (int i = 0; i < H3_TX * (H3_KC / 8); ++i) {
+                const int t = ORDER == 1 ? (i % H3_TX) : (i / (H3_KC / 8));
+                const int ks = ORDER == 1 ? (i / H3_TX) : (i % (H3_KC / 8));
                 const uint32_t d = tmem_base + (uint32_t)(t * 3 + dz) * bn;
-#pragma unroll
-                for (int ks = 0; ks < H3_KC / 8; ++ks) {
-                  const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
-                  const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;    // every chunk starts a fresh chain
-                  if (three) {
-                    // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
-                    mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                    mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_lo + ks * 2u, dhi, idesc, 1u);
-                    mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
-                  } else {
-                    mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                  }
+                const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
+                const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;    // every chunk starts a fresh chain
+                if (three) {
+                  // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
+                  mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                  mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_lo + ks * 2u, dhi, idesc, 1u);
+                  mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
+                } else {
+                  mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
                 }
               }
               mma_commit(&b_empty[bst]);
@@ -425,9 +427,16 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
     if (rc) return rc;
   }
   const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024;
-  PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(kNumSMs, p.num_units * p.nblocks);
-  PVB_LAUNCH(conv_halo_kernel, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+  int order = 1;
+  { const char *e = getenv("PVCNN_HALO_ORDER"); if (e && (e[0] == '0' || e[0] == '1')) order = e[0] - '0'; }
+  if (order == 1) {
+    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(conv_halo_kernel<1>, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(conv_halo_kernel<0>, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+  }
   return 0;
 }
 

@@ -1,0 +1,265 @@
+"""Host side of the native SharedMLP (reference: modules/shared_mlp.py:6-33): every (1x1 conv, BatchNorm, ReLU) layer
+runs as one C-ABI call forward (pvcnn_mlp_layer_forward: tcgen05 GEMM + fused BN statistics / apply) and one backward
+(pvcnn_mlp_layer_backward), on channels-last rows.  torch is used for device memory and autograd plumbing only.
+
+Layouts: the module boundary keeps the reference's [B, C, N] / [B, C, M, U]; inside, activations are [rows, pad4(C)]
+with rows = B*N (or B*M*U).  `pool_u` folds the set-abstraction max over the U neighbours (modules/pointnet.py:87) into
+the last layer so the [B, C, M, U] activation is never written.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .fused import _scratch, precision_passes
+
+_LL = ctypes.c_longlong
+
+
+def _pad4(x):
+    return (x + 3) // 4 * 4
+
+
+def _lib_sizes():
+    lib = _lib.load()
+    lib.pvcnn_mlp_partials_floats.restype = ctypes.c_longlong
+    lib.pvcnn_mlp_wprep_floats.restype = ctypes.c_longlong
+    return lib
+
+
+class _ToCL(Function):
+    """[B, C, N] -> ([B*N, pad4(C)], lo) ; backward: channels-last gradient -> [B, C, N]."""
+
+    @staticmethod
+    def forward(ctx, x, want_lo):
+        x = x.contiguous().float()
+        b, c, n = x.shape
+        cp = _pad4(c)
+        xcl = torch.empty((b * n, cp), dtype=torch.float32, device=x.device)
+        lo = torch.empty_like(xcl) if want_lo else None
+        _lib.call("pvcnn_points_to_cl", b, c, n, x, xcl, lo)
+        ctx.shape = (b, c, n)
+        if lo is None:
+            lo = xcl.new_empty(0)
+        ctx.mark_non_differentiable(lo)
+        return xcl, lo
+
+    @staticmethod
+    def backward(ctx, g, _glo):
+        b, c, n = ctx.shape
+        out = torch.empty((b, c, n), dtype=torch.float32, device=g.device)
+        _lib.call("pvcnn_cl_to_points", b, c, n, g.contiguous(), out)
+        return out, None
+
+
+class _FromCL(Function):
+    """[B*N, pad4(C)] -> [B, C, N]."""
+
+    @staticmethod
+    def forward(ctx, xcl, b, c, n):
+        out = torch.empty((b, c, n), dtype=torch.float32, device=xcl.device)
+        _lib.call("pvcnn_cl_to_points", b, c, n, xcl.contiguous(), out)
+        ctx.shape = (b, c, n)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, n = ctx.shape
+        gcl = torch.empty((b * n, _pad4(c)), dtype=torch.float32, device=g.device)
+        _lib.call("pvcnn_points_to_cl", b, c, n, g.contiguous().float(), gcl, None)
+        return gcl, None, None, None
+
+
+class _MLP(Function):
+    """x_cl [rows, pad4(cin)] -> relu(bn(conv(.))) stack -> [rows, pad4(cout)]  (or [rows/pool_u, pad4(cout)])."""
+
+    @staticmethod
+    def forward(ctx, x_cl, x_lo, meta, *params):
+        lib = _lib_sizes()
+        dev = x_cl.device
+        rows = x_cl.shape[0]
+        npass, training, pool_u = meta["npass"], meta["training"], meta["pool_u"]
+        widths, bns = meta["widths"], meta["bns"]
+        cin = meta["cin"]
+        saved = []
+        x, xl = x_cl, (x_lo if npass > 1 else None)
+        out = None
+        nl = len(widths)
+        for li, cout in enumerate(widths):
+            w, bias, gamma, beta = params[4 * li:4 * li + 4]
+            bn = bns[li]
+            co = _pad4(cout)
+            last = li == nl - 1
+            pool = pool_u if (last and pool_u) else 0
+            keep = meta["need_bwd"]
+            alloc = (lambda *s, dtype=torch.float32: torch.empty(s, dtype=dtype, device=dev))
+            y = alloc(rows, co) if keep else _scratch("mlp_y%d" % (li & 1), rows * co, dev).view(-1)[:rows * co].view(rows, co)
+            coef = alloc(4 * co)
+            wprep = _scratch("mlp_wprep", lib.pvcnn_mlp_wprep_floats(cin, cout), dev)
+            partials = _scratch("mlp_partials", lib.pvcnn_mlp_partials_floats(cout), dev)
+            z = zl = pooled = argmax = tmp = None
+            if pool:
+                groups = rows // pool
+                pooled = alloc(groups, co)
+                argmax = alloc(groups, co, dtype=torch.int32)
+                segs = lib.pvcnn_mlp_pool_segments(_LL(groups), pool)
+                if segs > 1:
+                    tmp = _scratch("mlp_pooltmp", 2 * groups * segs * co, dev)
+            else:
+                z = alloc(rows, co)
+                zl = alloc(rows, co) if (npass > 1 and not last) else None
+            _lib.call("pvcnn_mlp_layer_forward", _LL(rows), cin, cout, int(training), npass, float(bn.eps),
+                      float(bn.momentum if bn.momentum is not None else 0.1), x, xl, w.detach(),
+                      None if bias is None else bias.detach(), gamma.detach(), beta.detach(),
+                      bn.running_mean if (bn.track_running_stats and bn.running_mean is not None) else None,
+                      bn.running_var if (bn.track_running_stats and bn.running_var is not None) else None,
+                      wprep, partials, coef, y, z, zl, pool, pooled, argmax, tmp, device=dev)
+            if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            if keep:
+                saved.append((x, xl, y, coef, argmax))
+            out = pooled if pool else z
+            x, xl, cin = z, zl, cout
+        ctx.saved = saved
+        ctx.meta = dict(meta, rows=rows)
+        ctx.params = [None if p is None else p.detach() for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        meta = ctx.meta
+        if not meta["need_bwd"]:
+            raise RuntimeError("SharedMLP forward ran without saving activations (no_grad / eval); cannot run backward")
+        lib = _lib_sizes()
+        dev = g.device
+        rows, npass, pool_u, widths = meta["rows"], meta["npass"], meta["pool_u"], meta["widths"]
+        cins = [meta["cin"]] + list(widths[:-1])
+        grads = [None] * len(ctx.params)
+        g = g.contiguous().float()
+        nl = len(widths)
+        for li in range(nl - 1, -1, -1):
+            cin, cout = cins[li], widths[li]
+            ci, co = _pad4(cin), _pad4(cout)
+            x, xl, y, coef, argmax = ctx.saved[li]
+            w = ctx.params[4 * li]
+            if li == nl - 1 and pool_u:
+                gz = _scratch("mlp_gz_pool", rows * co, dev)
+                _lib.call("pvcnn_mlp_pool_backward", _LL(rows // pool_u), pool_u, cout, g, argmax, gz, device=dev)
+                g = gz
+            gy = _scratch("mlp_gy", rows * co, dev)
+            gyl = _scratch("mlp_gy_lo", rows * co, dev) if npass > 1 else None
+            need_gx = li > 0 or meta["need_input_grad"]
+            gx = torch.empty((rows, ci), dtype=torch.float32, device=dev) if need_gx else None
+            dw = torch.empty_like(w)
+            dbias = torch.empty(cout, dtype=torch.float32, device=dev)
+            dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+            wprep = _scratch("mlp_wprep", lib.pvcnn_mlp_wprep_floats(cin, cout), dev)
+            partials = _scratch("mlp_partials", lib.pvcnn_mlp_partials_floats(cout), dev)
+            sums = _scratch("mlp_sums", 4 * co, dev)
+            _lib.call("pvcnn_mlp_layer_backward", _LL(rows), cin, cout, npass, g, x, xl, w, y, coef, wprep, partials,
+                      sums, gy, gyl, gx, dw, dbias, dgamma, dbeta, device=dev)
+            grads[4 * li] = dw
+            grads[4 * li + 1] = dbias if ctx.params[4 * li + 1] is not None else None
+            grads[4 * li + 2] = dgamma
+            grads[4 * li + 3] = dbeta
+            g = gx
+        return (g, None, None, *grads)
+
+
+def native_supported(layers):
+    """True when `layers` is the reference's (conv k=1, BatchNorm, ReLU)* stack with what the kernels assume."""
+    mods = list(layers)
+    if len(mods) == 0 or len(mods) % 3 != 0:
+        return False
+    for i in range(0, len(mods), 3):
+        conv, bn, act = mods[i:i + 3]
+        if not isinstance(conv, (torch.nn.Conv1d, torch.nn.Conv2d)) or not isinstance(bn, torch.nn.modules.batchnorm._BatchNorm):
+            return False
+        if any(k != 1 for k in conv.kernel_size) or any(s != 1 for s in conv.stride) or conv.groups != 1:
+            return False
+        if any(p != 0 for p in conv.padding) or conv.padding_mode != "zeros":
+            return False
+        if not bn.affine or not bn.track_running_stats or bn.momentum is None or not isinstance(act, torch.nn.ReLU):
+            return False
+        if conv.out_channels > 1024 or conv.weight.dtype != torch.float32:
+            return False
+    return True
+
+
+def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True):
+    """Run the (conv, bn, relu)* stack `layers` on channels-last rows.  Returns [rows, pad4(cout)] (or pooled)."""
+    mods = list(layers)
+    convs, bns = mods[0::3], mods[1::3]
+    params = []
+    for conv, bn in zip(convs, bns):
+        params += [conv.weight, conv.bias, bn.weight, bn.bias]
+    training = bool(bns[0].training)
+    need_bwd = training and torch.is_grad_enabled() and (
+        (input_needs_grad and x_cl.requires_grad) or any(p is not None and p.requires_grad for p in params))
+    meta = dict(npass=precision_passes(), training=training, pool_u=int(pool_u), widths=[c.out_channels for c in convs],
+                bns=bns, cin=convs[0].in_channels, need_bwd=bool(need_bwd),
+                need_input_grad=bool(input_needs_grad and x_cl.requires_grad))
+    return _MLP.apply(x_cl, x_lo, meta, *params)
+
+
+def shared_mlp_forward(layers, x):
+    """x [B, C, *spatial] -> [B, Cout, *spatial] through the native path."""
+    b, c = x.shape[:2]
+    spatial = tuple(x.shape[2:])
+    n = 1
+    for s in spatial:
+        n *= s
+    x_cl, x_lo = _ToCL.apply(x.reshape(b, c, n), precision_passes() > 1)
+    z = mlp_cl(layers, x_cl, x_lo if x_lo.numel() else None)
+    cout = list(layers)[-3].out_channels
+    return _FromCL.apply(z, b, cout, n).view(b, cout, *spatial)
+
+
+class _GroupConcatCL(Function):
+    """modules/ball_query.py:16-30 with channels-last output rows (b, m, u) x pad4(3 + C)  (+ lo)."""
+
+    @staticmethod
+    def forward(ctx, points_coords, centers_coords, features, indices, want_lo):
+        points_coords = points_coords.contiguous().float()
+        centers_coords = centers_coords.contiguous().float()
+        features = None if features is None else features.contiguous().float()
+        indices = indices.int().contiguous()
+        b, _, n = points_coords.shape
+        _, m, u = indices.shape
+        c = 0 if features is None else features.shape[1]
+        cp = _pad4(3 + c)
+        out = torch.empty((b * m * u, cp), dtype=torch.float32, device=points_coords.device)
+        lo = torch.empty_like(out) if want_lo else None
+        _lib.call("pvcnn_group_concat_cl", b, c, n, m, u, points_coords, centers_coords, features, indices, out, lo)
+        ctx.save_for_backward(indices)
+        ctx.dims = (b, c, n, m, u)
+        if lo is None:
+            lo = out.new_empty(0)
+        ctx.mark_non_differentiable(lo)
+        return out, lo
+
+    @staticmethod
+    def backward(ctx, g, _glo):
+        (indices,) = ctx.saved_tensors
+        b, c, n, m, u = ctx.dims
+        dev = g.device
+        need_p, need_c, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and c > 0
+        gf = torch.empty((b, c, n), dtype=torch.float32, device=dev) if need_f else None
+        gp = torch.empty((b, 3, n), dtype=torch.float32, device=dev) if need_p else None
+        gc = torch.empty((b, 3, m), dtype=torch.float32, device=dev) if need_c else None
+        if need_f or need_p or need_c:
+            _lib.call("pvcnn_group_concat_cl_grad", b, c, n, m, u, g.contiguous(), indices, gf, gp, gc)
+        return gp, gc, gf, None, None
+
+
+def sa_branch(layers, coords, centers, features, indices):
+    """PointNet++ set-abstraction branch (modules/pointnet.py:85-87) on the native path:
+    grouping -> channels-last rows -> tensor-core MLP -> max over the U neighbours -> [B, Cout, M]."""
+    b = coords.shape[0]
+    _, m, u = indices.shape
+    rows, lo = _GroupConcatCL.apply(coords, centers, features, indices, precision_passes() > 1)
+    pooled = mlp_cl(layers, rows, lo if lo.numel() else None, pool_u=u)
+    cout = list(layers)[-3].out_channels
+    return _FromCL.apply(pooled, b, cout, m)

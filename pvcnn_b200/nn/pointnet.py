@@ -57,10 +57,22 @@ class PointNetSAModule(nn.Module):
         self.num_centers = num_centers
         self.out_channels = sum(w[-1] for w in branches)
 
+    def _branch(self, grouper, mlp, coords, centers, features):
+        """One (BallQuery -> SharedMLP(dim=2) -> max over neighbours) branch.  On CUDA the grouping writes channels-last
+        rows that feed the tensor-core MLP directly and the max over U is folded into the last layer's BatchNorm pass:
+        neither the [B,C+3,M,U] input nor the [B,C',M,U] output of the reference is materialised."""
+        from .shared_mlp import native_mlp_enabled
+        if coords.is_cuda and native_mlp_enabled() and grouper.include_coordinates:
+            from .. import mlp as _mlp
+            if _mlp.native_supported(mlp.layers):
+                idx = F.ball_query(centers.contiguous(), coords.contiguous(), grouper.radius, grouper.num_neighbors)
+                return _mlp.sa_branch(mlp.layers, coords, centers, features, idx)
+        return mlp(grouper(coords, centers, features)).max(dim=-1).values
+
     def forward(self, inputs):
         features, coords = inputs
         centers = F.furthest_point_sample(coords, self.num_centers)
-        pooled = [mlp(g(coords, centers, features)).max(dim=-1).values for g, mlp in zip(self.groupers, self.mlps)]
+        pooled = [self._branch(g, mlp, coords, centers, features) for g, mlp in zip(self.groupers, self.mlps)]
         return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), centers
 
     def extra_repr(self):
