@@ -228,6 +228,33 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ---- the same step in the other precision / with activity skipping off (both must be driver-visible).
+    # PVCNN_B200_PRECISION and PVCNN_B200_SPARSE are read per call, so the modes run in this process on the same inputs.
+    modes = {}
+    if not minimal:
+        def timed(nsteps, nwarm):
+            for _ in range(nwarm):
+                step(feats, coords, gout)
+            barrier()
+            e0.record()
+            for _ in range(nsteps):
+                step(feats, coords, gout)
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1) / nsteps], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0])
+        other = "tf32" if args.precision == "fp32" else "fp32"
+        for name, prec, sparse in ((other, other, "1"), (args.precision + "_dense", args.precision, "0"),
+                                   (other + "_dense", other, "0")):
+            os.environ["PVCNN_B200_PRECISION"], os.environ["PVCNN_B200_SPARSE"] = prec, sparse
+            t_ms = timed(max(5, args.steps // 2), 3)
+            modes[name] = {"ms_per_step": t_ms, "value": world * bl * N / t_ms * 1e3, "unit": "points/s",
+                           "precision": prec, "activity_skipping": sparse == "1"}
+        os.environ["PVCNN_B200_PRECISION"] = args.precision
+        os.environ.pop("PVCNN_B200_SPARSE", None)
+
     extra = {}
     if rank == 0 and world == 1 and not minimal:
         extra = single_gpu_extras(torch, dev, m, args)
@@ -247,6 +274,7 @@ def run_ours(args):
             "e2e": {"value": world * bl * N / ms_e2e * 1e3, "unit": "points/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 4 * (2 * bl * C * N + bl * 3 * N), "d2h_bytes_per_step": 4 * 2 * bl * C * N},
             "gpu_launches": int(launches),
+            "modes": modes,
             "peaks": pk,
         }
         line.update(extra)
@@ -275,22 +303,42 @@ def single_gpu_extras(torch, dev, m, args):
     torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / reps
     achieved = CONV_FLOPS / k_ms / 1e9
-    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    tf32_peak = pk["bf16_tflops"] / 2.0   # kernel timed alone -> burst figure; kind::tf32 is the half-rate kind
+    traffic, traffic_src = None, None
+    try:  # dram bytes per launch of THIS tree's kernel, from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_conv_halo.json")))
+        ent = prof["npass%d" % npass]
+        traffic, traffic_src = ent["dram_bytes_read"] + ent["dram_bytes_write"], prof["source"]
+    except Exception:  # noqa: BLE001
+        pass
     extra["roofline"] = {
-        "kernel": "conv_halo_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32, smem halo reuse)", "bound": "tensor",
+        "kernel": "conv_halo_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32, one smem halo per channel chunk, "
+                  "z shift in the epilogue)", "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-        "traffic": 223.3e6 if npass == 3 else None, "kernel_ms": k_ms,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in profiles/r01_ncu_full_v2.md (135.3 MB + 88.0 MB; algorithmic in+out = 268 MB)",
-        "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of the kernel "
-                "run alone; executed tensor FLOPs are %dx that. peak = %s bf16_tflops_sustained / 2 (tf32 is the "
-                "half-rate kind; no direct tf32 measurement in MEASURED_PEAKS.json)" % (CONV_FLOPS / 1e9, npass,
-                                                                                       pk["source"]),
+        "traffic": traffic, "kernel_ms": k_ms, "traffic_source": traffic_src,
+        "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of a dense launch "
+                "run alone (random dense input); executed tensor FLOPs are %dx that. peak = %s bf16_tflops (burst) / 2: "
+                "MEASURED_PEAKS.json holds no direct tf32 measurement" % (CONV_FLOPS / 1e9, npass, pk["source"]),
     }
+    # the same kernel in the other precision (sub-result)
+    npass2 = 1 if npass == 3 else 3
+    for _ in range(3):
+        dense.igemm_conv(x_hi, x_lo, w_hi, w_lo, None, npass=npass2)
+    e0.record()
+    for _ in range(reps):
+        dense.igemm_conv(x_hi, x_lo, w_hi, w_lo, None, npass=npass2)
+    e1.record()
+    torch.cuda.synchronize()
+    k2 = e0.elapsed_time(e1) / reps
+    extra["roofline"]["other_precision"] = {"npass": npass2, "kernel_ms": k2, "achieved": CONV_FLOPS / k2 / 1e9,
+                                            "frac": CONV_FLOPS / k2 / 1e9 / tf32_peak}
     # GPU reference arm (reference CUDA ops + cuDNN), informational
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))  # checker-side tool: runs oracle/_ref (reference .so)
         import ref_gpu_time
         extra["reference_gpu"] = [ref_gpu_time.run(True, steps=10, warmup=5), ref_gpu_time.run(False, steps=5, warmup=2)]
+        extra["reference_gpu_note"] = ("the reference's own CUDA ops + cuDNN on this GPU, same inputs: [0] cuDNN default "
+                                       "(allow_tf32=True, what the reference runs), [1] allow_tf32=False (fp32-strict)")
     except Exception as e:  # noqa: BLE001
         extra["reference_gpu"] = {"unavailable": repr(e)[:200]}
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
@@ -340,11 +388,13 @@ def cpu_baseline(sample_batch=2, iters=2):
     # 4.2 s/step with 128 threads vs 0.16 s/step with 8 threads for the same sample).  So the thread count is tuned: one
     # timed pass per candidate, the fastest one is the baseline's configuration.
     oracle.pvconv_forward_backward(params, f, c, g, R, threads=min(_host_thread_candidates()))  # warm-up
+    warm = 1
     best = None
     for th in _host_thread_candidates():
         t0 = time.perf_counter()
         oracle.pvconv_forward_backward(params, f, c, g, R, threads=th)
         dt1 = time.perf_counter() - t0
+        warm += 1
         if best is None or dt1 < best[0]:
             best = (dt1, th)
     threads = best[1]
@@ -353,24 +403,31 @@ def cpu_baseline(sample_batch=2, iters=2):
         oracle.pvconv_forward_backward(params, f, c, g, R, threads=threads)
     dt = (time.perf_counter() - t0) / iters
     return {"value": sample_batch * N / dt, "unit": "points/s", "cores": threads, "kind": "port",
-            "ms_per_step": dt * 1e3,
-            "sample": "B=%d of the 16 clouds (N=4096, C=64, R=32), fwd+bwd, %d iterations after 1 warm-up; the "
-                      "reference has no CPU path, this is the oracle port (C kernels + torch CPU conv/BN)" %
-                      (sample_batch, iters)}
+            "ms_per_step": dt * 1e3, "iterations": iters, "warmup_passes": warm,
+            "sample": "B=%d of the 16 clouds (N=4096, C=64, R=32), fwd+bwd, %d timed iterations after %d untimed passes "
+                      "(1 warm-up + one per thread-count candidate); the reference has no CPU path, this is the oracle "
+                      "port (C kernels + torch CPU conv/BN)" % (sample_batch, iters, warm)}
 
 
 def run_reference(args):
+    """CPU arm: the oracle port on a bounded sample.  It runs (and REPORTS) its own iteration counts: at most 20 timed and
+    3 warm-up passes of a B=2 sample, whatever --steps / --warmup ask for (requested values are echoed in `config`)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     sample = 2
-    cb = cpu_baseline(sample_batch=sample, iters=max(1, min(args.steps, 3)))
+    iters = max(1, min(args.steps, 20))
+    cb = cpu_baseline(sample_batch=sample, iters=iters)
     ms = cb["ms_per_step"]
     line = {"impl": "reference", "metric": "PVConv fwd+bwd points/sec (B=16,N=4096,C=64,R=32)", "value": cb["value"],
-            "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "unit": "points/s", "n_gpus": args.gpus, "steps": iters, "warmup": cb["warmup_passes"], "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, bounded sample B=%d" % sample,
-                       "parallelism": "host threads"},
+            "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, bounded sample B=%d "
+                                   "(NOT the B=16 metric batch: same_config=false)" % sample,
+                       "parallelism": "host threads", "same_config": False, "sample_batch": sample,
+                       "requested_steps": args.steps, "requested_warmup": args.warmup,
+                       "what": "CPU oracle port (the reference has no CPU path); the reference's own CUDA+cuDNN path on "
+                               "the same GPU is the `reference_gpu` key of the --impl ours line"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -244,6 +244,14 @@ PVCNN_API int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *gra
                                     const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws,
                                     float *grad_features, const pvcnn_pvconv_grads *grads, void *stream);
 
+/* ---- device-side resampling of modules/functional/sampling.py:66-82 (`logits_mask`): the reference loops over the
+ *      batch on the host (mask[i].nonzero() sync, np.random.choice/shuffle).  mask: uint8/bool [b,n]; picks int32 [b,k]:
+ *      a uniform k-subset of the foreground indices in random order when there are >= k of them, otherwise every
+ *      foreground index k/nc times plus k%nc distinct extras, shuffled; all zeros when there is none.  Counter-based
+ *      generator keyed by `seed` (oracle: oracle.logits_mask_sample, bit-identical).  n, k <= 8192. */
+PVCNN_API int pvcnn_logits_mask_sample(int b, int n, int k, unsigned long long seed, const unsigned char *mask,
+                                       int *picks, void *stream);
+
 /* =====================================================================================================
  * SharedMLP on the tensor-core path: replaces nn.Conv1d/Conv2d(k=1) + nn.BatchNorm1d/2d + nn.ReLU of
  * modules/shared_mlp.py:6-33 (cuDNN + ATen in the reference) layer by layer, on channels-last rows

@@ -21,7 +21,7 @@ __all__ = [
     "build", "num_threads", "voxelize_coords", "avg_voxelize", "avg_voxelize_grad",
     "trilinear_devoxelize", "trilinear_devoxelize_grad", "ball_query", "grouping", "grouping_grad", "group_concat", "group_concat_grad",
     "gather", "gather_grad", "furthest_point_sampling", "three_nn", "three_nn_interpolate",
-    "three_nn_interpolate_grad", "pvconv_forward_backward",
+    "three_nn_interpolate_grad", "pvconv_forward_backward", "logits_mask_sample", "torch_mean",
 ]
 
 
@@ -219,6 +219,44 @@ def three_nn_interpolate_grad(grad_y, idx, w, m):
     gx = np.empty((b, c, m), np.float32)
     lib().oracle_three_nn_interpolate_grad(_ci(b), _ci(c), _ci(n), _ci(m), _p(grad_y), _p(idx), _p(w), _p(gx))
     return gx
+
+
+def _lm_mix(seed, b, stream, j):
+    """splitmix64 finaliser of (seed, sample, stream, index) -- the counter-based generator of pvcnn_logits_mask_sample"""
+    with np.errstate(over="ignore"):
+        x = (np.uint64(seed) ^ (np.uint64(b) * np.uint64(0x9E3779B97F4A7C15)) ^ (np.uint64(stream) * np.uint64(0xBF58476D1CE4E5B9))
+             ^ (np.asarray(j, dtype=np.uint64) * np.uint64(0x94D049BB133111EB)))
+        x = x ^ (x >> np.uint64(30)); x = x * np.uint64(0xBF58476D1CE4E5B9)
+        x = x ^ (x >> np.uint64(27)); x = x * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def logits_mask_sample(mask, k, seed):
+    """Restatement of the resampling of modules/functional/sampling.py:66-82 with the device generator instead of numpy's:
+    nc >= k: the k candidates with the smallest random keys (a uniform k-subset in random order, = np.random.choice(nc, k,
+    replace=False)); 0 < nc < k: arange(nc).repeat(k // nc) ++ (k % nc)-subset, shuffled by a second key stream; nc == 0:
+    zeros.  mask: bool [B,N] -> int32 [B,k]."""
+    mask = np.asarray(mask).astype(bool)
+    bsz, n = mask.shape
+    out = np.zeros((bsz, k), np.int32)
+    hi = np.uint64(0xFFFFFFFF00000000)
+    for b in range(bsz):
+        cand = np.nonzero(mask[b])[0].astype(np.int32)
+        nc = cand.size
+        if nc == 0:
+            continue
+        j = np.arange(nc, dtype=np.uint64)
+        order = np.argsort((_lm_mix(seed, b, 0, j) & hi) | j, kind="stable")
+        if nc >= k:
+            out[b] = cand[order[:k]]
+            continue
+        rep, rem = k // nc, k % nc
+        lst = np.concatenate([np.arange(nc).repeat(rep), order[:rem]]).astype(np.int64)
+        t = np.arange(k, dtype=np.uint64)
+        perm = np.argsort((_lm_mix(seed, b, 1, t) & hi) | t, kind="stable")
+        out[b] = cand[lst[perm]]
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

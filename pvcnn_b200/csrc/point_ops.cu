@@ -590,6 +590,114 @@ __global__ void __launch_bounds__(128) three_nn_interp_grad_kernel(int c, int n,
   }
 }
 
+
+// =====================================================================================
+// logits_mask resampling on the device (modules/functional/sampling.py:66-82).  The reference loops over the
+// batch on the host: mask[i].nonzero() (a device->host sync per sample), np.random.choice / shuffle, a copy
+// back.  Here one CTA per sample does: ordered compaction of the foreground candidates (block scan), a random
+// k-subset / repeat-fill + shuffle with a counter-based generator (splitmix64 of (seed, sample, stream, index)),
+// realised as bitonic sorts of 64-bit (random key, index) pairs in shared memory.  Same distribution as the
+// reference's numpy calls (uniform subsets / permutations); no host round trip.
+//   smem: keys[P] (uint64) + cand[n] (int) + extras[n] (int)
+// =====================================================================================
+__device__ __forceinline__ unsigned long long lm_mix(unsigned long long seed, unsigned long long b,
+                                                     unsigned long long stream, unsigned long long j) {
+  unsigned long long x = seed ^ (b * 0x9E3779B97F4A7C15ull) ^ (stream * 0xBF58476D1CE4E5B9ull) ^ (j * 0x94D049BB133111EBull);
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+
+__device__ void lm_bitonic_sort(unsigned long long *keys, int p2) {
+  for (int size = 2; size <= p2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));  // index of the lower element of pair t
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const unsigned long long a = keys[lo], c = keys[hi];
+        if ((a > c) == up) { keys[lo] = c; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) logits_mask_sample_kernel(int n, int k, unsigned long long seed,
+                                                                  const unsigned char *__restrict__ mask,
+                                                                  int *__restrict__ picks) {
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  __shared__ int warp_tot[32];
+  __shared__ int s_nc;
+  int p2max = 1;
+  while (p2max < max(n, k)) p2max <<= 1;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(lm_smem);
+  int *cand = reinterpret_cast<int *>(keys + p2max);
+  int *extras = cand + n;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned char *mk = mask + (size_t)b * n;
+  // ---- ordered compaction: thread t owns the contiguous chunk [t*per, (t+1)*per)
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int i0 = tid * per, i1 = min(n, i0 + per);
+  int local = 0;
+  for (int i = i0; i < i1; ++i) local += mk[i] != 0;
+  int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int w = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += w;
+    }
+    warp_tot[lane] = inc2 - v;  // exclusive warp offsets
+    if (lane == 31) s_nc = inc2;
+  }
+  __syncthreads();
+  int pos = warp_tot[warp] + incl - local;
+  for (int i = i0; i < i1; ++i)
+    if (mk[i]) cand[pos++] = i;
+  const int nc = s_nc;
+  __syncthreads();
+  int *out = picks + (size_t)b * k;
+  if (nc == 0) {  // sampling.py:66: selected_indices stays zero
+    for (int t = tid; t < k; t += blockDim.x) out[t] = 0;
+    return;
+  }
+  // ---- stream 0: random order of the candidates (its prefix is a uniform subset without replacement)
+  int p2 = 1;
+  while (p2 < nc) p2 <<= 1;
+  for (int j = tid; j < p2; j += blockDim.x)
+    keys[j] = j < nc ? ((lm_mix(seed, b, 0, j) & 0xFFFFFFFF00000000ull) | (unsigned long long)j) : ~0ull;
+  lm_bitonic_sort(keys, p2);
+  if (nc >= k) {  // sampling.py:71-73
+    for (int t = tid; t < k; t += blockDim.x) out[t] = cand[(int)(keys[t] & 0xFFFFFFFFull)];
+    return;
+  }
+  // ---- fewer candidates than k (sampling.py:74-80): every candidate k/nc times, k%nc distinct extras, shuffled
+  const int rep = k / nc, rem = k - rep * nc;
+  for (int t = tid; t < rem; t += blockDim.x) extras[t] = (int)(keys[t] & 0xFFFFFFFFull);
+  __syncthreads();
+  p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  for (int t = tid; t < p2; t += blockDim.x)
+    keys[t] = t < k ? ((lm_mix(seed, b, 1, t) & 0xFFFFFFFF00000000ull) | (unsigned long long)t) : ~0ull;
+  lm_bitonic_sort(keys, p2);
+  for (int t = tid; t < k; t += blockDim.x) {
+    const int src = (int)(keys[t] & 0xFFFFFFFFull);                 // position in the un-shuffled list
+    const int ci = src < rep * nc ? src / rep : extras[src - rep * nc];  // arange(nc).repeat(rep) ++ extras
+    out[t] = cand[ci];
+  }
+}
 }  // namespace pvb
 
 // =====================================================================================
@@ -858,6 +966,19 @@ int pvcnn_three_nearest_neighbors_interpolate_grad(int b, int c, int n, int m, c
   constexpr int CT = 16;
   PVB_LAUNCH(three_nn_interp_grad_kernel<CT>, dim3(ceil_div(n, 128), ceil_div(c, CT), b), 128, 0, s, c, n, m, grad_y,
              indices, weights, grad_x);
+  return 0;
+}
+
+int pvcnn_logits_mask_sample(int b, int n, int k, unsigned long long seed, const unsigned char *mask, int *picks,
+                             void *stream) {
+  PVB_CHECK_ARG(b > 0 && n > 0 && k > 0 && mask && picks);
+  int p2 = 1;
+  while (p2 < (n > k ? n : k)) p2 <<= 1;
+  const size_t smem = (size_t)p2 * 8 + (size_t)n * 8;
+  if (smem > 200 * 1024) return PVCNN_E_UNSUPPORTED;  // n, k <= 8192 (the reference's largest use: N = 1024, k = 512)
+  if (smem > 48 * 1024)
+    PVB_CUDA(cudaFuncSetAttribute(pvb::logits_mask_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVB_LAUNCH(pvb::logits_mask_sample_kernel, b, 1024, smem, stream, n, k, seed, mask, picks);
   return 0;
 }
 

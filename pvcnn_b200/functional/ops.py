@@ -1,5 +1,7 @@
 """autograd.Function wrappers -- same contracts as the reference's
 modules/functional/{voxelization,devoxelization,ball_query,grouping,sampling,interpolatation}.py."""
+import ctypes
+
 import numpy as np
 import os
 
@@ -143,10 +145,14 @@ def furthest_point_sample(coords, num_samples):
 
 
 def logits_mask(coords, logits, num_points_per_object):
-    """modules/functional/sampling.py:51-84: foreground mask from 2-way logits, masked mean, and a
-    fixed-size resampling of the foreground points.  The resampling keeps the reference's
-    numpy RNG call sequence (choice / choice+shuffle per sample) so that results are
-    reproducible against it under the same np.random seed."""
+    """modules/functional/sampling.py:51-84: foreground mask from 2-way logits, masked mean, and a fixed-size
+    resampling of the foreground points.
+
+    Default: the resampling runs on the device (pvcnn_logits_mask_sample: ordered compaction + counter-based random
+    subset / repeat-fill + shuffle, one CTA per sample) -- no `.nonzero()` host sync, no per-sample Python loop.  It draws
+    the same distribution as the reference's numpy calls; the stream is keyed by ONE np.random draw per call, so
+    np.random.seed() still makes a run reproducible.  PVCNN_B200_LOGITS_MASK=numpy keeps the reference's exact numpy
+    call sequence (choice / choice+shuffle per sample, one host sync each) for bit-reproducibility against it."""
     bsz, _, npts = coords.shape
     k = int(num_points_per_object)
     mask = logits[:, 0, :] < logits[:, 1, :]
@@ -154,6 +160,11 @@ def logits_mask(coords, logits, num_points_per_object):
     masked = coords * mask.view(bsz, 1, npts)
     mean = masked.sum(dim=-1) / torch.max(count, torch.ones_like(count)).float()
     picks = torch.zeros((bsz, k), device=coords.device, dtype=torch.int32)
+    if os.environ.get("PVCNN_B200_LOGITS_MASK", "device").lower() != "numpy" and coords.is_cuda and max(npts, k) <= 8192:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        _lib.call("pvcnn_logits_mask_sample", bsz, npts, k, ctypes.c_ulonglong(seed), mask.contiguous().view(torch.uint8),
+                  picks, device=coords.device)
+        return gather(masked - mean.view(bsz, -1, 1), picks), mean, mask
     for i in range(bsz):
         cand = mask[i].nonzero().view(-1)
         nc = cand.numel()

@@ -64,3 +64,61 @@ def test_pointnet_a_module_and_logits_mask():
     assert sel.shape == (b, 3, 128) and mean.shape == (b, 3) and mask.shape == (b, n)
     m0 = (logits[:, 0] < logits[:, 1])
     assert torch.equal(mask, m0)
+
+
+@pytest.mark.parametrize("b,n,k", [(32, 1024, 512), (5, 777, 128), (3, 300, 700), (2, 4096, 2048)])
+def test_logits_mask_device_sampling_matches_oracle(b, n, k):
+    """the per-sample host loop of modules/functional/sampling.py:66-82 runs on the device.  Picks are
+    bit-identical to the numpy restatement with the same counter-based generator (oracle.logits_mask_sample); mask and
+    masked mean follow the reference's tensor program; foreground fractions cover nc = 0, nc < k and nc >= k."""
+    import modules.functional as F
+    g = rng(43)
+    coords = g.random((b, 3, n), dtype=np.float32)
+    logits = g.standard_normal((b, 2, n), dtype=np.float32)
+    frac = np.linspace(0.0, 1.0, b)          # sample 0 has no foreground point at all
+    logits[:, 1] = np.where(g.random((b, n)) < frac[:, None], logits[:, 0] + 1.0, logits[:, 0] - 1.0)
+    np.random.seed(7)
+    seed = int(np.random.randint(0, 2 ** 31 - 1))
+    np.random.seed(7)
+    ct, lt = torch.from_numpy(coords).cuda(), torch.from_numpy(logits).cuda()
+    sel, mean, mask = F.logits_mask(ct, lt, k)
+    m0 = logits[:, 0] < logits[:, 1]
+    assert np.array_equal(mask.cpu().numpy(), m0)
+    picks = oracle.logits_mask_sample(m0, k, seed)
+    masked = coords * m0[:, None, :]
+    mean0 = masked.sum(-1, dtype=np.float64) / np.maximum(m0.sum(-1, keepdims=True), 1)
+    assert rel_err(mean.cpu().numpy(), mean0) < 1e-5
+    want = np.take_along_axis(masked - mean.cpu().numpy()[:, :, None], picks[:, None, :].astype(np.int64).repeat(3, 1), axis=2)
+    assert np.array_equal(sel.cpu().numpy(), want.astype(np.float32))
+    # distribution-free properties of the reference's scheme
+    for i in range(b):
+        cand = set(np.nonzero(m0[i])[0].tolist())
+        if not cand:
+            assert (picks[i] == 0).all()
+            continue
+        assert set(picks[i].tolist()) <= cand
+        counts = np.bincount(picks[i], minlength=n)[sorted(cand)]
+        if len(cand) >= k:
+            assert counts.max() == 1
+        else:
+            assert counts.min() >= k // len(cand) and counts.max() <= k // len(cand) + 1
+
+
+def test_logits_mask_numpy_mode_keeps_reference_rng_sequence(monkeypatch):
+    import modules.functional as F
+    monkeypatch.setenv("PVCNN_B200_LOGITS_MASK", "numpy")
+    g = rng(44)
+    b, n, k = 4, 512, 128
+    coords = torch.from_numpy(g.random((b, 3, n), dtype=np.float32)).cuda()
+    logits = torch.from_numpy(g.standard_normal((b, 2, n), dtype=np.float32)).cuda()
+    np.random.seed(3)
+    sel, mean, mask = F.logits_mask(coords, logits, k)
+    np.random.seed(3)
+    m0 = mask.cpu().numpy()
+    masked = coords.cpu().numpy() * m0[:, None, :]
+    for i in range(b):   # the reference's call sequence (sampling.py:69-82)
+        cand = np.nonzero(m0[i])[0]
+        ch = np.random.choice(cand.size, k, replace=False) if cand.size >= k else None
+        assert ch is not None
+        want = (masked[i] - mean[i].cpu().numpy()[:, None])[:, cand[ch]]
+        assert np.array_equal(sel[i].cpu().numpy(), want.astype(np.float32))
