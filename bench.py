@@ -434,6 +434,76 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_config(args):
+    """BASELINE.json configs 2-5: whole networks rebuilt from our modules (pvcnn_b200/zoo.py), synthetic inputs of the
+    reference's shapes; one line per run.  `comparison_arm` = the same network and weights with the stand-alone sm_100a
+    point ops around torch's cuDNN/cuBLAS dense layers (TF32 allowed, the reference's default precision)."""
+    import numpy as np
+    import torch
+    from pvcnn_b200 import zoo, _lib
+    os.environ["PVCNN_B200_PRECISION"] = args.precision
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(SEED)
+    model, spec = zoo.build(args.config)
+    train = spec["mode"] == "train"
+    model = model.to(dev).train(train)
+    g = torch.Generator().manual_seed(SEED)
+    x = zoo.synthetic_input(spec, g)
+    x = {k: v.to(dev) for k, v in x.items()} if isinstance(x, dict) else x.to(dev)
+    bsz, npts = spec["batch"], spec["points"]
+    target = torch.randint(0, 50, (bsz, npts), generator=g).to(dev) if train else None
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3) if train else None   # configs/shapenet/__init__.py:43-44
+
+    def step():
+        if train:
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(model(x), target)
+            loss.backward()
+            opt.step()
+            return loss
+        with torch.no_grad():
+            return model(x)
+
+    def timed(nsteps, nwarm):
+        np.random.seed(0)
+        for _ in range(nwarm):
+            step()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / nsteps, (_lib.launch_count() - l0) // nsteps
+
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ms, launches = timed(args.steps, args.warmup)
+    clocks = sampler.stop()
+    os.environ["PVCNN_B200_PVCONV"], os.environ["PVCNN_B200_MLP"] = "composed", "torch"
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    ms_cmp, _ = timed(max(3, args.steps // 2), args.warmup)
+    os.environ.pop("PVCNN_B200_PVCONV"); os.environ.pop("PVCNN_B200_MLP")
+    what = {"s3dis_pvcnn": "S3DIS PVCNN (1xC) forward", "shapenet_c0p25_train": "ShapeNet PVCNN (0.25xC) train step (Adam)",
+            "pvcnn2": "S3DIS PVCNN++ forward", "frustum_pvcnne": "KITTI Frustum-PVCNN(E) end-to-end inference"}[args.config]
+    print(json.dumps({
+        "metric": "%s points/sec (B=%d,N=%d)" % (what, bsz, npts), "value": bsz * npts / ms * 1e3, "unit": "points/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+        "dtype": "f32 (3xTF32)" if args.precision == "fp32" else "tf32",
+        "config": {"workload": "%s, random-init weights, B=%d N=%d, pvcnn_b200/zoo.py:%s" % (what, bsz, npts, args.config),
+                   "precision": args.precision},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "comparison_arm": {"ms_per_step": ms_cmp, "value": bsz * npts / ms_cmp * 1e3,
+                           "what": "same network/weights: stand-alone sm_100a point ops + torch cuDNN/cuBLAS dense layers, TF32 allowed"},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -444,11 +514,17 @@ def main():
                     help="weak: B=16 clouds on every GPU (default, what the driver's scaling run uses); "
                          "strong: the global B=16 batch sharded over the GPUs (SURVEY.md 8d reports both)")
     ap.add_argument("--precision", default=os.environ.get("PVCNN_B200_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--config", default="metric", choices=["metric", "s3dis_pvcnn", "shapenet_c0p25_train", "pvcnn2",
+                                                            "frustum_pvcnne"],
+                    help="metric (default): BASELINE.json's single-PVConv metric; the others: BASELINE configs 2-5 "
+                         "(whole networks, 1 GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "metric":
+        run_config(args)
     else:
         run_ours(args)
 

@@ -54,10 +54,40 @@ class PVConv(nn.Module):
         vox = F.trilinear_devoxelize(grid, norm_coords, self.resolution, self.training)
         return vox + self.point_features(features), coords
 
+    def _fused_unsupported_reason(self):
+        """The fused pipeline hard-wires what the reference's PVConv always builds (modules/pvconv.py:19-31): 3x3x3 convs
+        with padding 1, affine BatchNorm with running statistics, ONE LeakyReLU slope, one BN eps per branch.  Anything
+        else (kernel_size 1/5, a module someone edited after construction) must not reach kernels that would read the
+        weights with the wrong layout."""
+        c1, n1, a1, c2, n2, a2 = (self.voxel_layers[i] for i in range(6))
+        if self.kernel_size != 3:
+            return "kernel_size=%r (the tensor-core pipeline implements 3x3x3 / padding 1)" % (self.kernel_size,)
+        for conv, cin in ((c1, self.in_channels), (c2, self.out_channels)):
+            if tuple(conv.weight.shape) != (self.out_channels, cin, 3, 3, 3) or conv.bias is None:
+                return "unexpected Conv3d weight shape %s / missing bias" % (tuple(conv.weight.shape),)
+            if tuple(conv.stride) != (1, 1, 1) or tuple(conv.padding) != (1, 1, 1) or conv.groups != 1:
+                return "Conv3d stride/padding/groups differ from (1, 1, 1)"
+        pt = self.point_features.layers
+        if len(pt) != 3 or tuple(pt[0].weight.shape) != (self.out_channels, self.in_channels, 1) or pt[0].bias is None:
+            return "point branch is not a single (Conv1d k=1, BatchNorm1d, ReLU) layer"
+        for bn in (n1, n2, pt[1]):
+            if not bn.affine or not bn.track_running_stats or bn.running_mean is None:
+                return "BatchNorm without affine parameters / running statistics"
+        if n1.eps != n2.eps or a1.negative_slope != a2.negative_slope:
+            return "the two voxel layers use different BatchNorm eps / LeakyReLU slopes"
+        if self.with_se and self.out_channels < 8:
+            return "SE3d with fewer than 8 channels"
+        return None
+
     def forward(self, inputs):
         features, coords = inputs
         mode = os.environ.get("PVCNN_B200_PVCONV", "fused")
         if mode == "composed":
             return self._forward_composed(features, coords)
+        why = self._fused_unsupported_reason()
+        if why is not None:
+            if mode == "fused_strict":
+                raise RuntimeError("PVConv: configuration outside the fused sm_100a pipeline: " + why)
+            return self._forward_composed(features, coords)   # stand-alone sm_100a ops + torch dense layers
         from ..fused import pvconv_fused
         return pvconv_fused(self, features, coords), coords

@@ -77,6 +77,19 @@ def test_reference_models_build_on_our_modules():
         assert sum(p.numel() for p in net3.parameters()) == 268898
         assert kitti.FrustumPVCNNE is not None
         assert isinstance(net.point_features[0], modules.PVConv)
+        # pvcnn_b200.zoo rebuilds the same four networks from our modules (what tests / bench use on the GPU box, where
+        # the reference tree is absent): state_dict keys AND shapes must equal the unmodified reference models'
+        from pvcnn_b200 import zoo
+        ones = torch.ones(3, 3)
+        ref_frustum = kitti.FrustumPVCNNE(num_classes=3, num_heading_angle_bins=12, num_size_templates=3,
+                                          num_points_per_object=512, size_templates=ones)
+        for ours, ref in ((zoo.S3DISPVCNN(13, 6), net), (zoo.S3DISPVCNN2(13, 6), net2),
+                          (zoo.ShapeNetPVCNN(50, 16, 3, width_multiplier=0.25), net3),
+                          (zoo.FrustumPVCNNE(size_templates=ones), ref_frustum)):
+            so, sr = ours.state_dict(), ref.state_dict()
+            assert list(so.keys()) == list(sr.keys()), type(ours).__name__
+            assert all(so[k].shape == sr[k].shape for k in so), type(ours).__name__
+            ours.load_state_dict(sr)   # a reference checkpoint loads unchanged
     finally:
         sys.path.remove(added)
 

@@ -67,9 +67,14 @@ def test_pvconv_train_step(mode, b, n, c, r, monkeypatch):
 
 @pytest.mark.parametrize("b,n,cin,cout,r,normalize,eps", [
     (2, 1500, 9, 64, 16, True, 0.0),      # first-layer shape: Cin=9 (padded to 12), ragged N
-    (2, 1024, 64, 128, 12, True, 0.0),    # R=12 and Cout=128 -> v1 conv kernel + single-group wgrad
+    (2, 1024, 64, 128, 12, True, 0.0),    # R=12 (z padded to 16) and Cout=128 (two N-blocks, single-group wgrad)
     (3, 777, 16, 32, 8, False, 0.0),      # normalize=False (ShapeNet), odd N
     (2, 1024, 4, 64, 16, True, 1e-15),    # KITTI first layer: Cin=4, eps set
+    (2, 2048, 64, 128, 16, True, 0.0),    # S3DIS PVCNN 64->128@16 (models/s3dis/pvcnn.py:10): halo kernel, 2 N-blocks
+    (4, 256, 128, 128, 8, True, 0.0),     # PVCNN++ 128->128@8 (models/s3dis/pvcnnpp.py:9-20)
+    (4, 256, 256, 256, 8, True, 0.0),     # PVCNN++ fp_blocks 256->256@8: train step (wgrad Cout > 128)
+    (2, 1024, 64, 128, 12, True, 1e-15),  # KITTI 64->128@12 (models/kitti/frustum/segmentation/pointnet.py:58)
+    (2, 1024, 64, 64, 12, True, 0.0),     # R=12 on the halo kernel (z rows padded to 16)
 ])
 def test_pvconv_fused_shapes(b, n, cin, cout, r, normalize, eps, monkeypatch):
     monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
@@ -296,3 +301,30 @@ def test_pvconv_metric_config_properties(monkeypatch):
     for k in skip:
         wk = k.replace("bias", "weight")
         assert float(pg[k].abs().max()) < 1e-4 * float(pg[wk].abs().max()) * pg[wk][0].numel() ** 0.5, k
+
+
+def test_pvconv_metric_config_vs_fp64_oracle(monkeypatch):
+    """BASELINE.json's metric configuration (B=16, N=4096, C=64, R=32, train mode, fwd+bwd) against the fp64 CPU oracle
+    itself (~1 min on the box's host cores).  Forward: element-wise 1e-5.  Gradients: with 2 x 33 M LeakyReLU inputs a
+    handful sit within fp32 rounding of zero and take the other branch than fp64 (and than any other fp32 run: the
+    scatter kernels' atomic summation order decides); one flip changes ONE voxel-channel's gradient by 10x, i.e. the 27-125
+    voxels around it and one channel of the weight gradients.  So: 99 % of the input-gradient elements at rounding level,
+    L2 at the few-flips level (measured: one flip = 8e-4), parameter gradients L2 only."""
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused")
+    b, n, c, r = 16, 4096, 64, 32
+    g = rng(1588147245 % (2 ** 31))
+    f = g.standard_normal((b, c, n), dtype=np.float32)
+    co = s3dis_like_coords(g, b, n)
+    go = g.standard_normal((b, c, n), dtype=np.float32)
+    m = make_block(c, c, r).cuda().train()
+    params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()
+              if "running" not in k and "num_batches" not in k}
+    ref = oracle.pvconv_forward_backward(params, f, co, go, r, training=True, dtype="float64", threads=os.cpu_count(),
+                                         vox_mean=device_mean(co))
+    out, gin, pg = _step(m, torch.from_numpy(f).cuda(), torch.from_numpy(co).cuda(), torch.from_numpy(go).cuda())
+    assert rel_err(out.cpu().numpy(), ref["out"]) < 1e-5
+    _close(gin.cpu(), torch.from_numpy(ref["grad_features"]), 2e-5, 0.99, "oracle gin")
+    for k, v in pg.items():
+        if k in ("voxel_layers.0.bias", "voxel_layers.3.bias", "point_features.layers.0.bias"):
+            continue
+        _close(v.cpu(), torch.from_numpy(ref["grads"][k]), None, None, "oracle " + k)
