@@ -67,7 +67,7 @@ __device__ __forceinline__ void h3_decode(const Halo3Params &p, int unit, int &x
   }
 }
 
-template <int ORDER>
+template <bool THREE, int BZ>
 __global__ void __launch_bounds__(H3_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w_hi,
                      const __grid_constant__ CUtensorMap map_w_lo, const Halo3Params p) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool three = p.npass > 1;
+  constexpr bool three = THREE;   // 3xTF32 (hi/lo split) or single-pass TF32: compile-time, so the MMA issue loop carries no dead path
   const uint32_t a_stage_bytes = p.a_bytes * (three ? 2u : 1u);
   const uint32_t b_stage_bytes = p.b_bytes * (three ? 2u : 1u);
   uint8_t *smem_b = smem + (size_t)p.a_stages * a_stage_bytes;
@@ -150,64 +150,62 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
       constexpr uint32_t dhi = desc_hi32(512, kH3LayoutSW64);
-      // descriptor offsets (16-byte units) of tile t / tap (dx,dy) inside the halo: rows are (x_local, y_local, z)
-      uint32_t tap_off[9][H3_TX];
-#pragma unroll
-      for (int t9 = 0; t9 < 9; ++t9)
-#pragma unroll
-        for (int t = 0; t < H3_TX; ++t)
-          tap_off[t9][t] = (uint32_t)(((t + t9 / 3) * (p.ty + 2) + (t9 % 3)) * p.bz) * (H3_KC * 4 / 16);
+      // One elected thread issues every MMA of the CTA, and it is ISSUE-bound (ncu r02: tensor pipe 33-53 %, tensor-core
+      // shared-memory pipe 49-62 %, no barrier stalls): every instruction next to a tcgen05.mma counts.  The halo
+      // geometry is a template parameter so that every tap's descriptor offset is an immediate:
+      //   rows are (x_local, y_local, z); 16-byte units: one row = 4, a y step = BZ * 4, an x step = (TY + 2) * BZ * 4
+      constexpr uint32_t YS = (uint32_t)BZ * (H3_KC * 4 / 16);
+      constexpr uint32_t XS = (uint32_t)(128 / BZ + 2) * YS;
       const uint32_t bn = (uint32_t)p.block_n;
       uint64_t *a_bar = three ? a_ready : a_full;  // single pass: nothing to convert, consume the TMA data directly
       int ast = 0, bst = 0;
       uint32_t aph = 0, bph = 0, g = 0;  // g: chunk phases issued so far (accumulator hand-shake parity)
       long long st_acc = 0, st_a = 0, st_b = 0;
       int items_done = 0;
+      const uint32_t b_base = desc_lo32(smem_u32(smem_b), 0);
+      const uint32_t b_step = b_stage_bytes >> 4, b_lo_off = p.b_bytes >> 4, a_lo_off = p.a_bytes >> 4;
       const long long t_begin = clock64();
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++items_done) {
         for (int cc = 0; cc < p.kchunks; ++cc, ++g) {
           mbar_wait_t(&a_bar[ast], aph, p.err, 24, st_a);
           tc_fence_after();
           const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)ast * a_stage_bytes), 0);
-          const uint32_t a_lo = a_hi + (p.a_bytes >> 4);
+          const uint32_t a_lo = a_hi + a_lo_off;
+#pragma unroll 1
           for (int dz = 0; dz < 3; ++dz) {
             // the epilogue has copied the previous chunk's P_dz (both tiles) into registers
             mbar_wait_t(&acc_empty[dz], (g & 1u) ^ 1u, p.err, 23, st_acc);
             tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)dz * bn, d1 = d0 + 3u * bn;
             // software-pipelined barrier polling: the try_wait for the NEXT weight tile is issued before this
             // tile's MMAs, so its latency hides behind the MMA issue instead of sitting on the critical path
             bool b_ready = mbar_try_wait(&b_full[bst], bph);
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
               if (!b_ready) mbar_wait_t(&b_full[bst], bph, p.err, 25, st_b);
-              {
-                const int nst = (bst + 1 == p.b_stages) ? 0 : bst + 1;
-                const uint32_t nph = (bst + 1 == p.b_stages) ? (bph ^ 1) : bph;
-                b_ready = mbar_try_wait(&b_full[nst], nph);
-              }
+              const uint32_t b_hi = b_base + (uint32_t)bst * b_step;
+              const uint64_t *done_bar = &b_empty[bst];
+              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
+              b_ready = mbar_try_wait(&b_full[bst], bph);
               tc_fence_after();
-              const uint32_t b_hi = desc_lo32(smem_u32(smem_b + (size_t)bst * b_stage_bytes), 0);
-              const uint32_t b_lo = b_hi + (p.b_bytes >> 4);
-              // Issue order inside a tap: consecutive MMAs into the SAME accumulator serialise on the accumulate
-              // dependency, so the two tiles' chains are interleaved (ORDER 1: k-step outer, tile inner).
 #pragma unroll
-              for (int i = 0; i < H3_TX * (H3_KC / 8); ++i) {
-                const int t = ORDER == 1 ? (i % H3_TX) : (i / (H3_KC / 8));
-                const int ks = ORDER == 1 ? (i / H3_TX) : (i % (H3_KC / 8));
-                const uint32_t d = tmem_base + (uint32_t)(t * 3 + dz) * bn;
-                const uint32_t ao = tap_off[t9][t] + (uint32_t)ks * 2u;  // +32 bytes per k-step
-                const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;    // every chunk starts a fresh chain
-                if (three) {
-                  // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
-                  mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                  mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_lo + ks * 2u, dhi, idesc, 1u);
-                  mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
-                } else {
-                  mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+              for (int ks = 0; ks < H3_KC / 8; ++ks) {
+#pragma unroll
+                for (int t = 0; t < H3_TX; ++t) {  // the two tiles' chains alternate (independent accumulators)
+                  const uint32_t ao = (uint32_t)(t + t9 / 3) * XS + (uint32_t)(t9 % 3) * YS + (uint32_t)ks * 2u;  // immediate
+                  const uint32_t d = t == 0 ? d0 : d1;
+                  const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;  // every chunk starts a fresh chain
+                  if (three) {
+                    // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
+                    mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                    mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_hi + b_lo_off + ks * 2u, dhi, idesc, 1u);
+                    mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
+                  } else {
+                    mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                  }
                 }
               }
-              mma_commit(&b_empty[bst]);
-              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
+              mma_commit(const_cast<uint64_t *>(done_bar));
             }
             mma_commit(&acc_full[dz]);
           }
@@ -251,8 +249,8 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
     const int q = (warp - 4) & 3;      // TMEM lane quarter
     const int my_t = (warp - 4) >> 2;  // the output tile (x-plane) this warp drains: the two tiles drain in parallel
     const int m = q * 32 + lane;
-    const int lz = m % p.bz, ly = m / p.bz;
-    const bool z_first = lz == 0, z_last = lz == p.bz - 1;
+    const int lz = m % BZ, ly = m / BZ;
+    const bool z_first = lz == 0, z_last = lz == BZ - 1;
     const int bn = p.block_n;
     uint32_t g = 0;
     long long st_full = 0;
@@ -428,15 +426,17 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
   }
   const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024;
   const int grid = min(kNumSMs, p.num_units * p.nblocks);
-  int order = 1;
-  { const char *e = getenv("PVCNN_HALO_ORDER"); if (e && (e[0] == '0' || e[0] == '1')) order = e[0] - '0'; }
-  if (order == 1) {
-    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_halo_kernel<1>, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+#define PVB_HALO_LAUNCH(T3, BZV)                                                                                            \
+  do {                                                                                                                      \
+    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<T3, BZV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    PVB_LAUNCH((conv_halo_kernel<T3, BZV>), grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);                          \
+  } while (0)
+  if (npass > 1) {
+    if (p.bz == 32) PVB_HALO_LAUNCH(true, 32); else if (p.bz == 16) PVB_HALO_LAUNCH(true, 16); else PVB_HALO_LAUNCH(true, 8);
   } else {
-    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_halo_kernel<0>, grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);
+    if (p.bz == 32) PVB_HALO_LAUNCH(false, 32); else if (p.bz == 16) PVB_HALO_LAUNCH(false, 16); else PVB_HALO_LAUNCH(false, 8);
   }
+#undef PVB_HALO_LAUNCH
   return 0;
 }
 

@@ -25,9 +25,8 @@ for (b, r, cin, cout) in shapes:
     w_hi, w_lo = dense.prep_weight(w)
     x_lo = dense.split_tf32(x, want_hi=False)[1]
     ref = None
-    for ver in ("v3/0", "v3/1"):
+    for ver in ("v3", "v1"):
         os.environ["PVCNN_B200_CONV"] = ver.split("/")[0]
-        os.environ["PVCNN_HALO_ORDER"] = ver.split("/")[1] if "/" in ver else ""
         for npass in (3, 1):
             try:
                 out = dense.igemm_conv(x, x_lo, w_hi, w_lo, None, npass=npass)
