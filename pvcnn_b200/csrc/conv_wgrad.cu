@@ -53,7 +53,7 @@ struct WgradParams {
   long long *dbg;           // optional [8] stall-cycle counters of CTA 0 (PVCNN_STALL_PROFILE)
 };
 
-template <int G>
+template <int G, bool THREE>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                       const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
@@ -175,6 +175,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const uint32_t g_lo = g_hi + (uint32_t)p.chunks_out * (WG_BLK >> 4);
         const uint32_t a_base = g_hi + (p.g_bytes >> 4);
         const uint32_t first = pos_in_chain == 0 ? 0u : 1u;
+        // The single issuing thread is issue-bound (see conv_halo.cu): precision mode and group count are template
+        // parameters, the usual 4 k-steps are unrolled, and A_hi (the X block) is fetched from shared memory once for its
+        // two products (collector fill / lastuse).
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (g < ngroups) {
@@ -182,14 +185,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             const uint32_t a_lo = a_base + (uint32_t)(G * 4 + g * 4) * (WG_BLK >> 4);
             const uint32_t d_main = tmem_base + (uint32_t)buf * tmem_cols_per_buf + (uint32_t)(g * p.block_n);
             const uint32_t d_corr = d_main + (uint32_t)(G * p.block_n);
-            for (int ks = 0; ks < p.ksteps; ++ks) {
+            auto kstep = [&](int ks) {
               const uint32_t ko = (uint32_t)ks * 64u;
               const uint32_t accum = ks == 0 ? first : 1u;
-              mma_tf32_lo32(d_main, a_hi + ko, g_hi + ko, dhi, idesc, accum);
-              if (p.npass > 1) {
-                mma_tf32_lo32(d_corr, a_hi + ko, g_lo + ko, dhi, idesc, accum);
+              if (THREE) {
+                mma_tf32_lo32_c<kCollFill>(d_main, a_hi + ko, g_hi + ko, dhi, idesc, accum);
+                mma_tf32_lo32_c<kCollLastUse>(d_corr, a_hi + ko, g_lo + ko, dhi, idesc, accum);
                 mma_tf32_lo32(d_corr, a_lo + ko, g_hi + ko, dhi, idesc, 1u);
+              } else {
+                mma_tf32_lo32(d_main, a_hi + ko, g_hi + ko, dhi, idesc, accum);
               }
+            };
+            if (p.ksteps == 4) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) kstep(ks);
+            } else {
+              for (int ks = 0; ks < p.ksteps; ++ks) kstep(ks);
             }
           }
         }
@@ -378,13 +389,17 @@ static int wgrad_launch_block(int nb, int sx, int sy, int sz, int cin, int cout,
   if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_lo, (npass > 1 && !p.lo_in_kernel) ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+#define PVB_WG_LAUNCH(GV, T3)                                                                                         \
+  do {                                                                                                                \
+    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<GV, T3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    PVB_LAUNCH((conv_wgrad_kernel<GV, T3>), p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p); \
+  } while (0)
   if (p.groups_per_cta == 2) {
-    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_wgrad_kernel<2>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+    if (npass > 1) PVB_WG_LAUNCH(2, true); else PVB_WG_LAUNCH(2, false);
   } else {
-    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_wgrad_kernel<1>, p.num_sets * p.ksplit, WG_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+    if (npass > 1) PVB_WG_LAUNCH(1, true); else PVB_WG_LAUNCH(1, false);
   }
+#undef PVB_WG_LAUNCH
   return 0;
 }
 

@@ -398,14 +398,16 @@ __global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r3 = r * r * r, cp4 = cp >> 2;
   const float *co = nc + (size_t)b * 3 * n;
-  for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
+  // a row of cp <= 64 channels needs only 16 lanes (16 bytes each): two points per warp pass, so all 32 lanes load
+  const int lpp = cp4 <= 16 ? 16 : 32, sub = lane / lpp, cl = lane % lpp;
+  for (int q = sub; q < PT_TILE / PT_WARPS; q += 32 / lpp) {
     const int pt = warp * (PT_TILE / PT_WARPS) + q;
     const int i = i0 + pt;
-    if (i >= n) break;
+    if (i >= n) continue;
     Corners k;
     corner_setup(co[i], co[i + n], co[i + 2 * n], r, k);
     const float *prow = p + ((size_t)b * n + i) * cp;
-    for (int c4 = lane; c4 < cp4; c4 += 32) {
+    for (int c4 = cl; c4 < cp4; c4 += lpp) {
       const float4 sc = ld4(bn2.scale + c4 * 4), sh = ld4(bn2.shift + c4 * 4);
       float4 acc;
       {
@@ -477,7 +479,11 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
   }
   __syncthreads();
   const float *co = nc + (size_t)b * 3 * n;
-  for (int c4 = lane; c4 < cp4; c4 += 32) {
+  // cp <= 64: a row needs 16 lanes, so the two half-warps walk different points (all 32 lanes load / scatter) and
+  // their reduction partials are combined with one shuffle at the end
+  const int lpp = cp4 <= 16 ? 16 : 32, sub = lane / lpp, cl = lane % lpp;
+  const unsigned fold_mask = __ballot_sync(0xffffffffu, cl < cp4);  // lanes that run the (single, when lpp == 16) pass
+  for (int c4 = cl; c4 < cp4; c4 += lpp) {
     const float4 sc2 = ld4(bn2.scale + c4 * 4), sh2 = ld4(bn2.shift + c4 * 4);
     const float4 mu2 = ld4(bn2.mean + c4 * 4), is2 = ld4(bn2.invstd + c4 * 4);
     const float4 scp = ld4(bnp.scale + c4 * 4), shp = ld4(bnp.shift + c4 * 4);
@@ -485,10 +491,10 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
     float4 S1 = make_float4(0.f, 0.f, 0.f, 0.f), S2 = S1, T1 = S1, T2 = S1, DS = S1;
     float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
     if (se_s) sv = ld4(se_s + (size_t)b * cp + c4 * 4);
-    for (int q = 0; q < PT_TILE / PT_WARPS; ++q) {
+    for (int q = sub; q < PT_TILE / PT_WARPS; q += 32 / lpp) {
       const int pt = warp * (PT_TILE / PT_WARPS) + q;
       const int i = i0 + pt;
-      if (i >= n) break;
+      if (i >= n) continue;
       const float4 g = make_float4(gtile[(c4 * 4 + 0) * 33 + pt], gtile[(c4 * 4 + 1) * 33 + pt],
                                    gtile[(c4 * 4 + 2) * 33 + pt], gtile[(c4 * 4 + 3) * 33 + pt]);
       // ---- point branch: ReLU mask, BN1d reductions
@@ -534,11 +540,22 @@ __global__ void __launch_bounds__(256) bwd_points_kernel(int n, int c, int cp, i
       }
       DS.x = fmaf(g.x, V.x, DS.x); DS.y = fmaf(g.y, V.y, DS.y); DS.z = fmaf(g.z, V.z, DS.z); DS.w = fmaf(g.w, V.w, DS.w);
     }
-    st4(red + ((size_t)warp * 5 + 0) * cp + c4 * 4, S1);
-    st4(red + ((size_t)warp * 5 + 1) * cp + c4 * 4, S2);
-    st4(red + ((size_t)warp * 5 + 2) * cp + c4 * 4, T1);
-    st4(red + ((size_t)warp * 5 + 3) * cp + c4 * 4, T2);
-    st4(red + ((size_t)warp * 5 + 4) * cp + c4 * 4, DS);
+    if (lpp == 16) {  // fold the other half-warp's points in (same channel quad, lanes l and l ^ 16)
+#define PVB_FOLD4(v)                                      \
+  v.x += __shfl_xor_sync(fold_mask, v.x, 16);             \
+  v.y += __shfl_xor_sync(fold_mask, v.y, 16);             \
+  v.z += __shfl_xor_sync(fold_mask, v.z, 16);             \
+  v.w += __shfl_xor_sync(fold_mask, v.w, 16);
+      PVB_FOLD4(S1) PVB_FOLD4(S2) PVB_FOLD4(T1) PVB_FOLD4(T2) PVB_FOLD4(DS)
+#undef PVB_FOLD4
+    }
+    if (sub == 0) {
+      st4(red + ((size_t)warp * 5 + 0) * cp + c4 * 4, S1);
+      st4(red + ((size_t)warp * 5 + 1) * cp + c4 * 4, S2);
+      st4(red + ((size_t)warp * 5 + 2) * cp + c4 * 4, T1);
+      st4(red + ((size_t)warp * 5 + 3) * cp + c4 * 4, T2);
+      st4(red + ((size_t)warp * 5 + 4) * cp + c4 * 4, DS);
+    }
   }
   __syncthreads();
   const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;  // blocks of one sample are contiguous
@@ -961,54 +978,69 @@ struct CompactJob {
 };
 struct CompactJobs { CompactJob j[6]; };
 
-// one CTA per list: ordered stream compaction (ballot scan) of flags -> coordinates
-__global__ void __launch_bounds__(1024) compact_lists_kernel(CompactJobs jobs, int r, int ty, int wg_bz, int wg_by,
+// Ordered stream compaction of the six flag arrays into coordinate lists, spread over the chip:
+//   pass 1: one CTA per (1024-flag chunk, list) counts its set flags;
+//   pass 2: the same grid: a chunk's base = sum of the earlier chunks' counts, ballot scan inside the chunk, write.
+// (r01: a single 1024-thread CTA per list walked up to 16 chunks serially: 32 us.)
+__global__ void __launch_bounds__(1024) compact_count_kernel(CompactJobs jobs, int chunks, int *__restrict__ chunk_counts) {
+  __shared__ int warp_tot[32];
+  const CompactJob jb = jobs.j[blockIdx.y];
+  const int i = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool f = i < jb.n && jb.flags[i];
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_tot[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) chunk_counts[blockIdx.y * chunks + blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(1024) compact_write_kernel(CompactJobs jobs, int chunks, int r, int ty, int wg_bz,
+                                                             int wg_by, const int *__restrict__ chunk_counts,
                                                              int *__restrict__ counts) {
   __shared__ int warp_tot[32];
-  __shared__ int base;
-  const CompactJob jb = jobs.j[blockIdx.x];
+  const CompactJob jb = jobs.j[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pairs_x = (r + 1) / 2, tiles_y = (r + ty - 1) / ty;
   const int wg_ty = (r + wg_by - 1) / wg_by, wg_tz = (r + wg_bz - 1) / wg_bz;
-  if (threadIdx.x == 0) base = 0;
+  int base = 0;
+  for (int c = 0; c < (int)blockIdx.x; ++c) base += __ldg(chunk_counts + blockIdx.y * chunks + c);
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const bool f = i < jb.n && jb.flags[i];
+  const unsigned bal = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
   __syncthreads();
-  for (int i0 = 0; i0 < jb.n; i0 += 1024) {
-    const int i = i0 + threadIdx.x;
-    const bool f = i < jb.n && jb.flags[i];
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) {
-      const int v = warp_tot[w];
-      if (w < warp) woff += v;
-      tot += v;
-    }
-    if (f) {
-      const int pos = base + woff + __popc(bal & ((1u << lane) - 1));
-      int u = i;
-      if (jb.is_ktile) {
-        const int tz = u % wg_tz; u /= wg_tz;
-        const int tyi = u % wg_ty; u /= wg_ty;
-        const int x = u % r; u /= r;
-        jb.list[pos] = make_int4(tz * wg_bz, tyi * wg_by, x, u);
-      } else {
-        const int yt = u % tiles_y; u /= tiles_y;
-        const int xp = u % pairs_x; u /= pairs_x;
-        jb.list[pos] = make_int4(xp * 2, yt * ty, u, 0);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) base += tot;
-    __syncthreads();
+  int woff = 0, tot = 0;
+  for (int w = 0; w < 32; ++w) {
+    const int v = warp_tot[w];
+    if (w < warp) woff += v;
+    tot += v;
   }
-  if (threadIdx.x == 0) counts[blockIdx.x] = base;
+  if (f) {
+    const int pos = base + woff + __popc(bal & ((1u << lane) - 1));
+    int u = i;
+    if (jb.is_ktile) {
+      const int tz = u % wg_tz; u /= wg_tz;
+      const int tyi = u % wg_ty; u /= wg_ty;
+      const int x = u % r; u /= r;
+      jb.list[pos] = make_int4(tz * wg_bz, tyi * wg_by, x, u);
+    } else {
+      const int yt = u % tiles_y; u /= tiles_y;
+      const int xp = u % pairs_x; u /= pairs_x;
+      jb.list[pos] = make_int4(xp * 2, yt * ty, u, 0);
+    }
+  }
+  // the chunk that holds the list's last flag publishes the total
+  if (threadIdx.x == 0 && (int)blockIdx.x == (jb.n - 1) / 1024) counts[blockIdx.y] = base + tot;
 }
 
 int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int *cnt, int *counts, unsigned char *occ,
                           unsigned char *act1, unsigned char *act_dg, unsigned char *fwd2_flag, unsigned char *wg1_flag,
                           unsigned char *wg2_flag, unsigned char *dg2_flag, int4 *fwd1, int4 *dgrad1, int4 *fwd2,
-                          int4 *wg1, int4 *wg2, int4 *dg2, cudaStream_t s) {
+                          int4 *wg1, int4 *wg2, int4 *dg2, int *chunk_counts, cudaStream_t s) {
   const long long ncols = (long long)nb * r * r;
   PVB_LAUNCH(colocc_kernel, ceil_div(ncols, 256), 256, 0, s, r, ncols, cnt, occ);
   const int n_units = nb * ((r + 1) / 2) * ((r + ty - 1) / ty);
@@ -1024,7 +1056,9 @@ int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int
   jobs.j[3] = CompactJob{wg1_flag, wg1, n_kt, 1};
   jobs.j[4] = CompactJob{wg2_flag, wg2, n_kt, 1};
   jobs.j[5] = CompactJob{dg2_flag, dg2, n_units, 0};
-  PVB_LAUNCH(compact_lists_kernel, 6, 1024, 0, s, jobs, r, ty, wg_bz, wg_by, counts);
+  const int chunks = ceil_div(nmax, 1024);
+  PVB_LAUNCH(compact_count_kernel, dim3(chunks, 6), 1024, 0, s, jobs, chunks, chunk_counts);
+  PVB_LAUNCH(compact_write_kernel, dim3(chunks, 6), 1024, 0, s, jobs, chunks, r, ty, wg_bz, wg_by, chunk_counts, counts);
   return 0;
 }
 
@@ -1141,15 +1175,26 @@ __global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by
       // lanes: (z parity, channel quad) -- 32 lanes cover two z rows of 16 quads; loads unrolled for memory-level parallelism
       const int zpar = cp4 <= 16 ? (lane >> 4) : 0, zstep = cp4 <= 16 ? 2 : 1;
       for (int c4 = cp4 <= 16 ? (lane & 15) : lane; c4 < cp4; c4 += (cp4 <= 16 ? 16 : 32)) {
+        // s1 collects EVERY row of the tile (straight-line adds, 8 loads in flight); the two boundary rows z = 0 and
+        // z = r-1 are fetched once more (L1 hits) and moved to their own classes.  A three-way accumulator select
+        // (`float4 &d = cond ? s0 : ...`) made ptxas spill the accumulators to local memory (r01: 1.5 TB/s).
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
         const float *row = g + ((((size_t)b * r + x) * r + y) * r + (size_t)tz * bz) * cp + c4 * 4;
+        const int zend = min(bz, r - tz * bz);
 #pragma unroll 8
-        for (int zz = zpar; zz < bz; zz += zstep) {
-          const int z = tz * bz + zz;
-          if (z < r) {
-            const float4 v = ld4(row + (size_t)zz * cp);
-            float4 &d = z == 0 ? s0 : (z == r - 1 ? s2 : s1);
-            d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+        for (int zz = zpar; zz < zend; zz += zstep) {
+          const float4 v = ldg_stream4(row + (size_t)zz * cp);
+          s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+        }
+        if (tz == 0 && zpar == 0) {                       // z = 0 belongs to this lane's z parity
+          s0 = ld4(row);
+          s1.x -= s0.x; s1.y -= s0.y; s1.z -= s0.z; s1.w -= s0.w;
+        }
+        {
+          const int zl = r - 1 - tz * bz;                 // local index of z = r-1, if it lies in this tile
+          if (zl >= 0 && zl < zend && zl > 0 && (zl % zstep) == zpar) {
+            s2 = ld4(row + (size_t)zl * cp);
+            s1.x -= s2.x; s1.y -= s2.y; s1.z -= s2.z; s1.w -= s2.w;
           }
         }
         for (int set = inactive ? 0 : 1; set < 2; ++set) {

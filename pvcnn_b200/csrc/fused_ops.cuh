@@ -83,7 +83,7 @@ int launch_build_activity(int nb, int r, int ty, int wg_bz, int wg_by, const int
                           unsigned char *occ /*[nb*r*r]*/, unsigned char *act1, unsigned char *act_dg,
                           unsigned char *fwd2_flag, unsigned char *wg1_flag, unsigned char *wg2_flag,
                           unsigned char *dg2_flag, int4 *fwd1, int4 *dgrad1, int4 *fwd2, int4 *wg1, int4 *wg2, int4 *dg2,
-                          cudaStream_t s);
+                          int *chunk_counts /*[6 * ceil(max(units, k-tiles) / 1024)]*/, cudaStream_t s);
 // 27 boundary-class column sums of g: [0] over the k-tiles not in kt_active, [1] over all voxels
 int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char *kt_active, const float *g,
                       float *classsum2 /*[2][27][cp]*/, cudaStream_t s);

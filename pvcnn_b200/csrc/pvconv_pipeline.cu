@@ -37,6 +37,7 @@ struct SparseBuf {
   float *classsum;           // [27][co]  conv2 forward constants
   float *tapsum;             // [27][co]
   float *classsum_g;         // [2][27][co]  class sums of gY2: constant-region k-tiles, all voxels
+  int *chunk_counts;         // [6][chunks]  per-1024-flag chunk counts of the list compaction
   int ty, wg_bz, wg_by;
   long long total_ints;
 };
@@ -70,6 +71,7 @@ static SparseBuf sparse_at(int *base, int b, int r, int co) {
   v.classsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
   v.tapsum = reinterpret_cast<float *>(base + o); o += 27LL * co;
   v.classsum_g = reinterpret_cast<float *>(base + o); o += 2 * 27LL * co;
+  v.chunk_counts = base + o; o += 6 * (((units > kt ? units : kt) + 1023) / 1024) + 4;
   v.total_ints = o;
   return v;
 }
@@ -190,7 +192,8 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   if (sparse) {  // which tiles can differ from the closed form (zero / constant input)?
     sp = sparse_at(ws->sparse, b, r, co);
     PVB_TRY(launch_build_activity(b, r, sp.ty, sp.wg_bz, sp.wg_by, ws->cnt, sp.counts, sp.occ, sp.act1, sp.act_dg, sp.fwd2_flag,
-                                  sp.wg1_flag, sp.wg2_flag, sp.dg2_flag, sp.fwd1, sp.dgrad1, sp.fwd2, sp.wg1, sp.wg2, sp.dg2, s));
+                                  sp.wg1_flag, sp.wg2_flag, sp.dg2_flag, sp.fwd1, sp.dgrad1, sp.fwd2, sp.wg1, sp.wg2, sp.dg2,
+                                  sp.chunk_counts, s));
   }
   // 2. points to channels-last, scatter-mean into the grid        (vox.cu:48-72)
   PVB_TRY(launch_points_to_cl(b, d->cin, n, ci, features, ws->fcl, lo ? ws->fcl_lo : nullptr, s));

@@ -292,7 +292,7 @@ def test_pvconv_metric_config_properties(monkeypatch):
     perm = torch.from_numpy(g.permutation(n)).cuda()
     out_p, gin_p, pg_p = _step(m, f[:, :, perm].contiguous(), co[:, :, perm].contiguous(), go[:, :, perm].contiguous())
     assert rel_err(out_p.cpu().numpy(), out[:, :, perm].cpu().numpy()) < 5e-6
-    _close(gin_p, gin[:, :, perm], 5e-6, 0.99, "permutation gin")
+    _close(gin_p, gin[:, :, perm], 1e-5, 0.99, "permutation gin")
     for k in pg_p:
         if k not in skip:
             _close(pg_p[k], pg[k], None, None, "permutation " + k)
