@@ -111,6 +111,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from pvcnn_b200.parallel import pin_process_to_gpu_numa_node
+        numa = pin_process_to_gpu_numa_node(local)   # before the pinned host buffers are first touched
+    else:
+        numa = None
     import modules
     from pvcnn_b200 import _lib
     torch.manual_seed(SEED)
@@ -128,15 +132,17 @@ def run_ours(args):
     feats = feats_h.to(dev).requires_grad_(True)
     coords, gout = coords_h.to(dev), gout_h.to(dev)
     from pvcnn_b200.parallel import GradBucket
-    bucket = GradBucket(params, dev)
+    # p.grad of every parameter is a view of ONE flat fp32 buffer; the fused backward writes into it directly
+    bucket = GradBucket(params, dev).attach(m)
 
     def step(f, c, go):
-        for p in params:
-            p.grad = None
+        bucket.zero()   # replaces `p.grad = None` (the fused block overwrites its gradients, nothing to clear)
         f.grad = None
         out, _ = m((f, c))
         out.backward(go)
-        bucket.all_reduce_mean()  # ONE collective: flat fp32 gradient bucket over NCCL / NVLink (no-op at N=1)
+        # ONE collective per step: NCCL all-reduce (AVG) of the flat bucket, launched inside the backward right after the
+        # last parameter gradient and overlapped with the input-gradient kernels; finish() orders the stream behind it
+        bucket.finish()
         return out
 
     # L2 hygiene: the step streams > 2 GB of activations through a 126 MB L2, so consecutive steps
@@ -254,6 +260,17 @@ def run_ours(args):
                            "precision": prec, "activity_skipping": sparse == "1"}
         os.environ["PVCNN_B200_PRECISION"] = args.precision
         os.environ.pop("PVCNN_B200_SPARSE", None)
+        if world > 1 and not strong and B % world == 0:
+            # strong scaling next to the (default) weak number: the SAME global batch of 16 clouds sharded over the ranks
+            bs = B // world
+            fs, cs, gs_ = [t[rank * bs:(rank + 1) * bs].contiguous().to(dev) for t in full]
+            fs.requires_grad_(True)
+            f_keep, c_keep, g_keep = feats, coords, gout
+            feats, coords, gout = fs, cs, gs_
+            t_ms = timed(max(5, args.steps // 2), 3)
+            feats, coords, gout = f_keep, c_keep, g_keep
+            modes["strong_scaling"] = {"global_batch": B, "per_gpu_batch": bs, "ms_per_step": t_ms,
+                                       "value": B * N / t_ms * 1e3, "unit": "points/s"}
 
     extra = {}
     if rank == 0 and world == 1 and not minimal:
@@ -268,7 +285,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "single PVConv(64,64,k=3,R=32) block, train mode, fwd+bwd, B=%d/GPU N=4096%s" % (
                            bl, " (global B=16 sharded)" if strong else ""),
-                       "parallelism": "dp%d" % world, "precision": args.precision,
+                       "parallelism": "dp%d" % world, "precision": args.precision, "numa_node": numa,
                        "l2": "activations (>2 GB/step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": world * bl * N / ms_e2e * 1e3, "unit": "points/s", "ms_per_step": ms_e2e,

@@ -282,6 +282,19 @@ PVCNN_API int pvcnn_mlp_layer_backward(long long rows, int cin, int cout, int np
                                        const float *x_lo, const float *w, const float *y, const float *coef,
                                        float *wprep, float *partials, float *sums, float *gy, float *gy_lo, float *gx,
                                        float *dw, float *dbias, float *dgamma, float *dbeta, void *stream);
+/* model-level glue: channel concatenation written straight into channels-last rows (the 1472-channel
+ * torch.cat + repeat of models/s3dis/pvcnn.py:44-46 never exists in [B,C,N] form); src_n == 1 broadcasts a per-cloud
+ * vector over the points.  pvcnn_cl_slice_to_points is its gradient (and the generic [rows] -> [B,C,N] slice reader). */
+PVCNN_API int pvcnn_cat_to_cl(int b, int c, int n, int src_n, const float *x, int ld, int col0, float *rows,
+                              float *rows_lo, void *stream);
+PVCNN_API int pvcnn_cl_slice_to_points(int b, int c, int n, const float *rows, int ld, int col0, float *x, void *stream);
+/* plain 1x1 convolution on channels-last rows (a classifier's last layer, models/utils.py:43: no BatchNorm / ReLU):
+ * y = x W^T + bias on igemm_conv_kernel; backward: dw (conv_wgrad_kernel), dbias (column sums), gx (may be NULL) */
+PVCNN_API int pvcnn_linear_cl_forward(long long rows, int cin, int cout, int npass, const float *x, const float *x_lo,
+                                      const float *w, const float *bias, float *wprep, float *y, void *stream);
+PVCNN_API int pvcnn_linear_cl_backward(long long rows, int cin, int cout, int npass, const float *gy, const float *gy_lo,
+                                       const float *x, const float *x_lo, const float *w, float *wprep, float *partials,
+                                       float *gx, float *dw, float *dbias, void *stream);
 /* modules/ball_query.py:16-30 (grouping + centre subtraction + concat) with channels-last output rows
  * [b*m*u, pad4(3+c)] feeding pvcnn_mlp_layer_forward directly: the reference's [B,3+C,M,U] is never materialised */
 PVCNN_API int pvcnn_group_concat_cl(int b, int c, int n, int m, int u, const float *points_coords,
@@ -290,6 +303,14 @@ PVCNN_API int pvcnn_group_concat_cl(int b, int c, int n, int m, int u, const flo
 PVCNN_API int pvcnn_group_concat_cl_grad(int b, int c, int n, int m, int u, const float *grad_rows, const int *indices,
                                          float *grad_features, float *grad_points_coords, float *grad_centers_coords,
                                          void *stream);
+
+/* Same as pvcnn_pvconv_backward, split for data-parallel training: phase 1 = every kernel that produces a parameter
+ * gradient (ends with the conv1 weight gradient), phase 2 = the input gradient (conv1 data gradient + scatter to the
+ * points); phase 0 = both.  The caller launches its single gradient all-reduce between the phases (pvcnn_b200/parallel.py)
+ * so the collective overlaps phase 2. */
+PVCNN_API int pvcnn_pvconv_backward_phase(const pvcnn_pvconv_desc *d, const float *grad_out,
+                                          const pvcnn_pvconv_params *prm, const pvcnn_pvconv_ws *ws,
+                                          float *grad_features, const pvcnn_pvconv_grads *grads, int phase, void *stream);
 
 #ifdef __cplusplus
 }

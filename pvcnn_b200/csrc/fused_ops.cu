@@ -23,8 +23,6 @@ __device__ __forceinline__ float4 tf32_lo4(float4 v) {
   return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
 __device__ __forceinline__ float leaky(float z, float slope) { return z > 0.0f ? z : z * slope; }
-__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
 #define PVB_TRY_LAUNCH(expr)     \
   do {                           \
@@ -160,42 +158,6 @@ int launch_grid_lo_at_points(int b, int n, int r3, int cp, const int *ind, const
   PVB_LAUNCH(grid_lo_at_points_kernel, grid_for(total, 256, kNumSMs * 16), 256, 0, s, n, r3, cp, total, ind, grid,
              grid_lo);
   return 0;
-}
-
-// --------------------------------------------------------------------------------------------
-// Column reductions over [rows, cp]: thread -> (channel quad c4 = t % cp4, row lane = t / cp4).
-// --------------------------------------------------------------------------------------------
-constexpr int RED_THREADS = 256;
-constexpr int RED_MAX_BLOCKS = kNumSMs * 4;
-
-template <int NSETS, typename F>
-__device__ __forceinline__ void column_reduce(long long rows, int cp, float *partials, F &&body,
-                                              long long row_begin = 0, long long part_block = -1) {
-  __shared__ float4 red[NSETS][RED_THREADS];
-  const int cp4 = cp >> 2;
-  const int rl = RED_THREADS / cp4;  // row lanes (cp4 <= 256)
-  const int c4 = threadIdx.x % cp4, lane_r = threadIdx.x / cp4;
-  float4 acc[NSETS];
-#pragma unroll
-  for (int k = 0; k < NSETS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (part_block < 0) part_block = blockIdx.x;
-  if (lane_r < rl)
-    for (long long r = (long long)blockIdx.x * rl + lane_r; r < rows; r += (long long)gridDim.x * rl)
-      body(row_begin + r, c4, acc);
-#pragma unroll
-  for (int k = 0; k < NSETS; ++k) red[k][threadIdx.x] = acc[k];
-  __syncthreads();
-  if (threadIdx.x < cp4) {
-#pragma unroll
-    for (int k = 0; k < NSETS; ++k) {
-      float4 s = red[k][threadIdx.x];
-      for (int j = 1; j < rl; ++j) {
-        const float4 v = red[k][threadIdx.x + j * cp4];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      st4(partials + ((size_t)part_block * NSETS + k) * cp + threadIdx.x * 4, s);
-    }
-  }
 }
 
 __global__ void __launch_bounds__(RED_THREADS) bn_stats_kernel(long long rows, int cp, const float *__restrict__ y,

@@ -42,6 +42,61 @@ __global__ void __launch_bounds__(256) cl_to_points_kernel(int c, int n, int cp,
   }
 }
 
+// Channel concatenation written straight into channels-last rows (model-level glue: the 1472-channel `torch.cat` of
+// models/s3dis/pvcnn.py:44-46 and its `repeat` of the cloud feature never exist in [B,C,N] form):
+//   out[(b, i)][col0 + ch] = x[b][ch][src_n == 1 ? 0 : i]      (+ lo), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) cat_to_cl_kernel(int c, int n, int src_n, int ld, int col0,
+                                                        const float *__restrict__ x, float *__restrict__ out,
+                                                        float *__restrict__ out_lo) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = c0 + ty + 8 * j, i = n0 + tx;
+    tile[ty + 8 * j][tx] = (cc < c && i < n) ? x[((size_t)b * c + cc) * src_n + (src_n == 1 ? 0 : i)] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = n0 + ty + 8 * j, cc = c0 + tx;
+    if (p < n && cc < c) {
+      const float v = tile[tx][ty + 8 * j];
+      const size_t o = ((size_t)b * n + p) * ld + col0 + cc;
+      out[o] = v;
+      if (out_lo) out_lo[o] = __fsub_rn(v, __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
+    }
+  }
+}
+
+// inverse: x[b][ch][i] = rows[(b, i)][col0 + ch]
+__global__ void __launch_bounds__(256) cl_slice_to_points_kernel(int c, int n, int ld, int col0,
+                                                                 const float *__restrict__ rows, float *__restrict__ x) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int p = n0 + ty + 8 * j, cc = c0 + tx;
+    tile[ty + 8 * j][tx] = (p < n && cc < c) ? rows[((size_t)b * n + p) * ld + col0 + cc] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cc = c0 + ty + 8 * j, i = n0 + tx;
+    if (cc < c && i < n) x[((size_t)b * c + cc) * n + i] = tile[tx][ty + 8 * j];
+  }
+}
+
+// column sums of [rows, cp] (bias gradient of a plain linear layer)
+__global__ void __launch_bounds__(RED_THREADS) colsum_kernel(long long rows, int cp, const float *__restrict__ g,
+                                                             float *__restrict__ partials) {
+  column_reduce<1>(rows, cp, partials, [&](long long r, int c4, float4 *acc) {
+    const float4 v = ldg_stream4(g + (size_t)r * cp + c4 * 4);
+    acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+  });
+}
+
 // relu(bn(y)) followed by max over groups of U consecutive rows; one CTA per (group, row segment).
 // thread -> (channel quad c4 = t % cp4, row lane = t / cp4); partial (max, argmax) per segment, combined below.
 constexpr int PL_THREADS = 256;
@@ -251,6 +306,62 @@ int pvcnn_group_concat_cl_grad(int b, int c, int n, int m, int u, const float *g
   const int cp = mp_pad4(c + 3);
   PVB_LAUNCH(group_concat_cl_grad_kernel, dim3(ceil_div((long long)m * u, 32), ceil_div(c + 3, 32), b), 256, 0, s, c, n, m,
              u, cp, grad_rows, indices, grad_features, grad_points_coords, grad_centers_coords);
+  return 0;
+}
+
+/* channel concatenation in channels-last form: source x [b,c,n] (or [b,c,1]: broadcast over the points, src_n = 1) ->
+ * columns [col0, col0+c) of rows [b*n, ld] (+ lo rows, may be NULL).  Pad columns of the destination are the caller's
+ * to zero. */
+int pvcnn_cat_to_cl(int b, int c, int n, int src_n, const float *x, int ld, int col0, float *rows, float *rows_lo,
+                    void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && (src_n == n || src_n == 1) && x && rows && ld >= col0 + c && col0 >= 0);
+  PVB_LAUNCH(cat_to_cl_kernel, dim3(ceil_div(n, 32), ceil_div(c, 32), b), 256, 0, stream, c, n, src_n, ld, col0, x, rows,
+             rows_lo);
+  return 0;
+}
+
+int pvcnn_cl_slice_to_points(int b, int c, int n, const float *rows, int ld, int col0, float *x, void *stream) {
+  PVB_CHECK_ARG(b > 0 && c > 0 && n > 0 && x && rows && ld >= col0 + c && col0 >= 0);
+  PVB_LAUNCH(cl_slice_to_points_kernel, dim3(ceil_div(n, 32), ceil_div(c, 32), b), 256, 0, stream, c, n, ld, col0, rows, x);
+  return 0;
+}
+
+/* plain 1x1 convolution (no BatchNorm / ReLU: the classifier's last layer, models/utils.py:43) on channels-last rows */
+int pvcnn_linear_cl_forward(long long rows, int cin, int cout, int npass, const float *x, const float *x_lo,
+                            const float *w, const float *bias, float *wprep, float *y, void *stream) {
+  PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3) && x && w && wprep && y);
+  PVB_CHECK_ARG(npass == 1 || x_lo);
+  const int ci = mp_pad4(cin), co = mp_pad4(cout);
+  const long long nf = (long long)cout * mp_ld32(cin);
+  MLP_TRY(pvcnn_conv_weight_prep(cout, cin, 1, 0, mp_ld32(cin), w, wprep, wprep + nf, stream));
+  if (co != cout) MLP_TRY(launch_memset_f32(y, rows * co, (cudaStream_t)stream));
+  return igemm_launch(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, wprep, wprep + nf, mp_ld32(cin), bias, y, co, npass,
+                      (cudaStream_t)stream);
+}
+
+int pvcnn_linear_cl_backward(long long rows, int cin, int cout, int npass, const float *gy, const float *gy_lo,
+                             const float *x, const float *x_lo, const float *w, float *wprep, float *partials,
+                             float *gx, float *dw, float *dbias, void *stream) {
+  PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3));
+  PVB_CHECK_ARG(gy && x && w && wprep && partials && dw && (npass == 1 || (gy_lo && x_lo)));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ci = mp_pad4(cin), co = mp_pad4(cout);
+  PVB_CHECK_ARG(co / 4 <= RED_THREADS);
+  if (dbias) {
+    const int rl = RED_THREADS / (co / 4);
+    long long g = (rows + rl * 8 - 1) / (rl * 8);
+    if (g > RED_MAX_BLOCKS) g = RED_MAX_BLOCKS;
+    PVB_LAUNCH(colsum_kernel, (int)g, RED_THREADS, 0, s, rows, co, gy, partials);
+    MLP_TRY(launch_reduce_partials((int)g, co, partials, partials + (size_t)g * co, s));
+    PVB_CUDA(cudaMemcpyAsync(dbias, partials + (size_t)g * co, sizeof(float) * (size_t)cout, cudaMemcpyDeviceToDevice, s));
+  }
+  MLP_TRY(wgrad_launch(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, gy, gy_lo, co, dw, npass, s, nullptr, nullptr, nullptr, nullptr));
+  if (gx) {
+    const long long nd = (long long)cin * mp_ld32(cout);
+    MLP_TRY(pvcnn_conv_weight_prep(cout, cin, 1, 1, mp_ld32(cout), w, wprep, wprep + nd, stream));
+    if (ci != cin) MLP_TRY(launch_memset_f32(gx, rows * ci, s));
+    MLP_TRY(igemm_launch(1, 1, 1, (int)rows, cout, cin, 1, gy, gy_lo, co, wprep, wprep + nd, mp_ld32(cout), nullptr, gx, ci, npass, s));
+  }
   return 0;
 }
 

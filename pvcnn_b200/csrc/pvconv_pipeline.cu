@@ -269,7 +269,13 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
 int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, const pvcnn_pvconv_params *prm,
                           const pvcnn_pvconv_ws *ws, float *grad_features, const pvcnn_pvconv_grads *gr,
                           void *stream) {
-  PVB_CHECK_ARG(d && grad_out && prm && ws && grad_features && gr && d->training);
+  return pvcnn_pvconv_backward_phase(d, grad_out, prm, ws, grad_features, gr, 0, stream);
+}
+
+int pvcnn_pvconv_backward_phase(const pvcnn_pvconv_desc *d, const float *grad_out, const pvcnn_pvconv_params *prm,
+                                const pvcnn_pvconv_ws *ws, float *grad_features, const pvcnn_pvconv_grads *gr,
+                                int phase, void *stream) {
+  PVB_CHECK_ARG(d && grad_out && prm && ws && grad_features && gr && d->training && phase >= 0 && phase <= 2);
   cudaStream_t s = (cudaStream_t)stream;
   const int b = d->b, n = d->n, r = d->r, r3 = r * r * r;
   const int ci = pad4(d->cin), co = pad4(d->cout);
@@ -287,6 +293,7 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   int nblk = 0;
   const size_t cb = sizeof(float) * (size_t)d->cout;
 
+  if (phase != 2) {  // ---- phase 1: everything that produces a PARAMETER gradient (the last one is dW1)
   // 1. per-point stage: point-branch ReLU mask + reductions; voxel-branch scatter (x leaky') + reductions
   PVB_TRY(launch_memset_f32(ws->d2, Mv * co, s));
   SeBuf se{};
@@ -369,6 +376,10 @@ int pvcnn_pvconv_backward(const pvcnn_pvconv_desc *d, const float *grad_out, con
   PVB_TRY(wgrad_launch(b, r, r, r, d->cin, d->cout, 27, ws->g0, ws->g0_lo, ci, ws->gy1, ws->gy1_lo, co, gr->w1,
                        d->npass, s, sparse ? sp.wg1 : nullptr, sparse ? sp.counts + 3 : nullptr, &wbz, &wby));
   if (sparse) PVB_CHECK_ARG(wbz == sp.wg_bz && wby == sp.wg_by);
+  }  // phase 1
+  if (phase == 1) return 0;
+  // ---- phase 2: the input gradient (conv1 dgrad + scatter back to the points); a data-parallel caller launches its
+  //      gradient all-reduce between the phases so that it overlaps these kernels
   float *gg0 = ws->d2;
   if (sparse) {
     PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cin, ws->gy1, co, wp + W.w1d, wp + W.w1d + W.n1d, ld32(d->cout),

@@ -201,7 +201,7 @@ class _PVConvFused(Function):
             for bn in bns:
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
-        ctx.plan, ctx.prm, ctx.keep, ctx.desc = plan, prm, keep, desc
+        ctx.plan, ctx.prm, ctx.keep, ctx.desc, ctx.module = plan, prm, keep, desc, module
         ctx.shapes = [None if t is None else t.shape
                       for t in (w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1, se_w2)]
         ctx.in_shape = features.shape
@@ -217,16 +217,32 @@ class _PVConvFused(Function):
         dev = grad_out.device
         grad_out = grad_out.contiguous().float()
         plan.add_backward_scratch()
-        grads = [None if s is None else torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        nparam = 14 if ctx.shapes[12] is not None else 12  # SE weights are optional inputs of forward()
+        # data-parallel bucket attached (pvcnn_b200/parallel.py): the kernels write the parameter gradients straight into
+        # the flat all-reduce buffer (p.grad is a view of it) and autograd gets None for them
+        views = getattr(ctx.module, "_pvcnn_grad_views", None)
+        direct = views is not None and len(views) == nparam and views[0].device == dev
+        if direct:
+            grads = list(views) + [None] * (14 - nparam)
+        else:
+            grads = [None if s is None else torch.empty(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
         gs = Grads()
         for k, t in zip(_GRAD_FIELDS, grads):
             setattr(gs, k, _ptr(t))
         gfeat = torch.empty(ctx.in_shape, dtype=torch.float32, device=dev)
-        _poison([gfeat] + grads)
+        _poison([gfeat] + ([] if direct else grads))
         ws = plan.struct()
+        if direct:
+            # phase 1 ends with the last parameter gradient; the bucket may launch its all-reduce on a side stream now,
+            # overlapping phase 2 (conv1 data gradient + scatter back to the points)
+            _lib.call("pvcnn_pvconv_backward_phase", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm),
+                      ctypes.byref(ws), gfeat, ctypes.byref(gs), 1, device=dev)
+            ctx.module._pvcnn_bucket.module_grads_ready(ctx.module)
+            _lib.call("pvcnn_pvconv_backward_phase", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm),
+                      ctypes.byref(ws), gfeat, ctypes.byref(gs), 2, device=dev)
+            return (gfeat, None, None, None, *([None] * nparam))
         _lib.call("pvcnn_pvconv_backward", ctypes.byref(desc), grad_out, ctypes.byref(ctx.prm), ctypes.byref(ws),
                   gfeat, ctypes.byref(gs), device=dev)
-        nparam = 14 if ctx.shapes[12] is not None else 12  # SE weights are optional inputs of forward()
         return (gfeat, None, None, None, *grads[:nparam])
 
 

@@ -263,3 +263,126 @@ def sa_branch(layers, coords, centers, features, indices):
     pooled = mlp_cl(layers, rows, lo if lo.numel() else None, pool_u=u)
     cout = list(layers)[-3].out_channels
     return _FromCL.apply(pooled, b, cout, m)
+
+
+class _CatCL(Function):
+    """torch.cat(tensors, dim=1) of [B,C_i,N] (or [B,C_i,1], broadcast over N) written straight into channels-last rows
+    [B*N, pad4(sum C_i)] (+ lo).  Model-level glue of models/s3dis/pvcnn.py:44-46 / models/shapenet/pvcnn.py:40-42."""
+
+    @staticmethod
+    def forward(ctx, n, want_lo, *tensors):
+        b = tensors[0].shape[0]
+        dev = tensors[0].device
+        widths = [t.shape[1] for t in tensors]
+        ctot = sum(widths)
+        ld = _pad4(ctot)
+        rows = torch.empty((b * n, ld), dtype=torch.float32, device=dev)
+        lo = torch.empty_like(rows) if want_lo else None
+        if ld != ctot:
+            rows[:, ctot:].zero_()
+            if lo is not None:
+                lo[:, ctot:].zero_()
+        col = 0
+        for t in tensors:
+            t = t.contiguous().float()
+            _lib.call("pvcnn_cat_to_cl", b, t.shape[1], n, t.shape[2], t, ld, col, rows, lo, device=dev)
+            col += t.shape[1]
+        ctx.meta = (b, n, ld, widths, [t.shape[2] for t in tensors])
+        if lo is None:
+            lo = rows.new_empty(0)
+        ctx.mark_non_differentiable(lo)
+        return rows, lo
+
+    @staticmethod
+    def backward(ctx, g, _glo):
+        b, n, ld, widths, src_ns = ctx.meta
+        g = g.contiguous()
+        outs = []
+        col = 0
+        for i, (c, sn) in enumerate(zip(widths, src_ns)):
+            if ctx.needs_input_grad[2 + i]:
+                gx = torch.empty((b, c, n), dtype=torch.float32, device=g.device)
+                _lib.call("pvcnn_cl_slice_to_points", b, c, n, g, ld, col, gx, device=g.device)
+                outs.append(gx.sum(dim=2, keepdim=True) if sn == 1 else gx)
+            else:
+                outs.append(None)
+            col += c
+        return (None, None, *outs)
+
+
+def cat_cl(tensors, n):
+    """-> (rows [B*N, pad4(sum C)], lo | None)"""
+    rows, lo = _CatCL.apply(n, precision_passes() > 1, *tensors)
+    return rows, (lo if lo.numel() else None)
+
+
+class _LinearCL(Function):
+    """Conv1d(k=1) without BatchNorm / ReLU on channels-last rows (the classifier's last layer)."""
+
+    @staticmethod
+    def forward(ctx, x, x_lo, w, bias):
+        lib = _lib_sizes()
+        dev = x.device
+        rows = x.shape[0]
+        cout, cin = w.shape[0], w.shape[1]
+        npass = precision_passes()
+        if npass > 1 and x_lo is None:
+            from . import dense
+            x_lo = dense.split_tf32(x, want_hi=False)[1]
+        y = torch.empty((rows, _pad4(cout)), dtype=torch.float32, device=dev)
+        wprep = _scratch("mlp_wprep", lib.pvcnn_mlp_wprep_floats(cin, cout), dev)
+        _lib.call("pvcnn_linear_cl_forward", _LL(rows), cin, cout, npass, x, x_lo, w.detach(),
+                  None if bias is None else bias.detach(), wprep, y, device=dev)
+        ctx.save_for_backward(x, x_lo, w.detach())
+        ctx.meta = (rows, cin, cout, npass, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib_sizes()
+        x, x_lo, w = ctx.saved_tensors
+        rows, cin, cout, npass, has_bias = ctx.meta
+        dev = gy.device
+        gy = gy.contiguous()
+        gy_lo = None
+        if npass > 1:
+            from . import dense
+            gy_lo = dense.split_tf32(gy, want_hi=False)[1]
+        need_gx = ctx.needs_input_grad[0]
+        gx = torch.empty((rows, _pad4(cin)), dtype=torch.float32, device=dev) if need_gx else None
+        dw = torch.empty_like(w)
+        db = torch.empty(cout, dtype=torch.float32, device=dev) if has_bias else None
+        wprep = _scratch("mlp_wprep", lib.pvcnn_mlp_wprep_floats(cin, cout), dev)
+        partials = _scratch("mlp_partials", lib.pvcnn_mlp_partials_floats(cout), dev)
+        _lib.call("pvcnn_linear_cl_backward", _LL(rows), cin, cout, npass, gy, gy_lo, x, x_lo, w, wprep, partials, gx, dw,
+                  db, device=dev)
+        return gx, None, dw, db
+
+
+def head_cl(seq, rows, lo, b, n):
+    """Run a per-point head -- nn.Sequential of SharedMLP | nn.Dropout | nn.Conv1d(k=1) (models/utils.py:15-45) -- on
+    channels-last rows and return [B, Cout, N].  Returns None if the head holds anything else (caller falls back)."""
+    from .nn.shared_mlp import SharedMLP
+    mods = list(seq)
+    for m in mods:
+        ok = isinstance(m, torch.nn.Dropout) or (isinstance(m, SharedMLP) and native_supported(m.layers)) or (
+            isinstance(m, torch.nn.Conv1d) and m.kernel_size == (1,) and m.groups == 1 and m.stride == (1,))
+        if not ok:
+            return None
+    x, xl, cout = rows, lo, None
+    for m in mods:
+        if isinstance(m, torch.nn.Dropout):
+            x = torch.nn.functional.dropout(x, m.p, m.training)   # element-wise i.i.d.: layout-agnostic
+            xl = None
+        elif isinstance(m, SharedMLP):
+            if xl is None and precision_passes() > 1:
+                from . import dense
+                xl = dense.split_tf32(x.contiguous(), want_hi=False)[1]
+            x = mlp_cl(m.layers, x, xl)
+            xl = None
+            cout = list(m.layers)[-3].out_channels
+        else:
+            x = _LinearCL.apply(x, xl, m.weight, m.bias)
+            xl = None
+            cout = m.out_channels
+    return _FromCL.apply(x, b, cout, n)

@@ -29,9 +29,21 @@ class PointNetAModule(nn.Module):
 
     def forward(self, inputs):
         features, coords = inputs
+        origin = torch.zeros((coords.size(0), 3, 1), device=coords.device)
+        from .shared_mlp import native_mlp_enabled
+        if features.is_cuda and native_mlp_enabled():
+            from .. import mlp as _mlp
+            if all(_mlp.native_supported(m.layers) for m in self.mlps):
+                # features (+ coordinates) go side by side into channels-last rows ONCE, the tensor-core MLP runs on them,
+                # and the max over ALL points is folded into the last layer's BatchNorm pass (segmented over the chip):
+                # neither the concat nor the [B, C', N] activation is written
+                b, _, n = features.shape
+                rows, lo = _mlp.cat_cl([features, coords] if self.include_coordinates else [features], n)
+                pooled = [_mlp._FromCL.apply(_mlp.mlp_cl(m.layers, rows, lo, pool_u=n), b,
+                                             list(m.layers)[-3].out_channels, 1) for m in self.mlps]
+                return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), origin
         if self.include_coordinates:
             features = torch.cat([features, coords], dim=1)
-        origin = torch.zeros((coords.size(0), 3, 1), device=coords.device)
         pooled = [mlp(features).max(dim=-1, keepdim=True).values for mlp in self.mlps]
         return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), origin
 
@@ -91,6 +103,16 @@ class PointNetFPModule(nn.Module):
         points_coords, centers_coords, centers_features = inputs[:3]
         skip = inputs[3] if len(inputs) > 3 else None
         x = F.nearest_neighbor_interpolate(points_coords, centers_coords, centers_features)
+        from .shared_mlp import native_mlp_enabled
+        if x.is_cuda and native_mlp_enabled():
+            from .. import mlp as _mlp
+            if _mlp.native_supported(self.mlp.layers):
+                # interpolated features and the skip connection are written side by side into channels-last rows that
+                # feed the tensor-core MLP directly (no [B, C1+C2, N] concat, no separate layout conversion)
+                b, _, n = x.shape
+                rows, lo = _mlp.cat_cl([x] if skip is None else [x, skip], n)
+                z = _mlp.mlp_cl(self.mlp.layers, rows, lo)
+                return _mlp._FromCL.apply(z, b, list(self.mlp.layers)[-3].out_channels, n), points_coords
         if skip is not None:
             x = torch.cat([x, skip], dim=1)
         return self.mlp(x), points_coords

@@ -13,6 +13,20 @@ import torch.nn as nn
 
 from . import functional as F
 from .nn import PVConv, SharedMLP, PointNetAModule, PointNetSAModule, PointNetFPModule
+from .nn.shared_mlp import native_mlp_enabled
+
+
+def _classify(head, taps, n):
+    """cat(taps, dim=1) -> per-point head.  On CUDA the concatenation is written straight into channels-last rows
+    (broadcast taps [B,C,1] are expanded on the fly) and the whole head runs on them (pvcnn_b200/mlp.py: cat_cl, head_cl):
+    neither the [B, sum C, N] concat nor the repeated cloud feature is materialised."""
+    if taps[0].is_cuda and native_mlp_enabled():
+        from . import mlp
+        rows, lo = mlp.cat_cl(taps, n)
+        out = mlp.head_cl(head, rows, lo, taps[0].shape[0], n)
+        if out is not None:
+            return out
+    return head(torch.cat([t.expand(-1, -1, n) for t in taps], dim=1))
 
 
 def _scaled(width, c):
@@ -79,8 +93,8 @@ class S3DISPVCNN(nn.Module):
             x, _ = layer((x, coords))
             taps.append(x)
         cloud = self.cloud_features(x.max(dim=-1).values)
-        taps.append(cloud.unsqueeze(-1).expand(-1, -1, coords.size(-1)))
-        return self.classifier(torch.cat(taps, dim=1))
+        taps.append(cloud.unsqueeze(-1))
+        return _classify(self.classifier, taps, coords.size(-1))
 
 
 class ShapeNetPVCNN(nn.Module):
@@ -107,8 +121,8 @@ class ShapeNetPVCNN(nn.Module):
         for layer in self.point_features:
             x, _ = layer((x, coords))
             taps.append(x)
-        taps.append(x.max(dim=-1, keepdim=True).values.expand(-1, -1, n))
-        return self.classifier(torch.cat(taps, dim=1))
+        taps.append(x.max(dim=-1, keepdim=True).values)
+        return _classify(self.classifier, taps, n)
 
 
 class S3DISPVCNN2(nn.Module):
@@ -167,7 +181,7 @@ class S3DISPVCNN2(nn.Module):
         feat_stack[0] = x[:, 3:, :].contiguous()
         for i, stage in enumerate(self.fp_layers):
             feats, coords = stage((coord_stack[-1 - i], coords, feats, feat_stack[-1 - i]))
-        return self.classifier(feats)
+        return _classify(self.classifier, [feats], feats.size(-1))
 
 
 class _InstanceSegPVCNN(nn.Module):
@@ -189,11 +203,11 @@ class _InstanceSegPVCNN(nn.Module):
     def forward(self, inputs):
         x = inputs["features"]
         n = x.size(-1)
-        one_hot = inputs["one_hot_vectors"].unsqueeze(-1).expand(-1, -1, n)
+        one_hot = inputs["one_hot_vectors"].unsqueeze(-1)
         point, coords = self.point_features((x, x[:, :3, :]))
         cloud, _ = self.cloud_features((point, coords))
-        cloud = cloud.max(dim=-1, keepdim=True).values.expand(-1, -1, n)
-        return self.classifier(torch.cat([one_hot, point, cloud], dim=1))
+        cloud = cloud.max(dim=-1, keepdim=True).values
+        return _classify(self.classifier, [one_hot, point, cloud], n)
 
 
 class _CenterRegression(nn.Module):

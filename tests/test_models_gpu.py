@@ -75,6 +75,9 @@ def test_shapenet_train_step_native_vs_comparison_arm():
     torch.manual_seed(0)
     model, spec = zoo.build("shapenet_c0p25_train")
     model = model.cuda().train()
+    for mod in model.modules():          # the two arms would draw different dropout masks (different tensor layouts)
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
     g = torch.Generator().manual_seed(1588147245)
     b = 8
     x = zoo.synthetic_input(spec, g, batch=b).cuda()

@@ -42,6 +42,18 @@ def _worker(rank, world, port, out):
             want = sum(gathered[r][i] for r in range(world)) / world
             assert np.allclose(g.numpy(), want, rtol=1e-6, atol=1e-7)
         w0 = [p.detach().clone() for p in m.parameters()]
+    # round-2 path: p.grad ARE views of the flat buffer (autograd accumulates into them), zero() + finish() per step
+    b2 = GradBucket(m.parameters()).attach(m)
+    for _ in range(2):
+        b2.zero()
+        ((m(xs) - ys) ** 2).sum().backward()
+        b2.finish()
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b2.params, b2.views))
+    if rank == 0:
+        import numpy as np
+        for i, p in enumerate(m.parameters()):
+            want = sum(gathered[r][i] for r in range(world)) / world
+            assert np.allclose(p.grad.numpy(), want, rtol=1e-5, atol=1e-6)
         out.put(("ok", len(bucket.flat), float(sum(w.abs().sum() for w in w0))))
     dist.barrier()
     dist.destroy_process_group()
