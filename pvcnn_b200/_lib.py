@@ -45,44 +45,41 @@ def launch_count():
     return int(load().pvcnn_launch_count())
 
 
-def _arg(a):
-    import torch
-    if isinstance(a, torch.Tensor):
-        return ctypes.c_void_p(a.data_ptr())
-    if a is None:
-        return ctypes.c_void_p(0)
-    if isinstance(a, float):
-        return ctypes.c_float(a)
-    if isinstance(a, bool):
-        return ctypes.c_int(int(a))
-    if isinstance(a, int):
-        return ctypes.c_int(a)
-    return a
-
-
-def _raw_stream(index):
-    import torch
-    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
-    return get(index) if get is not None else torch.cuda.current_stream(index).cuda_stream
+_FN = {}
+_VOID0 = ctypes.c_void_p(0)
 
 
 def call(name, *args, device=None):
-    """Invoke `name(*args, stream)` on the current CUDA stream of `device`; raise on error."""
+    """Invoke `name(*args, stream)` on the current CUDA stream of `device`; raise on error.
+    (Host-side cost matters for the small point ops, which are launch-bound: function lookup is cached and the
+    argument conversion is a single pass.)"""
     import torch
-    fn = getattr(load(), name)
-    if device is None:
-        for a in args:
-            if isinstance(a, torch.Tensor):
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
+    Tensor = torch.Tensor
+    cargs = []
+    for a in args:
+        if isinstance(a, Tensor):
+            if device is None:
                 device = a.device
-                break
+            cargs.append(ctypes.c_void_p(a.data_ptr()))
+        elif a is None:
+            cargs.append(_VOID0)
+        elif isinstance(a, float):
+            cargs.append(ctypes.c_float(a))
+        elif isinstance(a, (bool, int)):
+            cargs.append(ctypes.c_int(int(a)))
+        else:
+            cargs.append(a)
     if device is None or device.type != "cuda":
         raise PvcnnError("%s: tensors must live on a CUDA device (the hot path has no CPU implementation)" % name)
-    index = device.index if device.index is not None else torch.cuda.current_device()
-    cargs = [_arg(a) for a in args]
-    if index == torch.cuda.current_device():   # common case: no device switch, ~10 us less host overhead per call
-        rc = fn(*cargs, ctypes.c_void_p(_raw_stream(index)))
+    cur = torch.cuda.current_device()
+    index = device.index if device.index is not None else cur
+    if index == cur:   # common case: no device switch
+        rc = fn(*cargs, ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(index)))
     else:
         with torch.cuda.device(index):
-            rc = fn(*cargs, ctypes.c_void_p(_raw_stream(index)))
+            rc = fn(*cargs, ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(index)))
     if rc != 0:
         raise PvcnnError("%s failed with code %d" % (name, rc))

@@ -76,9 +76,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
       acc_full[3], acc_empty[3];
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role branches (and everything
-  // computed inside them from uniform inputs) on the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool three = THREE;   // 3xTF32 (hi/lo split) or single-pass TF32: compile-time, so the MMA issue loop carries no dead path
   const uint32_t a_stage_bytes = p.a_bytes * (three ? 2u : 1u);
   const uint32_t b_stage_bytes = p.b_bytes * (three ? 2u : 1u);
@@ -149,14 +147,10 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    // The WHOLE warp walks the loop (barrier polls, descriptor arithmetic: warp-uniform, so it runs on the uniform datapath
-    // and feeds tcgen05.mma's uniform-register operands directly); only the MMA / commit instructions are predicated on
-    // the elected lane.  With the loop inside `if (elect_one())` every descriptor was built in vector registers and moved
-    // with R2UR (8 per tap), which is what bounded the issue rate.
-    {
-      const bool leader = elect_one();
-      const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
-      const int num_items = __shfl_sync(0xffffffffu, num_units * p.nblocks, 0);
+    // (Tried in r02: letting the whole warp walk this loop so that the descriptor arithmetic stays on the uniform datapath
+    //  and only the tcgen05.mma / commit are predicated on the elected lane -- it removes the R2UR moves but measured
+    //  slower in 3xTF32 mode (0.515 vs 0.490 ms dense) and equal in TF32 mode, so the single elected thread stays.)
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
       constexpr uint32_t dhi = desc_hi32(512, kH3LayoutSW64);
       // One elected thread issues every MMA of the CTA, and it is ISSUE-bound (ncu r02: tensor pipe 33-53 %, tensor-core
@@ -204,27 +198,25 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
                   const uint32_t ao = (uint32_t)(t + t9 / 3) * XS + (uint32_t)(t9 % 3) * YS + (uint32_t)ks * 2u;  // immediate
                   const uint32_t d = t == 0 ? d0 : d1;
                   const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;  // every chunk starts a fresh chain
-                  if (leader) {
-                    if (three) {
-                      // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
-                      mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                      mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_hi + b_lo_off + ks * 2u, dhi, idesc, 1u);
-                      mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
-                    } else {
-                      mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                    }
+                  if (three) {
+                    // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
+                    mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                    mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_hi + b_lo_off + ks * 2u, dhi, idesc, 1u);
+                    mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
+                  } else {
+                    mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
                   }
                 }
               }
-              if (leader) mma_commit(const_cast<uint64_t *>(done_bar));
+              mma_commit(const_cast<uint64_t *>(done_bar));
             }
-            if (leader) mma_commit(&acc_full[dz]);
+            mma_commit(&acc_full[dz]);
           }
-          if (leader) mma_commit(&a_empty[ast]);
+          mma_commit(&a_empty[ast]);
           if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
         }
       }
-      if (leader && p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = items_done; }
+      if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = items_done; }
     }
   } else if (warp >= 12) {
     // ================================ converters: lo = x - trunc_tf32(x) ================================

@@ -1122,6 +1122,10 @@ __global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by
   __syncthreads();
   const int cp4 = cp >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int tz_n = (r + bz - 1) / bz, ty_n = (r + by - 1) / by;
+  float4 ri[3], ra[3];  // interior (x, y) classes in registers: [z class] of the inactive-only / all-voxel sets
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ri[k] = ra[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int reg_c4 = -1;      // a lane always works on the same channel quad when cp4 <= 32
   for (long long kt = (long long)blockIdx.x * nwarp + warp; kt < n_kt; kt += (long long)gridDim.x * nwarp) {
     const bool inactive = !kt_active[kt];
     long long u = kt;
@@ -1159,13 +1163,33 @@ __global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by
             s1.x -= s2.x; s1.y -= s2.y; s1.z -= s2.z; s1.w -= s2.w;
           }
         }
-        for (int set = inactive ? 0 : 1; set < 2; ++set) {
-          float *a0 = acc + ((size_t)set * 27 + (cx * 3 + cy) * 3) * cp + c4 * 4;
-          float *a1 = a0 + cp, *a2 = a0 + 2 * cp;
-          atomicAdd(a0 + 0, s0.x); atomicAdd(a0 + 1, s0.y); atomicAdd(a0 + 2, s0.z); atomicAdd(a0 + 3, s0.w);
-          atomicAdd(a1 + 0, s1.x); atomicAdd(a1 + 1, s1.y); atomicAdd(a1 + 2, s1.z); atomicAdd(a1 + 3, s1.w);
-          atomicAdd(a2 + 0, s2.x); atomicAdd(a2 + 1, s2.y); atomicAdd(a2 + 2, s2.z); atomicAdd(a2 + 3, s2.w);
+        if (cx == 1 && cy == 1 && cp4 <= 32) {
+          // interior (x, y): ~88 % of the lines share the classes (1,1,*) -> keep them in registers (r02: the 12-24
+          // shared-memory atomics per lane and k-tile, not the 134 MB read, were what this kernel spent its time on)
+#define PVB_ACC4(d, v) d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+          if (inactive) { PVB_ACC4(ri[0], s0) PVB_ACC4(ri[1], s1) PVB_ACC4(ri[2], s2) }
+          PVB_ACC4(ra[0], s0) PVB_ACC4(ra[1], s1) PVB_ACC4(ra[2], s2)
+#undef PVB_ACC4
+          reg_c4 = c4;
+        } else {
+          for (int set = inactive ? 0 : 1; set < 2; ++set) {
+            float *a0 = acc + ((size_t)set * 27 + (cx * 3 + cy) * 3) * cp + c4 * 4;
+            float *a1 = a0 + cp, *a2 = a0 + 2 * cp;
+            atomicAdd(a0 + 0, s0.x); atomicAdd(a0 + 1, s0.y); atomicAdd(a0 + 2, s0.z); atomicAdd(a0 + 3, s0.w);
+            atomicAdd(a1 + 0, s1.x); atomicAdd(a1 + 1, s1.y); atomicAdd(a1 + 2, s1.z); atomicAdd(a1 + 3, s1.w);
+            atomicAdd(a2 + 0, s2.x); atomicAdd(a2 + 1, s2.y); atomicAdd(a2 + 2, s2.z); atomicAdd(a2 + 3, s2.w);
+          }
         }
+      }
+    }
+  }
+  if (reg_c4 >= 0) {  // flush the interior-class registers: one round of atomics per lane for the whole kernel
+    for (int set = 0; set < 2; ++set) {
+      const float4 *src = set == 0 ? ri : ra;
+      float *a0 = acc + ((size_t)set * 27 + (1 * 3 + 1) * 3) * cp + reg_c4 * 4;
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(a0 + k * cp + 0, src[k].x); atomicAdd(a0 + k * cp + 1, src[k].y);
+        atomicAdd(a0 + k * cp + 2, src[k].z); atomicAdd(a0 + k * cp + 3, src[k].w);
       }
     }
   }
