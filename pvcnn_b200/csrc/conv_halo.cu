@@ -17,6 +17,11 @@
 //       - TMEM chains are 54 MMAs long for ANY Cin (the tensor core truncates when it accumulates; partial sums
 //         are combined in round-to-nearest fp32 registers), so Cin is unbounded;
 //       - the final store of unit i overlaps the MMAs of unit i+1 (accumulators are already in registers);
+//   * because the z shift is applied in the epilogue, the three dz taps of a (dx,dy) pair read the SAME halo rows: their
+//     weight tiles are loaded as ONE box [3 taps x Cout x KC] and issued as ONE tcgen05.mma with N = 3 * Cout (192),
+//     whose TMEM columns are exactly [P_-1 | P_0 | P_+1].  The A operand -- 2/3 of a N=64 MMA's shared-memory bytes
+//     -- is fetched once per three taps, which moves the kernel from the tensor core's shared-memory operand pipe
+//     (r02 ncu: 62 % at N=64, the MMA issue loop saturated) onto the tensor pipe itself;
 //   * Cout > 64 runs as N-blocks of 64 (work item = (unit, n-block)); z extents that are not 8/16/32 are padded
 //     (R=12 -> BZ=16: the TMA box zero-fills rows z >= sz, the epilogue masks them).
 //   * `lo = x - trunc_tf32(x)` of the 3xTF32 split is computed in the kernel by 4 converter warps (once per chunk);
@@ -30,11 +35,12 @@ namespace pvb {
 using namespace umma;
 
 constexpr int H3_THREADS = 512;  // w0 TMA(A), w1 MMA, w2 TMEM alloc, w3 TMA(B), w4-11 epilogue (tile = (w-4)/4), w12-15 converters
-constexpr int H3_KC = 16;        // channels per chunk (64-byte rows, SWIZZLE_64B)
+// channels per chunk: 16 in single-pass TF32 mode (64-byte rows, SWIZZLE_64B), 8 in 3xTF32 mode (32-byte rows,
+// SWIZZLE_32B: hi + lo copies of a 3-deep halo ring and a 6-deep ring of 3-tap weight boxes then fit in 227 KB)
 constexpr int H3_TX = 2;         // output x-planes (tiles) per work item
 constexpr int H3_MAX_A = 4;      // halo ring depth (2 in 3xTF32 mode at R=32)
-constexpr int H3_MAX_B = 8;      // weight-tile ring depth
-constexpr uint32_t kH3LayoutSW64 = 4;
+constexpr int H3_MAX_B = 12;     // weight-box ring depth
+constexpr uint32_t kH3LayoutSW64 = 4, kH3LayoutSW32 = 6;
 
 struct Halo3Params {
   int nb, sx, sy, sz;
@@ -42,11 +48,12 @@ struct Halo3Params {
   int ty;                         // y rows per tile = 128 / bz
   int tiles_y, pairs_x;
   int num_units;                  // nb * pairs_x * tiles_y (dense walk)
-  int kchunks;                    // ceil(k / 16)
+  int kchunks;                    // ceil(k / KC)
+  int drain;                      // chunks accumulated in TMEM between two drains (chain <= ~108 MMAs per accumulator)
   int cout, nblocks, block_n;     // N-blocks of block_n (<= 64, multiple of 16) output channels
   int npass, ldo;
   int a_stages, b_stages;
-  uint32_t a_bytes, b_bytes;      // bytes of ONE copy (hi) of a halo / a weight tile
+  uint32_t a_bytes, b_bytes;      // bytes of ONE copy (hi) of a halo / a 3-tap weight box
   const float *bias;
   float *out;
   int *err;
@@ -67,13 +74,13 @@ __device__ __forceinline__ void h3_decode(const Halo3Params &p, int unit, int &x
   }
 }
 
-template <bool THREE, int BZ>
+template <bool THREE, int BZ, int KC>
 __global__ void __launch_bounds__(H3_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w_hi,
                      const __grid_constant__ CUtensorMap map_w_lo, const Halo3Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t a_full[H3_MAX_A], a_ready[H3_MAX_A], a_empty[H3_MAX_A], b_full[H3_MAX_B], b_empty[H3_MAX_B],
-      acc_full[3], acc_empty[3];
+      acc_full, acc_empty;
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,7 +104,8 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty, 256);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -117,30 +125,27 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
         for (int cc = 0; cc < p.kchunks; ++cc) {
           mbar_wait(&a_empty[ast], aph ^ 1, p.err, 21);
           mbar_arrive_expect_tx(&a_full[ast], p.a_bytes);
-          tma_load_5d(smem + (size_t)ast * a_stage_bytes, &map_a, &a_full[ast], cc * H3_KC, 0, y0 - 1, x0 - 1, b);
+          tma_load_5d(smem + (size_t)ast * a_stage_bytes, &map_a, &a_full[ast], cc * KC, 0, y0 - 1, x0 - 1, b);
           if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
         }
       }
     }
   } else if (warp == 3) {
-    // ================================ TMA producer: weight tiles (27 per chunk) ================================
+    // ================================ TMA producer: weight boxes (9 per chunk, 3 dz taps each) ================================
     if (elect_one()) {
       int bst = 0;
       uint32_t bph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int n0 = (item % p.nblocks) * p.block_n;
         for (int cc = 0; cc < p.kchunks; ++cc) {
-          for (int dz = 0; dz < 3; ++dz) {
-#pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {  // t9 = (dx+1)*3 + (dy+1); torch tap index = kx*9 + ky*3 + kz
-              const int tap = (t9 / 3) * 9 + (t9 % 3) * 3 + dz;
-              mbar_wait(&b_empty[bst], bph ^ 1, p.err, 22);
-              uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
-              mbar_arrive_expect_tx(&b_full[bst], b_stage_bytes);
-              tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * H3_KC, n0, tap);
-              if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * H3_KC, n0, tap);
-              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
-            }
+#pragma unroll 1
+          for (int t9 = 0; t9 < 9; ++t9) {  // t9 = (dx+1)*3 + (dy+1); torch tap index = t9*3 + (dz+1): the 3 dz taps are adjacent
+            mbar_wait(&b_empty[bst], bph ^ 1, p.err, 22);
+            uint8_t *sb = smem_b + (size_t)bst * b_stage_bytes;
+            mbar_arrive_expect_tx(&b_full[bst], b_stage_bytes);
+            tma_load_3d(sb, &map_w_hi, &b_full[bst], cc * KC, n0, t9 * 3);
+            if (three) tma_load_3d(sb + p.b_bytes, &map_w_lo, &b_full[bst], cc * KC, n0, t9 * 3);
+            if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
           }
         }
       }
@@ -151,69 +156,72 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
     //  and only the tcgen05.mma / commit are predicated on the elected lane -- it removes the R2UR moves but measured
     //  slower in 3xTF32 mode (0.515 vs 0.490 ms dense) and equal in TF32 mode, so the single elected thread stays.)
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32(128, p.block_n, 0, 0);
-      constexpr uint32_t dhi = desc_hi32(512, kH3LayoutSW64);
-      // One elected thread issues every MMA of the CTA, and it is ISSUE-bound (ncu r02: tensor pipe 33-53 %, tensor-core
-      // shared-memory pipe 49-62 %, no barrier stalls): every instruction next to a tcgen05.mma counts.  The halo
-      // geometry is a template parameter so that every tap's descriptor offset is an immediate:
-      //   rows are (x_local, y_local, z); 16-byte units: one row = 4, a y step = BZ * 4, an x step = (TY + 2) * BZ * 4
-      constexpr uint32_t YS = (uint32_t)BZ * (H3_KC * 4 / 16);
-      constexpr uint32_t XS = (uint32_t)(128 / BZ + 2) * YS;
       const uint32_t bn = (uint32_t)p.block_n;
+      const uint32_t idesc = make_idesc_tf32(128, 3 * p.block_n, 0, 0);   // N = [P_-1 | P_0 | P_+1]
+      constexpr uint32_t dhi = KC == 16 ? desc_hi32(512, kH3LayoutSW64) : desc_hi32(256, kH3LayoutSW32);
+      // One elected thread issues every MMA of the CTA; every instruction next to a tcgen05.mma counts.  The halo geometry
+      // is a template parameter so that every tap's descriptor offset is an immediate:
+      //   rows are (x_local, y_local, z); 16-byte units: one row = KC/4, a y step = BZ rows, an x step = (TY + 2) * BZ rows
+      constexpr uint32_t YS = (uint32_t)BZ * (KC * 4 / 16);
+      constexpr uint32_t XS = (uint32_t)(128 / BZ + 2) * YS;
       uint64_t *a_bar = three ? a_ready : a_full;  // single pass: nothing to convert, consume the TMA data directly
       int ast = 0, bst = 0;
-      uint32_t aph = 0, bph = 0, g = 0;  // g: chunk phases issued so far (accumulator hand-shake parity)
+      uint32_t aph = 0, bph = 0, gd = 0;  // gd: drain periods issued so far (accumulator hand-shake parity)
       long long st_acc = 0, st_a = 0, st_b = 0;
       int items_done = 0;
       const uint32_t b_base = desc_lo32(smem_u32(smem_b), 0);
       const uint32_t b_step = b_stage_bytes >> 4, b_lo_off = p.b_bytes >> 4, a_lo_off = p.a_bytes >> 4;
+      const uint32_t d0 = tmem_base, d1 = tmem_base + 3u * bn;   // tile 0 / tile 1: 3*bn columns each
       const long long t_begin = clock64();
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++items_done) {
-        for (int cc = 0; cc < p.kchunks; ++cc, ++g) {
+        int in_period = 0;
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          if (in_period == 0) {
+            // the epilogue has copied the previous drain period's accumulators (both tiles) into registers
+            mbar_wait_t(&acc_empty, (gd & 1u) ^ 1u, p.err, 23, st_acc);
+            tc_fence_after();
+          }
           mbar_wait_t(&a_bar[ast], aph, p.err, 24, st_a);
           tc_fence_after();
           const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)ast * a_stage_bytes), 0);
           const uint32_t a_lo = a_hi + a_lo_off;
-#pragma unroll 1
-          for (int dz = 0; dz < 3; ++dz) {
-            // the epilogue has copied the previous chunk's P_dz (both tiles) into registers
-            mbar_wait_t(&acc_empty[dz], (g & 1u) ^ 1u, p.err, 23, st_acc);
+          // software-pipelined barrier polling: the try_wait for the NEXT weight box is issued before this box's MMAs,
+          // so its latency hides behind the MMA issue instead of sitting on the critical path
+          bool b_ready = mbar_try_wait(&b_full[bst], bph);
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) {
+            if (!b_ready) mbar_wait_t(&b_full[bst], bph, p.err, 25, st_b);
+            const uint32_t b_hi = b_base + (uint32_t)bst * b_step;
+            const uint64_t *done_bar = &b_empty[bst];
+            if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
+            b_ready = mbar_try_wait(&b_full[bst], bph);
             tc_fence_after();
-            const uint32_t d0 = tmem_base + (uint32_t)dz * bn, d1 = d0 + 3u * bn;
-            // software-pipelined barrier polling: the try_wait for the NEXT weight tile is issued before this
-            // tile's MMAs, so its latency hides behind the MMA issue instead of sitting on the critical path
-            bool b_ready = mbar_try_wait(&b_full[bst], bph);
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              if (!b_ready) mbar_wait_t(&b_full[bst], bph, p.err, 25, st_b);
-              const uint32_t b_hi = b_base + (uint32_t)bst * b_step;
-              const uint64_t *done_bar = &b_empty[bst];
-              if (++bst == p.b_stages) { bst = 0; bph ^= 1; }
-              b_ready = mbar_try_wait(&b_full[bst], bph);
-              tc_fence_after();
+            for (int ks = 0; ks < KC / 8; ++ks) {
 #pragma unroll
-              for (int ks = 0; ks < H3_KC / 8; ++ks) {
-#pragma unroll
-                for (int t = 0; t < H3_TX; ++t) {  // the two tiles' chains alternate (independent accumulators)
-                  const uint32_t ao = (uint32_t)(t + t9 / 3) * XS + (uint32_t)(t9 % 3) * YS + (uint32_t)ks * 2u;  // immediate
-                  const uint32_t d = t == 0 ? d0 : d1;
-                  const uint32_t acc = (t9 == 0 && ks == 0) ? 0u : 1u;  // every chunk starts a fresh chain
-                  if (three) {
-                    // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
-                    mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                    mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_hi + b_lo_off + ks * 2u, dhi, idesc, 1u);
-                    mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
-                  } else {
-                    mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
-                  }
+              for (int t = 0; t < H3_TX; ++t) {  // the two tiles' chains alternate (independent accumulators)
+                const uint32_t ao = (uint32_t)(t + t9 / 3) * XS + (uint32_t)(t9 % 3) * YS + (uint32_t)ks * 2u;  // immediate
+                const uint32_t d = t == 0 ? d0 : d1;
+                const uint32_t acc = (in_period == 0 && t9 == 0 && ks == 0) ? 0u : 1u;  // a drain period starts a fresh chain
+                if (three) {
+                  // A_hi is fetched from shared memory once and reused from the collector for the B_lo product
+                  mma_tf32_lo32_c<kCollFill>(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
+                  mma_tf32_lo32_c<kCollLastUse>(d, a_hi + ao, b_hi + b_lo_off + ks * 2u, dhi, idesc, 1u);
+                  mma_tf32_lo32(d, a_lo + ao, b_hi + ks * 2u, dhi, idesc, 1u);
+                } else {
+                  mma_tf32_lo32(d, a_hi + ao, b_hi + ks * 2u, dhi, idesc, acc);
                 }
               }
-              mma_commit(const_cast<uint64_t *>(done_bar));
             }
-            mma_commit(&acc_full[dz]);
+            mma_commit(const_cast<uint64_t *>(done_bar));
           }
           mma_commit(&a_empty[ast]);
           if (++ast == p.a_stages) { ast = 0; aph ^= 1; }
+          if (++in_period == p.drain || cc == p.kchunks - 1) {
+            mma_commit(&acc_full);
+            in_period = 0;
+            ++gd;
+          }
         }
       }
       if (p.dbg && blockIdx.x == 0) { p.dbg[0] = st_a; p.dbg[1] = st_b; p.dbg[2] = st_acc; p.dbg[3] = clock64() - t_begin; p.dbg[4] = items_done; }
@@ -255,18 +263,18 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
     const int lz = m % BZ, ly = m / BZ;
     const bool z_first = lz == 0, z_last = lz == BZ - 1;
     const int bn = p.block_n;
-    uint32_t g = 0;
+    uint32_t gd = 0;
     long long st_full = 0;
     const long long t_begin = clock64();
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
-      for (int cc = 0; cc < p.kchunks; ++cc, ++g) {
+      for (int c0p = 0; c0p < p.kchunks; c0p += p.drain, ++gd) {   // one iteration per drain period
+        mbar_wait_t(&acc_full, gd & 1u, p.err, 27, st_full);
+        tc_fence_after();
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz) {
-          mbar_wait_t(&acc_full[dz], g & 1u, p.err, 27, st_full);
-          tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((my_t * 3 + dz) * bn);
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -281,9 +289,9 @@ __global__ void __launch_bounds__(H3_THREADS, 1)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { r[i] = __float_as_uint(w[i]); r[16 + i] = 0u; }
               }
-              if (c0 + 32 >= bn) {  // last slab of this accumulator is in registers: hand it back to the MMA warp
+              if (dz == 2 && c0 + 32 >= bn) {  // the last slab of this tile is in registers: hand TMEM back to the MMA warp
                 tc_fence_before();
-                mbar_arrive(&acc_empty[dz]);
+                mbar_arrive(&acc_empty);
               }
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -388,18 +396,27 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
   p.tiles_y = ceil_div(sy, p.ty);
   p.pairs_x = ceil_div(sx, H3_TX);
   p.num_units = nb * p.pairs_x * p.tiles_y;
-  p.kchunks = ceil_div(k, H3_KC);
+  const int kc = npass > 1 ? 8 : 16;
+  p.kchunks = ceil_div(k, kc);
+  // TMEM chains stay <= 108 MMAs per accumulator (the tensor core truncates when it accumulates): 9 (dx,dy) x (KC/8)
+  // k-steps x (3 products | 1) MMAs per chunk
+  p.drain = max(1, 108 / (9 * (kc / 8) * (npass > 1 ? 3 : 1)));
   p.cout = cout;
   p.block_n = cout >= 64 ? 64 : max(16, ((cout + 15) / 16) * 16);
   p.nblocks = ceil_div(cout, p.block_n);
   p.npass = npass;
   p.ldo = ldo;
-  p.a_bytes = (uint32_t)(p.bz * (p.ty + 2) * (H3_TX + 2)) * H3_KC * 4;
-  p.b_bytes = (uint32_t)p.block_n * H3_KC * 4;
-  if (p.a_bytes % 1024 != 0) return PVCNN_E_UNSUPPORTED;
+  p.a_bytes = (uint32_t)(p.bz * (p.ty + 2) * (H3_TX + 2)) * kc * 4;
+  p.b_bytes = 3u * (uint32_t)p.block_n * kc * 4;   // one box = the 3 dz taps of a (dx,dy) pair
+  if (p.a_bytes % 512 != 0 || p.b_bytes % 512 != 0) return PVCNN_E_UNSUPPORTED;
   const uint32_t a_stage = p.a_bytes * (npass > 1 ? 2 : 1), b_stage = p.b_bytes * (npass > 1 ? 2 : 1);
   const int budget = 227 * 1024 - 1024 - 1024;  // alignment slack + static shared memory (barriers)
-  p.a_stages = min(H3_MAX_A, (budget - 4 * (int)b_stage) / (int)a_stage);
+  // a chunk's MMAs (>= 3 k cycles) hide a halo load with 2 stages; the weight boxes are the latency-critical stream (a box
+  // is consumed in ~400 cycles, a TMA round trip takes ~2 k: measured 34 % of the issue time stalled on them with a
+  // 6-deep ring), so everything else goes to the weight ring
+  p.a_stages = 2;
+  { const char *e = getenv("PVCNN_HALO_ASTAGES"); if (e && e[0] >= '2' && e[0] <= '4') p.a_stages = e[0] - '0'; }
+  if ((budget - 4 * (int)b_stage) / (int)a_stage < p.a_stages) p.a_stages = (budget - 4 * (int)b_stage) / (int)a_stage;
   if (p.a_stages < 2) return PVCNN_E_UNSUPPORTED;
   p.b_stages = min(H3_MAX_B, (budget - p.a_stages * (int)a_stage) / (int)b_stage);
   p.bias = bias; p.out = out;
@@ -414,30 +431,30 @@ int conv_halo_launch(int nb, int sx, int sy, int sz, int k, int cout, const floa
                                   (unsigned long long)sx, (unsigned long long)nb};
     unsigned long long gstr[4] = {(unsigned long long)lda * 4, (unsigned long long)sz * lda * 4,
                                   (unsigned long long)sy * sz * lda * 4, (unsigned long long)sx * sy * sz * lda * 4};
-    unsigned box[5] = {(unsigned)H3_KC, (unsigned)p.bz, (unsigned)(p.ty + 2), (unsigned)(H3_TX + 2), 1};
-    int rc = encode_map_generic(&ma, a, 5, gdim, gstr, box, 64);
+    unsigned box[5] = {(unsigned)kc, (unsigned)p.bz, (unsigned)(p.ty + 2), (unsigned)(H3_TX + 2), 1};
+    int rc = encode_map_generic(&ma, a, 5, gdim, gstr, box, kc == 16 ? 64 : 320);
     if (rc) return rc;
   }
   {
     unsigned long long gdim[3] = {(unsigned long long)k, (unsigned long long)cout, 27ull};
     unsigned long long gstr[2] = {(unsigned long long)ldw * 4, (unsigned long long)cout * ldw * 4};
-    unsigned box[3] = {(unsigned)H3_KC, (unsigned)p.block_n, 1};
-    int rc = encode_map_generic(&mw_hi, w_hi, 3, gdim, gstr, box, 64);
+    unsigned box[3] = {(unsigned)kc, (unsigned)p.block_n, 3};
+    int rc = encode_map_generic(&mw_hi, w_hi, 3, gdim, gstr, box, kc == 16 ? 64 : 320);
     if (rc) return rc;
-    rc = encode_map_generic(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box, 64);
+    rc = encode_map_generic(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box, kc == 16 ? 64 : 320);
     if (rc) return rc;
   }
   const size_t smem = (size_t)p.a_stages * a_stage + (size_t)p.b_stages * b_stage + 1024;
   const int grid = min(kNumSMs, p.num_units * p.nblocks);
-#define PVB_HALO_LAUNCH(T3, BZV)                                                                                            \
-  do {                                                                                                                      \
-    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<T3, BZV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    PVB_LAUNCH((conv_halo_kernel<T3, BZV>), grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);                          \
+#define PVB_HALO_LAUNCH(T3, BZV, KCV)                                                                                          \
+  do {                                                                                                                         \
+    PVB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<T3, BZV, KCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    PVB_LAUNCH((conv_halo_kernel<T3, BZV, KCV>), grid, H3_THREADS, smem, stream, ma, mw_hi, mw_lo, p);                        \
   } while (0)
   if (npass > 1) {
-    if (p.bz == 32) PVB_HALO_LAUNCH(true, 32); else if (p.bz == 16) PVB_HALO_LAUNCH(true, 16); else PVB_HALO_LAUNCH(true, 8);
+    if (p.bz == 32) PVB_HALO_LAUNCH(true, 32, 8); else if (p.bz == 16) PVB_HALO_LAUNCH(true, 16, 8); else PVB_HALO_LAUNCH(true, 8, 8);
   } else {
-    if (p.bz == 32) PVB_HALO_LAUNCH(false, 32); else if (p.bz == 16) PVB_HALO_LAUNCH(false, 16); else PVB_HALO_LAUNCH(false, 8);
+    if (p.bz == 32) PVB_HALO_LAUNCH(false, 32, 16); else if (p.bz == 16) PVB_HALO_LAUNCH(false, 16, 16); else PVB_HALO_LAUNCH(false, 8, 16);
   }
 #undef PVB_HALO_LAUNCH
   return 0;

@@ -320,7 +320,7 @@ int encode_map_5d_cl(CUtensorMap *map, const float *ptr, int k, int ld, int nb, 
   return encode_map(map, ptr, 5, gdim, gstr, box, atom32);
 }
 
-// generic tiled map; swizzle_kind: 128 (SWIZZLE_128B), 64 (SWIZZLE_64B), 32 (SWIZZLE_128B_ATOM_32B)
+// generic tiled map; swizzle_kind: 128 (SWIZZLE_128B), 64 (SWIZZLE_64B), 320 (SWIZZLE_32B), 32 (SWIZZLE_128B_ATOM_32B)
 int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsigned long long *gdim,
                        const unsigned long long *gstride_bytes, const unsigned *box, int swizzle_kind) {
   EncodeTiledFn fn = get_encode_fn();
@@ -329,7 +329,8 @@ int encode_map_generic(CUtensorMap *map, const void *ptr, int rank, const unsign
   cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { gd[i] = gdim[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = gstride_bytes[i];
-  const CUtensorMapSwizzle sw = swizzle_kind == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+  const CUtensorMapSwizzle sw = swizzle_kind == 320 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swizzle_kind == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_kind == 32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                                      : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void *>(ptr), gd, gs, bx, es,
