@@ -104,8 +104,9 @@ def test_shapenet_train_step_native_vs_comparison_arm():
         if parts[-1] == "bias" and ga[k].abs().max() < 1e-4 * max(float(gb[k.replace("bias", "weight")].abs().max()), 1e-30) * 64:
             continue
         # SE gate weights see every voxel of the block through one scalar per (sample, channel): the most flip-sensitive
-        # gradients of the network (measured 1e-2 between two fp32 executions); everything else agrees to 5e-3
-        assert _l2(ga[k], gb[k]) < (3e-2 if ".fc." in k else 5e-3), k
+        # gradients of the network (measured 1e-2 between two fp32 executions); the rest: 6e-3 measured (mask flips of the
+        # LeakyReLU / ReLU layers between two fp32 executions), bound 1.5e-2
+        assert _l2(ga[k], gb[k]) < (3e-2 if ".fc." in k else 1.5e-2), k
 
 
 def test_frustum_end_to_end_has_no_host_sync_in_logits_mask(monkeypatch):
