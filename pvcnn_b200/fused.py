@@ -255,4 +255,7 @@ def pvconv_fused(module, features, coords):
     # activations saved for the backward must be private to this call; otherwise they live in shared scratch
     need_bwd = module.training and torch.is_grad_enabled() and (
         features.requires_grad or any(p.requires_grad for p in params))
+    if not torch.is_grad_enabled():   # inference: plain call, no autograd.Function bookkeeping
+        from .mlp import _NoCtx
+        return _PVConvFused.forward(_NoCtx(), features, coords, module, need_bwd, *params)
     return _PVConvFused.apply(features, coords, module, need_bwd, *params)

@@ -39,7 +39,7 @@ class PointNetAModule(nn.Module):
                 # neither the concat nor the [B, C', N] activation is written
                 b, _, n = features.shape
                 rows, lo = _mlp.cat_cl([features, coords] if self.include_coordinates else [features], n)
-                pooled = [_mlp._FromCL.apply(_mlp.mlp_cl(m.layers, rows, lo, pool_u=n), b,
+                pooled = [_mlp._run(_mlp._FromCL, _mlp.mlp_cl(m.layers, rows, lo, pool_u=n), b,
                                              list(m.layers)[-3].out_channels, 1) for m in self.mlps]
                 return (torch.cat(pooled, dim=1) if len(pooled) > 1 else pooled[0]), origin
         if self.include_coordinates:
@@ -112,7 +112,7 @@ class PointNetFPModule(nn.Module):
                 b, _, n = x.shape
                 rows, lo = _mlp.cat_cl([x] if skip is None else [x, skip], n)
                 z = _mlp.mlp_cl(self.mlp.layers, rows, lo)
-                return _mlp._FromCL.apply(z, b, list(self.mlp.layers)[-3].out_channels, n), points_coords
+                return _mlp._run(_mlp._FromCL, z, b, list(self.mlp.layers)[-3].out_channels, n), points_coords
         if skip is not None:
             x = torch.cat([x, skip], dim=1)
         return self.mlp(x), points_coords
