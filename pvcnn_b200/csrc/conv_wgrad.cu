@@ -403,12 +403,32 @@ static int wgrad_launch_block(int nb, int sx, int sy, int sz, int cin, int cout,
   return 0;
 }
 
+int wgrad_dz_launch(int nb, int sx, int sy, int sz, int cin, int cout, const float *x_hi, const float *x_lo, int ldx,
+                    const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
+                    const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out);  // conv_wgrad_dz.cu
+
 // Any cout: output channels are walked in blocks of 128 (the N extent of one TMEM accumulator set); a block reads its
 // own channel slice of g (pointer offset inside the channels-last rows) and writes its own rows of dW.
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
                  const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out) {
   PVB_CHECK_ARG(cout > 0 && g_hi && dw && cin > 0 && (ntaps == 1 || ntaps == 27));
+  // 3x3x3: the dz-merged kernel (conv_wgrad_dz.cu: one N = 3*Cout MMA per (dx,dy) pair, X blocks loaded once for three
+  // taps) in blocks of 64 output channels; PVCNN_B200_WGRAD=v1 forces the per-tap kernel below (A/B, diagnostics)
+  const char *e_wg = getenv("PVCNN_B200_WGRAD");
+  // (measured: 0.77 -> 0.59 ms dense at 64->64 R=32; wider layers would need several 64-channel passes that each re-read X
+  //  and are faster on the per-tap kernel's N=128 tiles: 64->128@16 0.18 vs 0.21 ms, so they stay there)
+  if (ntaps == 27 && cout <= 64 && !(e_wg && e_wg[0] == 'v' && e_wg[1] == '1')) {
+    bool ok = true;
+    for (int n0 = 0; n0 < cout && ok; n0 += 64) {
+      const int rc = wgrad_dz_launch(nb, sx, sy, sz, cin, min(64, cout - n0), x_hi, x_lo, ldx, g_hi + n0,
+                                     g_lo ? g_lo + n0 : nullptr, ldg, dw + (size_t)n0 * cin * ntaps, npass, s, ktile_list,
+                                     ktile_count, bz_out, by_out);
+      if (rc == PVCNN_E_UNSUPPORTED) ok = false;
+      else if (rc != 0) return rc;
+    }
+    if (ok) return 0;
+  }
   for (int n0 = 0; n0 < cout; n0 += 128) {
     const int nblk = min(128, cout - n0);
     const int rc = wgrad_launch_block(nb, sx, sy, sz, cin, nblk, ntaps, x_hi, x_lo, ldx, g_hi + n0, g_lo ? g_lo + n0 : nullptr,
