@@ -1113,7 +1113,7 @@ int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float s
 // neighbourhood is constant):  dW2[co][ci][tap] += c1[ci] * sum_{v inactive, tap valid at v} gY2[v][co].
 // Pass 1 reduces gY2 over the inactive k-tiles into the 27 boundary classes; pass 2 is the rank-1 update.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) class_colsum_kernel(int r, int cp, int by, int bz, long long n_kt,
+__global__ void __launch_bounds__(256) class_colsum_kernel(int r, int cp, int by, int bz, long long n_kt,
                                                            const unsigned char *__restrict__ kt_active,
                                                            const float *__restrict__ g,
                                                            float *__restrict__ classsum /*[2][27][cp] zeroed: inactive, all*/) {
@@ -1247,7 +1247,7 @@ int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char
   const size_t smem = sizeof(float) * 2 * 27 * (size_t)cp;
   if (smem > 48 * 1024)
     PVB_CUDA(cudaFuncSetAttribute(class_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PVB_LAUNCH(class_colsum_kernel, kNumSMs * 3, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum2);
+  PVB_LAUNCH(class_colsum_kernel, kNumSMs * 2, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum2);
   return 0;
 }
 
