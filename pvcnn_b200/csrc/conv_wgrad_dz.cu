@@ -24,6 +24,10 @@ constexpr int WZ_THREADS = 512;        // w0 TMA, w1 MMA, w2 TMEM alloc, w4-15 d
 constexpr int WZ_ROWS = 32;            // voxels per k-tile (4 MMA k-steps)
 constexpr uint32_t WZ_BLK = WZ_ROWS * 128;  // bytes of one [32 rows x 32 channels] block
 constexpr int WZ_MAX_STAGES = 5;
+// Measured (tools/wgrad_bench.py, dense 64->64 R=32 3xTF32): 32-voxel stages 0.59 ms; streaming each k-tile as two 16-voxel
+// stages (5-deep ring) 0.85 ms -- the kernel is bound by the L2->SM rate of its TMA boxes (80 KB per k-tile = 42 B/clk/SM,
+// ~11.5 TB/s chip-wide), not by ring depth, so the remaining lever is bytes: the gY `lo` copies (24 of the 80 KB) are derived
+// in shared memory by the drain warps instead of being TMA-loaded (GCONV), which also spares the 134 MB gY_lo tensors in HBM.
 
 struct WgradDzParams {
   int nb, sx, sy, sz;
@@ -42,13 +46,14 @@ struct WgradDzParams {
   const int *ktile_count;
 };
 
-template <bool THREE>
+template <bool THREE, bool GCONV>
 __global__ void __launch_bounds__(WZ_THREADS, 1)
     conv_wgrad_dz_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                          const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
                          const WgradDzParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[WZ_MAX_STAGES], empty_bar[WZ_MAX_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint64_t full_bar[WZ_MAX_STAGES], ready_bar[WZ_MAX_STAGES], empty_bar[WZ_MAX_STAGES], tmem_full_bar[2],
+      tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -60,10 +65,10 @@ __global__ void __launch_bounds__(WZ_THREADS, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_x_hi);
     prefetch_tensormap(&map_g_hi);
-    if (THREE) { prefetch_tensormap(&map_x_lo); prefetch_tensormap(&map_g_lo); }
+    if (THREE) { prefetch_tensormap(&map_x_lo); if (!GCONV) prefetch_tensormap(&map_g_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 12 * 32); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 12 * 32); }
     fence_barrier_init();
   }
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(WZ_THREADS, 1)
     // ================================ TMA producer ================================
     if (elect_one()) {
       const uint32_t passes = THREE ? 2u : 1u;
-      const uint32_t tx_bytes = p.box_bytes * (uint32_t)(3 * p.chunks_out + nab) * passes;
+      const uint32_t tx_bytes = p.box_bytes * ((uint32_t)(3 * p.chunks_out) * ((THREE && !GCONV) ? 2u : 1u) + (uint32_t)nab * passes);
       int stage = 0;
       uint32_t phase = 0;
       int blk_c[4], blk_dx[4], blk_dy[4];
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(WZ_THREADS, 1)
           for (int cc = 0; cc < p.chunks_out; ++cc) {
             uint8_t *dst = st + (size_t)(dzi * p.chunks_out + cc) * WZ_BLK;
             tma_load_5d(dst, &map_g_hi, &full_bar[stage], cc * 32, z0 + 1 - dzi, y0, x0, b);
-            if (THREE)
+            if (THREE && !GCONV)
               tma_load_5d(dst + (size_t)3 * p.chunks_out * WZ_BLK, &map_g_lo, &full_bar[stage], cc * 32, z0 + 1 - dzi, y0, x0, b);
           }
         uint8_t *sa = st + p.g_bytes;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(WZ_THREADS, 1)
           mbar_wait(&tmem_empty_bar[buf], ((chain >> 1) & 1) ^ 1, p.err, 32);
           tc_fence_after();
         }
-        mbar_wait(&full_bar[stage], phase, p.err, 33);
+        mbar_wait((THREE && GCONV) ? &ready_bar[stage] : &full_bar[stage], phase, p.err, 33);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
         const uint32_t g_hi = desc_lo32(st, WZ_BLK);
@@ -188,7 +193,34 @@ __global__ void __launch_bounds__(WZ_THREADS, 1)
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
     const long long nchains = (my_tiles + p.drain_tiles - 1) / p.drain_tiles;
+    const int tid = threadIdx.x - 4 * 32;   // 0..383
+    int stage = 0;
+    uint32_t phase = 0;
     for (long long ch = 0; ch < nchains; ++ch) {
+      if (THREE && GCONV) {
+        // derive the gY `lo` copies of this chain's stages in shared memory (lo = g - trunc_tf32(g), element-wise on the
+        // swizzled bytes), then hand each stage to the MMA warp; the drain below only starts once the chain's last stage
+        // has been converted, so the MMA warp never waits for a conversion that waits for it
+        const long long t0 = ch * p.drain_tiles, t1 = min(my_tiles, t0 + p.drain_tiles);
+        const int n16 = (int)((3u * (uint32_t)p.chunks_out * WZ_BLK) >> 4);
+        for (long long t = t0; t < t1; ++t) {
+          mbar_wait(&full_bar[stage], phase, p.err, 35);
+          const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)stage * p.stage_bytes);
+          float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)stage * p.stage_bytes + (size_t)3 * p.chunks_out * WZ_BLK);
+          for (int i = tid; i < n16; i += 12 * 32) {
+            const float4 v = src[i];
+            float4 l;
+            l.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+            l.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+            l.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+            l.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+            dst[i] = l;
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          mbar_arrive(&ready_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
       const int buf = (int)(ch & 1);
       mbar_wait(&tmem_full_bar[buf], (uint32_t)((ch >> 1) & 1), p.err, 34);
       tc_fence_after();
@@ -237,7 +269,9 @@ int *device_error_flag(int slot);           // conv_igemm.cu
 int wgrad_dz_launch(int nb, int sx, int sy, int sz, int cin, int cout, const float *x_hi, const float *x_lo, int ldx,
                     const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
                     const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out) {
-  if (cout > 64 || (npass > 1 && (!x_lo || !g_lo))) return PVCNN_E_UNSUPPORTED;
+  if (cout > 64 || (npass > 1 && !x_lo)) return PVCNN_E_UNSUPPORTED;
+  bool gconv = npass > 1 && g_lo == nullptr;     // no materialised gY_lo: derive it in shared memory
+  { const char *e = getenv("PVCNN_WGRAD_GLO"); if (npass > 1 && e && e[0] == 'k') gconv = true; if (npass > 1 && e && e[0] == 't' && g_lo) gconv = false; }
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && cin > 0 && cout > 0 && x_hi && g_hi && dw && ldx % 4 == 0 && ldg % 4 == 0);
   WgradDzParams p{};
   p.err = device_error_flag(2);
@@ -278,15 +312,18 @@ int wgrad_dz_launch(int nb, int sx, int sy, int sz, int cin, int cout, const flo
   if ((rc = encode_map_5d_cl(&mx_hi, x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mx_lo, npass > 1 ? x_lo : x_hi, cin, ldx, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   if ((rc = encode_map_5d_cl(&mg_hi, g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
-  if ((rc = encode_map_5d_cl(&mg_lo, npass > 1 ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
+  if ((rc = encode_map_5d_cl(&mg_lo, (npass > 1 && !gconv) ? g_lo : g_hi, cout, ldg, nb, sx, sy, sz, p.bz, p.by, 1, true))) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   const int grid = ngroups * p.ksplit;
-  if (npass > 1) {
-    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_dz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_wgrad_dz_kernel<true>, grid, WZ_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+  if (npass > 1 && gconv) {
+    PVB_CUDA((cudaFuncSetAttribute(conv_wgrad_dz_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    PVB_LAUNCH((conv_wgrad_dz_kernel<true, true>), grid, WZ_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+  } else if (npass > 1) {
+    PVB_CUDA((cudaFuncSetAttribute(conv_wgrad_dz_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    PVB_LAUNCH((conv_wgrad_dz_kernel<true, false>), grid, WZ_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
   } else {
-    PVB_CUDA(cudaFuncSetAttribute(conv_wgrad_dz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PVB_LAUNCH(conv_wgrad_dz_kernel<false>, grid, WZ_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
+    PVB_CUDA((cudaFuncSetAttribute(conv_wgrad_dz_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    PVB_LAUNCH((conv_wgrad_dz_kernel<false, false>), grid, WZ_THREADS, smem, s, mx_hi, mx_lo, mg_hi, mg_lo, p);
   }
   return 0;
 }
