@@ -197,6 +197,8 @@ typedef struct { /* parameters in torch layouts; running stats are updated in tr
   const float *w2, *b2, *g2, *be2; float *rm2, *rv2;   /* voxel_layers.3 / .4 */
   const float *wp, *bp, *gp, *bep; float *rmp, *rvp;   /* point_features.layers.0 / .1 */
   const float *se_w1, *se_w2;                          /* voxel_layers.6.fc.{0,2}.weight (with_se) */
+  long long *nbt1, *nbt2, *nbtp;                       /* num_batches_tracked of the three BatchNorms (int64, may be NULL):
+                                                          incremented in training mode by the statistics kernels */
 } pvcnn_pvconv_params;
 
 typedef struct { /* parameter gradients (same shapes as the parameters) */
@@ -271,8 +273,9 @@ PVCNN_API int pvcnn_mlp_pool_segments(long long groups, int u);
 PVCNN_API int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int npass, float bn_eps,
                                       float momentum, const float *x, const float *x_lo, const float *w,
                                       const float *bias, const float *gamma, const float *beta, float *running_mean,
-                                      float *running_var, float *wprep, float *partials, float *coef, float *y, float *z,
-                                      float *z_lo, int pool_u, float *pooled, int *argmax, float *pool_tmp, void *stream);
+                                      float *running_var, long long *num_batches_tracked, float *wprep, float *partials,
+                                      float *coef, float *y, float *z, float *z_lo, int pool_u, float *pooled, int *argmax,
+                                      float *pool_tmp, void *stream);
 /* dense gradient gz [groups*u, pad4(cout)] of a pooled output */
 PVCNN_API int pvcnn_mlp_pool_backward(long long groups, int u, int cout, const float *gpool, const int *argmax,
                                       float *gz, void *stream);

@@ -214,9 +214,12 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
                                                           float momentum, const float *__restrict__ partials,
                                                           const float *__restrict__ gamma,
                                                           const float *__restrict__ beta, float *running_mean,
-                                                          float *running_var, BnCoef coef) {
+                                                          float *running_var, BnCoef coef,
+                                                          long long *num_batches_tracked) {
   __shared__ double red[2][8];
   const int ch = blockIdx.x;  // one CTA per channel
+  // nn.BatchNorm's step counter (modules built on torch increment it with one ATen launch per layer and step)
+  if (ch == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
   if (ch >= c) {
     if (threadIdx.x == 0) { coef.mean[ch] = 0.f; coef.invstd[ch] = 0.f; coef.scale[ch] = 0.f; coef.shift[ch] = 0.f; }
     return;
@@ -251,9 +254,9 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(int nblocks, int c, in
 
 int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
                        const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
-                       cudaStream_t s) {
+                       cudaStream_t s, long long *num_batches_tracked) {
   PVB_LAUNCH(bn_finalize_kernel, cp, 256, 0, s, nblocks, c, cp, (double)rows, eps, momentum, partials,
-             gamma, beta, running_mean, running_var, coef);
+             gamma, beta, running_mean, running_var, coef, num_batches_tracked);
   return 0;
 }
 

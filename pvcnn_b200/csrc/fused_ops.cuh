@@ -32,7 +32,7 @@ int launch_bn_stats(long long rows, int cp, const float *y, float *partials, int
 // reduce partials (fp64), produce mean/invstd/scale/shift, update running stats (momentum, unbiased var)
 int launch_bn_finalize(int nblocks, int c, int cp, long long rows, float eps, float momentum, const float *partials,
                        const float *gamma, const float *beta, float *running_mean, float *running_var, BnCoef coef,
-                       cudaStream_t s);
+                       cudaStream_t s, long long *num_batches_tracked = nullptr);
 // eval mode: coefficients from running statistics
 int launch_bn_coef_from_running(int c, float eps, const float *gamma, const float *beta, const float *running_mean,
                                 const float *running_var, BnCoef coef, cudaStream_t s);

@@ -387,9 +387,9 @@ int pvcnn_mlp_pool_segments(long long groups, int u) {
  *   training: batch statistics (+ running-stat update); else running statistics                                      */
 int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int npass, float bn_eps, float momentum,
                             const float *x, const float *x_lo, const float *w, const float *bias, const float *gamma,
-                            const float *beta, float *running_mean, float *running_var, float *wprep, float *partials,
-                            float *coef, float *y, float *z, float *z_lo, int pool_u, float *pooled, int *argmax,
-                            float *pool_tmp, void *stream) {
+                            const float *beta, float *running_mean, float *running_var, long long *num_batches_tracked,
+                            float *wprep, float *partials, float *coef, float *y, float *z, float *z_lo, int pool_u,
+                            float *pooled, int *argmax, float *pool_tmp, void *stream) {
   PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3));
   PVB_CHECK_ARG(x && w && gamma && beta && wprep && partials && coef && y && (npass == 1 || x_lo));
   PVB_CHECK_ARG(pool_u > 0 ? (pooled && argmax && rows % pool_u == 0) : (z != nullptr));
@@ -404,7 +404,7 @@ int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int
   if (training) {
     int nblk = 0;
     MLP_TRY(launch_bn_stats(rows, co, y, partials, &nblk, s));
-    MLP_TRY(launch_bn_finalize(nblk, cout, co, rows, bn_eps, momentum, partials, gamma, beta, running_mean, running_var, bn, s));
+    MLP_TRY(launch_bn_finalize(nblk, cout, co, rows, bn_eps, momentum, partials, gamma, beta, running_mean, running_var, bn, s, num_batches_tracked));
   } else {
     PVB_CHECK_ARG(running_mean && running_var);
     MLP_TRY(launch_bn_coef_from_running(cout, bn_eps, gamma, beta, running_mean, running_var, bn, s));

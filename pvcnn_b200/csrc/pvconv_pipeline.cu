@@ -221,7 +221,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   if (d->training) {
     PVB_TRY(launch_bn_stats(Mv, co, ws->y1, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g1, prm->be1,
-                               prm->rm1, prm->rv1, bn1, s));
+                               prm->rm1, prm->rv1, bn1, s, prm->nbt1));
   } else {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g1, prm->be1, prm->rm1, prm->rv1, bn1, s));
   }
@@ -238,7 +238,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   if (d->training) {
     PVB_TRY(launch_bn_stats(Mv, co, ws->y2, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g2, prm->be2,
-                               prm->rm2, prm->rv2, bn2, s));
+                               prm->rm2, prm->rv2, bn2, s, prm->nbt2));
   } else {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g2, prm->be2, prm->rm2, prm->rv2, bn2, s));
   }
@@ -248,7 +248,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
   if (d->training) {
     PVB_TRY(launch_bn_stats(Mp, co, ws->p, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mp, d->bn_eps_pt, d->momentum, ws->partials, prm->gp, prm->bep,
-                               prm->rmp, prm->rvp, bnp, s));
+                               prm->rmp, prm->rvp, bnp, s, prm->nbtp));
   } else {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_pt, prm->gp, prm->bep, prm->rmp, prm->rvp, bnp, s));
   }

@@ -36,7 +36,7 @@ _WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("f
 
 
 class Params(ctypes.Structure):
-    _fields_ = [(k, _F) for k in _PARAM_FIELDS]
+    _fields_ = [(k, _F) for k in _PARAM_FIELDS] + [(k, ctypes.c_void_p) for k in ("nbt1", "nbt2", "nbtp")]
 
 
 class Grads(ctypes.Structure):
@@ -192,15 +192,18 @@ class _PVConvFused(Function):
                     raise RuntimeError("PVConv parameters must be contiguous float32 tensors")
             keep.append(t)
             setattr(prm, k, _ptr(t))
+        # nn.BatchNorm's step counters are incremented by the statistics kernels (no ATen launch per layer and step)
+        for name, bn in zip(("nbt1", "nbt2", "nbtp"), bns):
+            t = bn.num_batches_tracked
+            ok = training and t is not None and t.is_cuda and t.dtype == torch.int64
+            setattr(prm, name, t.data_ptr() if ok else None)
+            if training and t is not None and not ok:
+                t += 1
         out = torch.empty((b, module.out_channels, n), dtype=torch.float32, device=dev)
         _poison([out])
         ws = plan.struct()
         _lib.call("pvcnn_pvconv_forward", ctypes.byref(desc), features, coords, ctypes.byref(prm), ctypes.byref(ws),
                   out, device=dev)
-        if training:
-            for bn in bns:
-                if bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
         ctx.plan, ctx.prm, ctx.keep, ctx.desc, ctx.module = plan, prm, keep, desc, module
         ctx.shapes = [None if t is None else t.shape
                       for t in (w1, b1, g1, be1, w2, b2, g2, be2, wp, bp, gp, bep, se_w1, se_w2)]

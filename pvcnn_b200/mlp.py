@@ -133,9 +133,9 @@ class _MLP(Function):
                       None if bias is None else bias.detach(), gamma.detach(), beta.detach(),
                       bn.running_mean if (bn.track_running_stats and bn.running_mean is not None) else None,
                       bn.running_var if (bn.track_running_stats and bn.running_var is not None) else None,
+                      bn.num_batches_tracked if (training and bn.num_batches_tracked is not None
+                                                 and bn.num_batches_tracked.dtype == torch.int64) else None,
                       wprep, partials, coef, y, z, zl, pool, pooled, argmax, tmp, device=dev)
-            if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
             if keep:
                 saved.append((x, xl, y, coef, argmax))
             out = pooled if pool else z
