@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) devox_fused_kernel(int n, int c, int cp, 
 int launch_devox_fused(int b, int n, int c, int cp, int r, float slope, const float *norm_coords, const float *y2,
                        BnCoef bn2, const float *p, BnCoef bnp, const float *se_s, float *out, cudaStream_t s) {
   const size_t smem = (size_t)cp * 33 * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static shared memory counts against the 48 KB default too
     PVB_CUDA(cudaFuncSetAttribute(devox_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PVB_LAUNCH(devox_fused_kernel, dim3(ceil_div(n, PT_TILE), b), 256, smem, s, n, c, cp, r, slope, norm_coords, y2, bn2,
              p, bnp, se_s, out);
@@ -536,7 +536,7 @@ int launch_bwd_points(int b, int n, int c, int cp, int r, float slope, const flo
                       const float *norm_coords, const float *y2, BnCoef bn2, const float *p, BnCoef bnp, float *ga_cl,
                       float *d2, float *partials, int *nblocks, const float *se_s, float *ds_partials, cudaStream_t s) {
   const size_t smem = ((size_t)cp * 33 + (size_t)PT_WARPS * 5 * cp) * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static shared memory counts against the 48 KB default too
     PVB_CUDA(cudaFuncSetAttribute(bwd_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid(ceil_div(n, PT_TILE), b);
   *nblocks = (int)(grid.x * grid.y);
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(256) bwd_final_kernel(int n, int c, int cp, in
 int launch_bwd_final(int b, int n, int c, int cp, int r3, const int *ind, const int *cnt, const float *gg0,
                      const float *gfpt, float *grad_features, cudaStream_t s) {
   const size_t smem = (size_t)cp * 33 * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static shared memory counts against the 48 KB default too
     PVB_CUDA(cudaFuncSetAttribute(bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PVB_LAUNCH(bwd_final_kernel, dim3(ceil_div(n, PT_TILE), b), 256, smem, s, n, c, cp, r3, ind, cnt, gg0, gfpt,
              grad_features);
@@ -1248,7 +1248,7 @@ int launch_class_sums(int nb, int r, int cp, int by, int bz, const unsigned char
   PVB_CUDA(cudaMemsetAsync(classsum2, 0, sizeof(float) * 2 * 27 * (size_t)cp, s));
   const long long n_kt = (long long)nb * r * ((r + by - 1) / by) * ((r + bz - 1) / bz);
   const size_t smem = sizeof(float) * 2 * 27 * (size_t)cp;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static shared memory counts against the 48 KB default too
     PVB_CUDA(cudaFuncSetAttribute(class_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PVB_LAUNCH(class_colsum_kernel, kNumSMs * 2, 256, smem, s, r, cp, by, bz, n_kt, kt_active, g, classsum2);
   return 0;

@@ -6,6 +6,10 @@
 // grid covers the whole chip, reads/writes are coalesced along the point dimension, scatter
 // reductions are warp-aggregated before they reach L2, zero-fills are issued by the callee, and
 // everything runs on the caller's stream.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pvb {
@@ -392,8 +396,8 @@ constexpr int FPS_THREADS = 1024;
 __device__ __forceinline__ unsigned fps_tie_key(int k) { return ((unsigned)(k & 511) << 22) | ((unsigned)k >> 9); }
 __device__ __forceinline__ int fps_key_to_k(unsigned key) { return (int)(((key & 0x3FFFFFu) << 9) | (key >> 22)); }
 
-template <int PPT>
-__global__ void __launch_bounds__(FPS_THREADS, 1) fps_kernel(int n, int m, int coords_in_smem,
+template <int PPT, int NT>
+__global__ void __launch_bounds__(NT, 1) fps_kernel(int n, int m, int coords_in_smem,
                                                              const float *__restrict__ coords,
                                                              int *__restrict__ indices) {
   extern __shared__ float s_xyz[];  // [3][n] when coords_in_smem
@@ -404,18 +408,19 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_kernel(int n, int m, int c
   float px[PPT], py[PPT], pz[PPT], dist[PPT];
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
-    const int k = tid + p * FPS_THREADS;
+    const int k = tid + p * NT;
     const bool v = k < n;
     px[p] = v ? co[k] : 0.f;
     py[p] = v ? co[k + n] : 0.f;
     pz[p] = v ? co[k + 2 * n] : 0.f;
-    dist[p] = 1e38f;
+    dist[p] = v ? 1e38f : 0.f;   // slots past the end never win (see the round loop)
     if (coords_in_smem && v) {
       s_xyz[k] = px[p];
       s_xyz[n + k] = py[p];
       s_xyz[2 * n + k] = pz[p];
     }
   }
+  if (tid < 64) { s_d[tid >> 5][tid & 31] = 0u; s_k[tid >> 5][tid & 31] = 0xffffffffu; }  // rows of absent warps never win
   if (tid == 0) out[0] = 0;
   __syncthreads();
   int old = 0;
@@ -426,22 +431,26 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_kernel(int n, int m, int c
     } else {
       x1 = __ldg(co + old); y1 = __ldg(co + old + n); z1 = __ldg(co + old + 2 * n);
     }
-    // per-thread best under (dist desc, tie key asc); threads without points contribute (0-bits, k=0)
-    unsigned bd = 0u, bk = fps_tie_key(0);
-    bool any = false;
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-      const int k = tid + p * FPS_THREADS;
-      if (k < n) {
-        const float d = sqdist(px[p] - x1, py[p] - y1, pz[p] - z1);
-        const float d2 = fminf(d, dist[p]);
-        dist[p] = d2;
-        const unsigned db = __float_as_uint(d2);  // d2 >= 0 (or +0): monotone as unsigned
-        // within a thread k ascends with p, and all its k share (k mod 512) only if 1024 % 512 == 0:
-        // k mod 512 is identical for every p, so strict '>' keeps the smallest k  (sampling.cu:141-144)
-        if (!any || db > bd) { bd = db; bk = fps_tie_key(k); any = true; }
-      }
+    // Per-thread best under (dist desc, tie key asc).  Slots past the end of the cloud carry distance 0 and can never
+    // win the strict '>' below, so the loop has no bounds test.  A thread's points share k mod 512 (the stride is a
+    // multiple of 512) and k ascends with p, so strict '>' keeps its smallest k  (sampling.cu:141-144) and the tie key
+    // of slot p is key(slot 0) + p * (stride >> 9).
+    unsigned bd;
+    int bp = 0;
+    {
+      const float d2 = fminf(sqdist(px[0] - x1, py[0] - y1, pz[0] - z1), dist[0]);
+      dist[0] = d2;
+      bd = __float_as_uint(d2);  // d2 >= 0 (or +0): monotone as unsigned
     }
+#pragma unroll
+    for (int p = 1; p < PPT; ++p) {
+      const float d2 = fminf(sqdist(px[p] - x1, py[p] - y1, pz[p] - z1), dist[p]);
+      dist[p] = d2;
+      const unsigned db = __float_as_uint(d2);
+      if (db > bd) { bd = db; bp = p; }
+    }
+    const bool any = tid < n;
+    const unsigned bk = fps_tie_key(tid) + (unsigned)bp * (NT >> 9);
     // warp argmax: max distance bits, then min tie key among the maxima
     unsigned wd = __reduce_max_sync(0xffffffffu, bd);
     unsigned wk = __reduce_min_sync(0xffffffffu, (bd == wd && any) ? bk : 0xffffffffu);
@@ -705,14 +714,161 @@ __global__ void __launch_bounds__(1024) logits_mask_sample_kernel(int n, int k, 
 // =====================================================================================
 using namespace pvb;
 
-template <int PPT>
+// Cluster variant: CS CTAs (one thread-block cluster) share a cloud.  Every CTA keeps the whole cloud's coordinates in its
+// shared memory (to read the last pick) and owns n/CS of the running distances in registers.  A round has NO block or
+// cluster barrier: each warp reduces its own points with REDUX, lane r (< CS) sends the warp's (distance bits, tie key)
+// to CTA r with st.async, which lands the 8 bytes in that CTA's candidate table and signals its transaction mbarrier;
+// every warp then waits on the LOCAL mbarrier (32*CS candidates = 256*CS bytes per round), reads the table (CS entries per
+// lane) and reduces again, so all warps of all CTAs pick the same winner.  Tables and mbarriers are double buffered; a
+// warp can only be one round ahead of any other warp of the cluster, because it needs everybody's candidate to go on.
+// (the M-round chain is the largest non-conv cost of PVCNN++.)  The result is index-identical to fps_kernel:
+// (max distance, min tie key) does not depend on how the points are partitioned.
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+
+template <int PPT, int CS, int NT>
+__global__ void __launch_bounds__(NT, 1) fps_cluster_kernel(int n, int m, const float *__restrict__ coords,
+                                                                     int *__restrict__ indices) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int NW = NT / 32;   // warps per CTA = candidates per CTA and round
+  extern __shared__ float s_xyz[];  // [3][n]
+  __shared__ __align__(8) uint2 s_cand[2][NW * CS];   // [parity][source rank * 32 + source warp] = (distance bits, tie key)
+  __shared__ __align__(8) uint64_t s_bar[2];
+  static_assert((CS * NT) % 512 == 0 && NW * CS <= 32 * 8, "tie rule needs a stride that is a multiple of 512");
+  const uint32_t rank = cluster.block_rank();
+  const int b = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *co = coords + (size_t)b * 3 * n;
+  int *out = indices + (size_t)b * m;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+  const uint32_t cand0 = (uint32_t)__cvta_generic_to_shared(&s_cand[0][0]);
+  constexpr uint32_t ROUND_BYTES = (uint32_t)NW * CS * 8u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // rounds 0 and 1 are armed here, round t + 2 right after round t completed
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(ROUND_BYTES) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8), "r"(ROUND_BYTES) : "memory");
+  }
+  for (int k = tid; k < n; k += NT) {
+    s_xyz[k] = co[k];
+    s_xyz[n + k] = co[k + n];
+    s_xyz[2 * n + k] = co[k + 2 * n];
+  }
+  float px[PPT], py[PPT], pz[PPT], dist[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int k = (int)rank * NT + tid + p * (CS * NT);  // stride is a multiple of 512: see the tie rule
+    const bool v = k < n;
+    px[p] = v ? co[k] : 0.f;
+    py[p] = v ? co[k + n] : 0.f;
+    pz[p] = v ? co[k + 2 * n] : 0.f;
+    dist[p] = v ? 1e38f : 0.f;
+  }
+  const int k0 = (int)rank * NT + tid;
+  const bool any = k0 < n;
+  const unsigned key0 = fps_tie_key(k0);
+  if (rank == 0 && tid == 0) out[0] = 0;
+  __syncthreads();
+  cluster.sync();   // every CTA of the cluster is resident and its mbarriers are initialised before the first st.async
+  // lane r < CS addresses CTA r: this warp's slot in that CTA's table, and that CTA's mbarriers
+  const uint32_t peer_cand = fps_mapa(cand0 + (rank * (uint32_t)NW + (uint32_t)warp) * 8u, lane < CS ? lane : 0);
+  const uint32_t peer_bar = fps_mapa(bar0, lane < CS ? lane : 0);
+  int old = 0;
+  for (int t = 0; t + 1 < m; ++t) {
+    const uint32_t buf = t & 1, parity = (t >> 1) & 1;
+    const float x1 = s_xyz[old], y1 = s_xyz[n + old], z1 = s_xyz[2 * n + old];
+    unsigned bd;          // same per-thread rule as fps_kernel: no bounds test, strict '>' keeps the smallest k
+    int bp = 0;
+    {
+      const float d2 = fminf(sqdist(px[0] - x1, py[0] - y1, pz[0] - z1), dist[0]);
+      dist[0] = d2;
+      bd = __float_as_uint(d2);
+    }
+#pragma unroll
+    for (int p = 1; p < PPT; ++p) {
+      const float d2 = fminf(sqdist(px[p] - x1, py[p] - y1, pz[p] - z1), dist[p]);
+      dist[p] = d2;
+      const unsigned db = __float_as_uint(d2);
+      if (db > bd) { bd = db; bp = p; }
+    }
+    const unsigned bk = key0 + (unsigned)bp * ((CS * NT) >> 9);
+    const unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    const unsigned wk = __reduce_min_sync(0xffffffffu, (bd == wd && any) ? bk : 0xffffffffu);
+    if (lane < CS) {
+      const unsigned long long v = ((unsigned long long)wk << 32) | wd;   // uint2 {x = distance bits, y = key}
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
+                       peer_cand + buf * ROUND_BYTES),
+                   "l"(v), "r"(peer_bar + buf * 8u)
+                   : "memory");
+    }
+    {  // wait for the 32*CS candidates of this round
+      uint32_t done;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar0 + buf * 8u), "r"(parity)
+            : "memory");
+      } while (!done);
+    }
+    unsigned ld = 0u, lk = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < (NW * CS + 31) / 32; ++i) {
+      const int e = i * 32 + lane;
+      if (e < NW * CS) {
+        const uint2 c = s_cand[buf][e];
+        if (c.y != 0xffffffffu && (lk == 0xffffffffu || c.x > ld || (c.x == ld && c.y < lk))) { ld = c.x; lk = c.y; }
+      }
+    }
+    const unsigned gd = __reduce_max_sync(0xffffffffu, ld);
+    const unsigned gk = __reduce_min_sync(0xffffffffu, ld == gd ? lk : 0xffffffffu);
+    old = (gk == 0xffffffffu) ? 0 : fps_key_to_k(gk);
+    if (rank == 0 && tid == 0) out[t + 1] = old;
+    // Re-arm this buffer for round t + 2.  Thread 0 is past the wait, so the phase is complete; peers may already be
+    // sending round t + 2 only after they received OUR round t + 1 candidates, which this thread has not sent yet.
+    if (tid == 0 && t + 3 < m)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + buf * 8u), "r"(ROUND_BYTES)
+                   : "memory");
+  }
+  cluster.sync();     // no CTA exits while a peer may still write into its shared memory
+}
+
+template <int PPT, int CS, int NT>
+static int launch_fps_cluster(int b, int n, int m, const float *coords, int *indices, cudaStream_t s) {
+  const size_t smem = sizeof(float) * 3 * (size_t)n;
+  PVB_CUDA((cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(b * CS));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PVB_CUDA((cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, CS, NT>, n, m, coords, indices)));
+  ++pvb::g_launches;
+  return 0;
+}
+
+template <int PPT, int NT>
 static int launch_fps(int b, int n, int m, const float *coords, int *indices, cudaStream_t s) {
   size_t smem = sizeof(float) * 3 * (size_t)n;
   int in_smem = smem <= 200 * 1024;
   if (!in_smem) smem = 0;
-  if (smem > 48 * 1024)
-    PVB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PVB_LAUNCH(fps_kernel<PPT>, b, FPS_THREADS, smem, s, n, m, in_smem, coords, indices);
+  if (smem + 1024 > 48 * 1024)   // the static tables count against the 48 KB default as well (n = 4096 is exactly 48 KB)
+    PVB_CUDA((cudaFuncSetAttribute(fps_kernel<PPT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  PVB_LAUNCH((fps_kernel<PPT, NT>), b, NT, smem, s, n, m, in_smem, coords, indices);
   return 0;
 }
 
@@ -930,13 +1086,38 @@ int pvcnn_furthest_point_sampling(int b, int n, int m, const float *coords, floa
   PVB_CHECK_ARG(b > 0 && n > 0 && coords && indices);
   if (m <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  // Default: a cluster of 4 CTAs per cloud (128 threads each up to 8192 points, 256 above) when the cloud fits in shared
+  // memory, else one CTA of 512 threads.  PVCNN_B200_FPS: "cta" = single-CTA kernels only, "t1024" = 1024-thread single-CTA
+  // kernels (the round-1 shape), "cNNN" = cluster of 4 CTAs x NNN threads (128, 256, 1024).
+  const char *e = getenv("PVCNN_B200_FPS");
+  const char *emin = getenv("PVCNN_B200_FPS_NMIN");
+  const int nmin = emin ? atoi(emin) : 2048;
+  const bool fits = sizeof(float) * 3 * (size_t)n <= 200 * 1024;
+  const bool single = e && (e[0] == 't' || (e[0] == 'c' && e[1] == 't'));
+  if (!single && fits && n >= nmin) {
+    const int nt = (e && e[0] == 'c') ? atoi(e + 1) : (n <= 8192 ? 128 : 256);
+    const int pp = ceil_div(n, 4 * nt);
+#define PVB_FPS_C(PPT, NT) return launch_fps_cluster<PPT, 4, NT>(b, n, m, coords, indices, s)
+    if (nt == 1024) { if (pp <= 1) PVB_FPS_C(1, 1024); if (pp <= 2) PVB_FPS_C(2, 1024); if (pp <= 4) PVB_FPS_C(4, 1024); }
+    if (nt == 256) { if (pp <= 1) PVB_FPS_C(1, 256); if (pp <= 2) PVB_FPS_C(2, 256); if (pp <= 4) PVB_FPS_C(4, 256); if (pp <= 8) PVB_FPS_C(8, 256); if (pp <= 16) PVB_FPS_C(16, 256); }
+    if (nt == 128) { if (pp <= 1) PVB_FPS_C(1, 128); if (pp <= 2) PVB_FPS_C(2, 128); if (pp <= 4) PVB_FPS_C(4, 128); if (pp <= 8) PVB_FPS_C(8, 128); if (pp <= 16) PVB_FPS_C(16, 128); if (pp <= 32) PVB_FPS_C(32, 128); }
+#undef PVB_FPS_C
+  }
+  if (!(e && e[0] == 't' && e[1] == '1')) {   // 512 threads, up to 32 points each
+    const int pp = ceil_div(n, 512);
+    if (pp <= 1) return launch_fps<1, 512>(b, n, m, coords, indices, s);
+    if (pp <= 2) return launch_fps<2, 512>(b, n, m, coords, indices, s);
+    if (pp <= 4) return launch_fps<4, 512>(b, n, m, coords, indices, s);
+    if (pp <= 8) return launch_fps<8, 512>(b, n, m, coords, indices, s);
+    if (pp <= 16) return launch_fps<16, 512>(b, n, m, coords, indices, s);
+    if (pp <= 32) return launch_fps<32, 512>(b, n, m, coords, indices, s);
+  }
   const int ppt = ceil_div(n, FPS_THREADS);
-  if (ppt <= 1) return launch_fps<1>(b, n, m, coords, indices, s);
-  if (ppt <= 2) return launch_fps<2>(b, n, m, coords, indices, s);
-  if (ppt <= 4) return launch_fps<4>(b, n, m, coords, indices, s);
-  if (ppt <= 8) return launch_fps<8>(b, n, m, coords, indices, s);
-  if (ppt <= 16) return launch_fps<16>(b, n, m, coords, indices, s);
-  if (ppt <= 32) return launch_fps<32>(b, n, m, coords, indices, s);
+  if (ppt <= 1) return launch_fps<1, 1024>(b, n, m, coords, indices, s);
+  if (ppt <= 2) return launch_fps<2, 1024>(b, n, m, coords, indices, s);
+  if (ppt <= 4) return launch_fps<4, 1024>(b, n, m, coords, indices, s);
+  if (ppt <= 8) return launch_fps<8, 1024>(b, n, m, coords, indices, s);
+  if (n <= 32 * 512) return launch_fps<32, 512>(b, n, m, coords, indices, s);
   float *scratch = distances;
   if (!scratch) PVB_CUDA(cudaMallocAsync((void **)&scratch, sizeof(float) * (size_t)b * n, s));
   PVB_LAUNCH(fps_kernel_big, b, FPS_THREADS, 0, s, n, m, coords, scratch, indices);
@@ -976,7 +1157,7 @@ int pvcnn_logits_mask_sample(int b, int n, int k, unsigned long long seed, const
   while (p2 < (n > k ? n : k)) p2 <<= 1;
   const size_t smem = (size_t)p2 * 8 + (size_t)n * 8;
   if (smem > 200 * 1024) return PVCNN_E_UNSUPPORTED;  // n, k <= 8192 (the reference's largest use: N = 1024, k = 512)
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)  // static shared memory counts against the 48 KB default too
     PVB_CUDA(cudaFuncSetAttribute(pvb::logits_mask_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PVB_LAUNCH(pvb::logits_mask_sample_kernel, b, 1024, smem, stream, n, k, seed, mask, picks);
   return 0;

@@ -161,11 +161,11 @@ def test_gather(b, c, n, m, ref_backend):
 
 
 @pytest.mark.parametrize("b,n,m", [(2, 1024, 256), (8, 8192, 1024), (3, 700, 64), (2, 300, 300), (1, 5000, 16),
-                                   (1, 20000, 32)])
+                                   (1, 20000, 32), (4, 4096, 512), (2, 6000, 300), (2, 16384, 200), (3, 12000, 64)])
 def test_fps(b, n, m, ref_backend):
     g = rng(16)
     co = g.random((b, 3, n), dtype=np.float32)
-    if n == 700:  # quantised coordinates -> many exact distance ties
+    if n in (700, 6000):  # quantised coordinates -> many exact distance ties
         co = np.round(co * 4) / 4
     idx0 = oracle.furthest_point_sampling(co, m)
     idx = B.furthest_point_sampling(cu(co), m)
