@@ -276,6 +276,18 @@ PVCNN_API int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int tra
                                       float *running_var, long long *num_batches_tracked, float *wprep, float *partials,
                                       float *coef, float *y, float *z, float *z_lo, int pool_u, float *pooled, int *argmax,
                                       float *pool_tmp, void *stream);
+/* Inference form of one SharedMLP layer (modules/shared_mlp.py:6-33 under model.eval()): prepare once per parameter
+ * version, then one fused GEMM per forward (bias + BatchNorm(running stats) + ReLU in the epilogue; y never written).
+ * group_bias [rows / group_rows, group_ld]: per-cloud additive term for input channels that are constant over a cloud
+ * (models/shapenet/pvcnn.py:40-42, models/s3dis/pvcnn.py:44-46 repeat them over the points before the concat). */
+PVCNN_API int pvcnn_mlp_layer_prepare(int cin, int cout, float bn_eps, const float *w, const float *gamma, const float *beta,
+                            const float *running_mean, const float *running_var, float *wprep, float *coef,
+                            void *stream);
+PVCNN_API int pvcnn_mlp_layer_forward_eval(long long rows, int cin, int cout, int npass, const float *x, const float *x_lo,
+                                 const float *wprep, const float *bias, const float *coef, long long group_rows,
+                                 const float *group_bias, int group_ld, float *y, float *z, float *z_lo, int pool_u,
+                                 float *pooled, int *argmax, float *pool_tmp, void *stream);
+
 /* dense gradient gz [groups*u, pad4(cout)] of a pooled output */
 PVCNN_API int pvcnn_mlp_pool_backward(long long groups, int u, int cout, const float *gpool, const int *argmax,
                                       float *gz, void *stream);

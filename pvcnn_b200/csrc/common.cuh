@@ -65,4 +65,17 @@ __device__ __forceinline__ void red_add2(float *p, float2 v) {
   asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// Optional fused epilogue of igemm_conv_kernel (ntaps == 1 GEMMs).  Per output element, in this order:
+//   v = acc + bias[c]  (+ group_bias[(row / group_rows) * group_ld + c])      -- a per-cloud bias: the contribution of
+//                                                                                channels that are constant over a cloud
+//   v = fmaf(v, scale[c], shift[c]); v = v > 0 ? v : v * slope                -- BatchNorm (given coefficients) + (Leaky)ReLU,
+//                                                                                the arithmetic of bn_apply_leaky_kernel
+//   out[row, c] = v;  out_lo[row, c] = v - trunc_tf32(v)                      -- lo operand of the next 3xTF32 GEMM
+struct IgemmEpilogue {
+  const float *scale = nullptr, *shift = nullptr;
+  float slope = 0.0f;
+  float *out_lo = nullptr;
+  const float *group_bias = nullptr;
+  int group_rows = 0, group_ld = 0;
+};
 }  // namespace pvb

@@ -37,6 +37,8 @@ constexpr int IG_BLOCK_M = 128;
 constexpr int IG_KC = 32;  // channels per k-block = 128 bytes = one swizzle row
 constexpr int IG_THREADS = 256;
 constexpr int IG_MAX_STAGES = 8;
+constexpr int IG_EPI_LD = 36;   // floats per row of an epilogue warp's 32 x 32 staging tile (16-byte aligned, conflict-free)
+constexpr int IG_EPI_BYTES = 4 * 32 * IG_EPI_LD * 4;
 constexpr int IG_MAX_CHAIN = 72;  // MMAs accumulated into one TMEM accumulator
 constexpr uint32_t IG_A_TILE_BYTES = IG_BLOCK_M * IG_KC * 4;  // 16 KB
 
@@ -56,6 +58,7 @@ struct IgemmParams {
   const float *bias;
   float *out;
   int *err;
+  IgemmEpilogue ep;
 };
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
@@ -174,9 +177,18 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    // TMEM -> registers (thread = one output row, 32 columns at a time; partial accumulators are combined here in
+    // round-to-nearest fp32: the tensor core's own accumulation truncates, so its chains are kept short, see DESIGN.md
+    // "accumulation") -> a warp-private shared-memory tile -> registers in the transposed role (8 lanes x float4 = 128
+    // contiguous bytes of one row, 4 rows per instruction) -> global.  Every store instruction writes whole 128-byte
+    // lines; storing straight from the row-per-thread layout (16 bytes per lane at a row stride of ldo floats) ran the
+    // wide layers of the network heads at < 1 TB/s.  Bias, the optional per-cloud bias, BatchNorm + (Leaky)ReLU and the
+    // tf32 lo split are applied in the transposed role, where a lane owns the same 4 columns for all of its rows.
     const int we = warp - 4;  // TMEM lane quarter this warp may access
     const int m = we * 32 + lane;
     const int lz = m % p.bz, ly = (m / p.bz) % p.by, lx = m / (p.bz * p.by);
+    const uint32_t stage_tile = smem_u32(smem + (size_t)p.stages * p.stage_bytes) + (uint32_t)we * (32u * IG_EPI_LD * 4u);
+    const int rsub = lane >> 3, cq = (lane & 7) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_bufs;
@@ -188,39 +200,120 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
       const int x = (mt % p.tx) * p.bx + lx; mt /= p.tx;
       const int b = mt;
       const bool valid = (lx < p.bx) && x < p.sx && y < p.sy && z < p.sz;
-      float *orow = p.out + ((((size_t)b * p.sx + x) * p.sy + y) * p.sz + z) * p.ldo + (size_t)n_tile * p.block_n;
+      const long long row_off = valid ? (long long)(((((size_t)b * p.sx + x) * p.sy + y) * p.sz + z) * p.ldo +
+                                                    (size_t)n_tile * p.block_n)
+                                      : -1;
+      const int grp = p.ep.group_bias ? z / p.ep.group_rows : 0;   // rows are flat along z whenever an epilogue is given
+      long long roff[8];
+      int rgrp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        roff[i] = __shfl_sync(0xffffffffu, row_off, i * 4 + rsub);
+        rgrp[i] = __shfl_sync(0xffffffffu, grp, i * 4 + rsub);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(acc * p.acc_slots * p.block_n);
       const int ncols = min(p.block_n, p.cout - n_tile * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        // partial accumulators are combined here in round-to-nearest fp32 (the tensor core's own
-        // accumulation truncates, so its chains are kept short; see DESIGN.md "accumulation")
-        for (int sl = 1; sl < p.acc_slots; ++sl) {
-          float t[16];
-          tmem_ld16(taddr + sl * p.block_n + c0, t);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        float v[32];
+        const bool wide = c0 + 32 <= p.block_n;   // block_n is a multiple of 16: the last chunk may hold 16 columns
+        {
+          uint32_t r[32];
+          if (wide) {
+            tmem_ld32_nowait(taddr + c0, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += t[i];
-        }
-        if (valid && c0 < ncols) {
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < ncols) v[i] += __ldg(p.bias + n_tile * p.block_n + c0 + i);
-          }
-          if (c0 + 16 <= ncols) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4 *>(orow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           } else {
-            for (int i = 0; i < 16 && c0 + i < ncols; ++i) orow[c0 + i] = v[i];
+            tmem_ld16(taddr + c0, v);
+#pragma unroll
+            for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+          }
+          for (int sl = 1; sl < p.acc_slots; ++sl) {
+            if (wide) {
+              tmem_ld32_nowait(taddr + sl * p.block_n + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+            } else {
+              float t[16];
+              tmem_ld16(taddr + sl * p.block_n + c0, t);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += t[i];
+            }
           }
         }
+        if (c0 + 32 >= ncols) {   // last chunk of this tile: the accumulator can be handed back before the stores
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_tile + (uint32_t)(lane * IG_EPI_LD + 4 * j) * 4u),
+                       "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        const int cl = c0 + cq;               // this lane's first column inside the n-tile
+        const int cg = n_tile * p.block_n + cl;   // ... and inside the output row
+        const int nv = ncols - cl;            // valid columns among the lane's 4 (<= 0: none)
+        if (nv > 0) {
+          float bs[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < nv) {
+              if (p.bias) bs[k] = __ldg(p.bias + cg + k);
+              if (p.ep.scale) { sc[k] = __ldg(p.ep.scale + cg + k); sh[k] = __ldg(p.ep.shift + cg + k); }
+            }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (roff[i] < 0) continue;
+            float o[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                         : "r"(stage_tile + (uint32_t)((i * 4 + rsub) * IG_EPI_LD + cq) * 4u)
+                         : "memory");
+            if (p.bias) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] += bs[k];
+            }
+            if (p.ep.group_bias) {
+              const float *gb = p.ep.group_bias + (size_t)rgrp[i] * p.ep.group_ld + cg;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nv) o[k] += __ldg(gb + k);
+            }
+            if (p.ep.scale) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float t = fmaf(o[k], sc[k], sh[k]);
+                o[k] = t > 0.0f ? t : t * p.ep.slope;
+              }
+            }
+            float *dst = p.out + roff[i] + cl;
+            if (nv >= 4) {
+              *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nv) dst[k] = o[k];
+            }
+            if (p.ep.out_lo) {
+              float *dlo = p.ep.out_lo + roff[i] + cl;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = __fsub_rn(o[k], __uint_as_float(__float_as_uint(o[k]) & 0xFFFFE000u));
+              if (nv >= 4) {
+                *reinterpret_cast<float4 *>(dlo) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < nv) dlo[k] = o[k];
+              }
+            }
+          }
+        }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tc_fence_before();
@@ -388,6 +481,9 @@ namespace pvb {
 int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
                  int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                  int npass, cudaStream_t stream);
+int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                    int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                    int npass, cudaStream_t stream, const IgemmEpilogue *ep);
 }
 using namespace pvb;
 
@@ -423,6 +519,16 @@ namespace pvb {
 int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
                  int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                  int npass, cudaStream_t stream) {
+  return igemm_launch_ep(nb, sx, sy, sz, k, cout, ntaps, a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, out, ldo, npass, stream,
+                         nullptr);
+}
+
+int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                    int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                    int npass, cudaStream_t stream, const IgemmEpilogue *ep) {
+  PVB_CHECK_ARG(ep == nullptr || (ntaps == 1 && nb == 1 && sx == 1 && sy == 1));   // flat rows only
+  PVB_CHECK_ARG(ep == nullptr || ((ep->scale == nullptr) == (ep->shift == nullptr)));
+  PVB_CHECK_ARG(ep == nullptr || ep->group_bias == nullptr || (ep->group_rows > 0 && ep->group_ld >= cout));
   PVB_CHECK_ARG(nb > 0 && sx > 0 && sy > 0 && sz > 0 && k > 0 && cout > 0 && (ntaps == 1 || ntaps == 27));
   PVB_CHECK_ARG(a_hi && w_hi && out && (npass == 1 || npass == 3) && (npass == 1 || w_lo));
   PVB_CHECK_ARG(lda % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0 && lda >= k && ldw >= k && ldo >= cout);
@@ -463,7 +569,7 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
   p.stage_bytes = (p.stage_bytes + 1023) & ~1023u;
   const uint32_t rows = (uint32_t)(p.bx * p.by * p.bz);
   p.tx_bytes = (rows * IG_KC * 4 + (uint32_t)bn * IG_KC * 4) * (npass > 1 ? 2 : 1);
-  const int smem_budget = 227 * 1024 - 2048;
+  const int smem_budget = 227 * 1024 - 2048 - IG_EPI_BYTES;
   p.stages = min(IG_MAX_STAGES, smem_budget / (int)p.stage_bytes);
   PVB_CHECK_ARG(p.stages >= 2);
   // the tensor core accumulates with truncation (measured: ~2^-24 relative bias per accumulate), so
@@ -479,6 +585,7 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
   while (cols < (uint32_t)(p.acc_bufs * p.acc_slots * bn)) cols <<= 1;
   p.tmem_cols = cols;
   p.bias = bias; p.out = out; p.err = g_err_flag;
+  if (ep) p.ep = *ep;
   // B tiles must start 1024-aligned inside the stage: a_bytes is a multiple of 16 KB, b_hi = bn*128 bytes;
   // b_lo starts at b_bytes/2 = bn*128 which is a multiple of 1024 only when bn % 8 == 0 (true: bn % 16 == 0).
 
@@ -502,7 +609,7 @@ int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, con
     rc = encode_map(&mw_lo, npass > 1 ? w_lo : w_hi, 3, gdim, gstr, box);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + IG_EPI_BYTES;
   PVB_CUDA(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(kNumSMs, p.num_m_tiles * p.n_tiles);
   PVB_LAUNCH(igemm_conv_kernel, grid, IG_THREADS, smem, stream, ma_hi, ma_lo, mw_hi, mw_lo, p);

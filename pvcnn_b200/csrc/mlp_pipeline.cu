@@ -16,6 +16,9 @@ namespace pvb {
 int igemm_launch(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
                  int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
                  int npass, cudaStream_t stream);
+int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, const float *a_hi, const float *a_lo,
+                    int lda, const float *w_hi, const float *w_lo, int ldw, const float *bias, float *out, int ldo,
+                    int npass, cudaStream_t stream, const IgemmEpilogue *ep);
 int wgrad_launch(int nb, int sx, int sy, int sz, int cin, int cout, int ntaps, const float *x_hi, const float *x_lo,
                  int ldx, const float *g_hi, const float *g_lo, int ldg, float *dw, int npass, cudaStream_t s,
                  const int4 *ktile_list, const int *ktile_count, int *bz_out, int *by_out);
@@ -424,6 +427,79 @@ int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int
       if (grid > kNumSMs * 8) grid = kNumSMs * 8;
       PVB_LAUNCH(pool_combine_kernel, (int)grid, 256, 0, s, total, segs, co, pm, pa, pooled, argmax);
     }
+  }
+  return 0;
+}
+
+/* Inference form of a SharedMLP layer (eval-mode BatchNorm: running statistics), in two calls.
+ *
+ * pvcnn_mlp_layer_prepare: everything that depends only on the parameters -- the hi/lo GEMM operand of the weight
+ *   (wprep, pvcnn_mlp_wprep_floats(cin, cout) floats) and the BatchNorm coefficients (coef, 4 * pad4(cout) floats:
+ *   mean, invstd, scale = gamma * invstd, shift = beta - mean * scale).  The caller keeps both for as long as the
+ *   parameters do not change, so a forward pass of a frozen network launches neither.
+ *
+ * pvcnn_mlp_layer_forward_eval: z = relu(bn(conv(x))) as ONE GEMM whose epilogue applies bias, BatchNorm and ReLU and
+ *   writes z (+ z_lo, the lo operand of the next 3xTF32 layer; NULL when not needed): the pre-activation tensor y is
+ *   never written (the two-kernel form writes y, reads it back, writes z and z_lo).  Same arithmetic as
+ *   pvcnn_mlp_layer_forward(training = 0): y = acc + bias in fp32, z = max(fma(y, scale, shift), 0).
+ *   group_bias [rows / group_rows, group_ld] (or NULL) is added to y before the BatchNorm: the contribution of input
+ *   channels that are constant over each cloud of group_rows consecutive rows (a max-pooled cloud feature or a one-hot
+ *   class vector repeated over the points, models/shapenet/pvcnn.py:40-42), computed by the caller as a
+ *   [clouds, cout] GEMM instead of being concatenated to every row.
+ *   pool_u > 0: as in pvcnn_mlp_layer_forward (y is then needed as scratch: [rows, pad4(cout)]). */
+int pvcnn_mlp_layer_prepare(int cin, int cout, float bn_eps, const float *w, const float *gamma, const float *beta,
+                            const float *running_mean, const float *running_var, float *wprep, float *coef,
+                            void *stream) {
+  PVB_CHECK_ARG(cin > 0 && cout > 0 && w && gamma && beta && running_mean && running_var && wprep && coef);
+  const long long nf = (long long)cout * mp_ld32(cin);
+  MLP_TRY(pvcnn_conv_weight_prep(cout, cin, 1, 0, mp_ld32(cin), w, wprep, wprep + nf, stream));
+  return launch_bn_coef_from_running(cout, bn_eps, gamma, beta, running_mean, running_var, mlp_coef(coef, mp_pad4(cout)),
+                                     (cudaStream_t)stream);
+}
+
+int pvcnn_mlp_layer_forward_eval(long long rows, int cin, int cout, int npass, const float *x, const float *x_lo,
+                                 const float *wprep, const float *bias, const float *coef, long long group_rows,
+                                 const float *group_bias, int group_ld, float *y, float *z, float *z_lo, int pool_u,
+                                 float *pooled, int *argmax, float *pool_tmp, void *stream) {
+  PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3));
+  PVB_CHECK_ARG(x && wprep && coef && (npass == 1 || x_lo));
+  PVB_CHECK_ARG(pool_u > 0 ? (pooled && argmax && y && rows % pool_u == 0) : (z != nullptr));
+  PVB_CHECK_ARG(group_bias == nullptr || (group_rows > 0 && group_rows < (1LL << 31) && rows % group_rows == 0));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ci = mp_pad4(cin), co = mp_pad4(cout);
+  PVB_CHECK_ARG(co / 4 <= 256);
+  const long long nf = (long long)cout * mp_ld32(cin);
+  BnCoef bn = mlp_coef(const_cast<float *>(coef), co);
+  IgemmEpilogue ep;
+  ep.group_bias = group_bias;
+  ep.group_rows = (int)group_rows;
+  ep.group_ld = group_ld;
+  if (pool_u == 0) {
+    if (co != cout) {   // pad columns are K columns of the next layer: keep them finite
+      MLP_TRY(launch_memset_f32(z, rows * co, s));
+      if (z_lo) MLP_TRY(launch_memset_f32(z_lo, rows * co, s));
+    }
+    ep.scale = bn.scale;
+    ep.shift = bn.shift;
+    ep.slope = 0.0f;
+    ep.out_lo = z_lo;
+    return igemm_launch_ep(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, wprep, wprep + nf, mp_ld32(cin), bias, z, co,
+                           npass, s, &ep);
+  }
+  if (co != cout) MLP_TRY(launch_memset_f32(y, rows * co, s));
+  MLP_TRY(igemm_launch_ep(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, wprep, wprep + nf, mp_ld32(cin), bias, y, co,
+                          npass, s, group_bias ? &ep : nullptr));
+  const long long groups = rows / pool_u;
+  const int segs = pvcnn_mlp_pool_segments(groups, pool_u);
+  PVB_CHECK_ARG(segs == 1 || pool_tmp);
+  float *pm = segs == 1 ? pooled : pool_tmp;
+  int *pa = segs == 1 ? argmax : reinterpret_cast<int *>(pool_tmp + (size_t)groups * segs * co);
+  PVB_LAUNCH(bn_relu_pool_kernel, dim3((unsigned)groups, segs), PL_THREADS, 0, s, pool_u, segs, co, y, bn, pm, pa);
+  if (segs > 1) {
+    const long long total = groups * co;
+    long long grid = (total + 255) / 256;
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    PVB_LAUNCH(pool_combine_kernel, (int)grid, 256, 0, s, total, segs, co, pm, pa, pooled, argmax);
   }
   return 0;
 }

@@ -7,6 +7,7 @@ with rows = B*N (or B*M*U).  `pool_u` folds the set-abstraction max over the U n
 the last layer so the [B, C, M, U] activation is never written.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -88,6 +89,60 @@ class _FromCL(Function):
         gcl = torch.empty((b * n, _pad4(c)), dtype=torch.float32, device=g.device)
         _lib.call("pvcnn_points_to_cl", b, c, n, g.contiguous().float(), gcl, None)
         return gcl, None, None, None
+
+
+def _eval_prepared(conv, bn, cin, cout, dev, lib):
+    """(wprep, coef) of a frozen layer, rebuilt only when a parameter or running statistic changed (in-place updates bump
+    torch's version counter; re-assignment changes the storage pointer)."""
+    tensors = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version) for t in tensors) + (float(bn.eps), str(dev))
+    cache = getattr(bn, "_pvcnn_eval_cache", None)
+    if cache is not None and cache[0] == key:
+        return cache[1], cache[2]
+    wprep = torch.empty(lib.pvcnn_mlp_wprep_floats(cin, cout), dtype=torch.float32, device=dev)
+    coef = torch.empty(4 * _pad4(cout), dtype=torch.float32, device=dev)
+    _lib.call("pvcnn_mlp_layer_prepare", cin, cout, float(bn.eps), conv.weight.detach(), bn.weight.detach(),
+              bn.bias.detach(), bn.running_mean, bn.running_var, wprep, coef, device=dev)
+    bn._pvcnn_eval_cache = (key, wprep, coef)
+    return wprep, coef
+
+
+def _mlp_eval(x_cl, x_lo, meta, group_bias=None, group_rows=0):
+    """Frozen (eval-mode) stack: per layer one GEMM with bias + BatchNorm + ReLU (+ lo split) in its epilogue."""
+    lib = _lib_sizes()
+    dev = x_cl.device
+    rows = x_cl.shape[0]
+    npass, pool_u, widths = meta["npass"], meta["pool_u"], meta["widths"]
+    convs, bns = meta["convs"], meta["bns"]
+    cin = meta["cin"]
+    x, xl = x_cl, (x_lo if npass > 1 else None)
+    nl = len(widths)
+    out = None
+    for li, cout in enumerate(widths):
+        conv, bn = convs[li], bns[li]
+        co = _pad4(cout)
+        last = li == nl - 1
+        pool = pool_u if (last and pool_u) else 0
+        wprep, coef = _eval_prepared(conv, bn, cin, cout, dev, lib)
+        y = z = zl = pooled = argmax = tmp = None
+        if pool:
+            groups = rows // pool
+            y = _scratch("mlp_y0", rows * co, dev)
+            pooled = torch.empty((groups, co), dtype=torch.float32, device=dev)
+            argmax = torch.empty((groups, co), dtype=torch.int32, device=dev)
+            segs = lib.pvcnn_mlp_pool_segments(_LL(groups), pool)
+            if segs > 1:
+                tmp = _scratch("mlp_pooltmp", 2 * groups * segs * co, dev)
+        else:
+            z = torch.empty((rows, co), dtype=torch.float32, device=dev)
+            zl = torch.empty((rows, co), dtype=torch.float32, device=dev) if (npass > 1 and not last) else None
+        gb = group_bias if li == 0 else None
+        _lib.call("pvcnn_mlp_layer_forward_eval", _LL(rows), cin, cout, npass, x, xl, wprep,
+                  None if conv.bias is None else conv.bias.detach(), coef, _LL(group_rows if gb is not None else 0), gb,
+                  0 if gb is None else gb.shape[1], y, z, zl, pool, pooled, argmax, tmp, device=dev)
+        out = pooled if pool else z
+        x, xl, cin = z, zl, cout
+    return out
 
 
 class _MLP(Function):
@@ -218,8 +273,11 @@ def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True):
     need_bwd = training and torch.is_grad_enabled() and (
         (input_needs_grad and x_cl.requires_grad) or any(p is not None and p.requires_grad for p in params))
     meta = dict(npass=precision_passes(), training=training, pool_u=int(pool_u), widths=[c.out_channels for c in convs],
-                bns=bns, cin=convs[0].in_channels, need_bwd=bool(need_bwd),
+                bns=bns, convs=convs, cin=convs[0].in_channels, need_bwd=bool(need_bwd),
                 need_input_grad=bool(input_needs_grad and x_cl.requires_grad))
+    if not training and not torch.is_grad_enabled() and os.environ.get("PVCNN_B200_MLP_EVAL", "fused") != "layers":
+        # inference: frozen-layer path (cached weight operands / BatchNorm coefficients, activation fused into the GEMM)
+        return _mlp_eval(x_cl.detach(), None if x_lo is None else x_lo.detach(), meta)
     return _run(_MLP, x_cl, x_lo, meta, *params)
 
 

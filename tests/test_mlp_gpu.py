@@ -255,3 +255,52 @@ def test_sa_module_launches_no_library_gemm():
            and any(t in k.lower() for t in ("cudnn", "cublas", "cutlass", "gemm", "implicit_convolve", "wgrad", "dgrad"))]
     assert not bad, bad
     assert any("igemm_conv_kernel" in k for k in names) and any("conv_wgrad_kernel" in k for k in names), names
+
+
+@pytest.mark.parametrize("cin,widths,n,prec", [(16, [32, 24], 500, "fp32"), (67, [64, 64, 128], 1000, "fp32"),
+                                               (1472, [512, 256], 300, "fp32"), (35, [30, 18], 257, "fp32"),
+                                               (64, [128, 64], 640, "tf32")])
+def test_shared_mlp_inference_fused_epilogue(cin, widths, n, prec, monkeypatch):
+    """Inference path: one GEMM per layer with bias + BatchNorm(running stats) + ReLU (+ lo split) in its epilogue and the
+    weight operand / BatchNorm coefficients cached across calls.  It performs the arithmetic of the layer-by-layer path
+    (pvcnn_mlp_layer_forward, training = 0) in the same order, so the two are BIT-identical; the layered path is the one
+    the fp64 oracle tests pin.  Widths that are not multiples of 4 / 16 cover the padded-column handling."""
+    monkeypatch.setenv("PVCNN_B200_PRECISION", prec)
+    g = rng(70)
+    prod = modules.SharedMLP(cin, widths, dim=1)
+    _randomise_bn(prod, 3)
+    ref = R.clone_as_oracle(prod, R.SharedMLP(cin, widths, dim=1)).eval()
+    prod = prod.cuda().eval()
+    x = torch.from_numpy(g.standard_normal((2, cin, n), dtype=np.float32)).cuda()
+    with torch.no_grad():
+        fused = prod(x)
+        fused2 = prod(x)                       # second call: cached operands
+        monkeypatch.setenv("PVCNN_B200_MLP_EVAL", "layers")
+        layered = prod(x)
+        monkeypatch.delenv("PVCNN_B200_MLP_EVAL")
+        outr = ref(x.cpu().double())
+    assert torch.equal(fused, layered) and torch.equal(fused, fused2)
+    if prec == "fp32":
+        assert rel_err(fused.cpu().numpy(), outr.numpy()) < 1e-5
+    # a parameter update invalidates the cache (in-place: version counter; load_state_dict copies in place too)
+    with torch.no_grad():
+        prod.layers[0].weight.mul_(0.5)
+        prod.layers[1].running_mean.add_(0.05)
+        changed = prod(x)
+        monkeypatch.setenv("PVCNN_B200_MLP_EVAL", "layers")
+        assert torch.equal(changed, prod(x))
+    assert not torch.equal(changed, fused)
+
+
+def test_inference_path_launch_count():
+    """A frozen 3-layer SharedMLP forward is 3 GEMM launches (+ the two layout kernels) after the first call."""
+    from pvcnn_b200 import _lib
+    prod = modules.SharedMLP(32, [64, 64, 32], dim=1).cuda().eval()
+    x = torch.randn(2, 32, 1024, device="cuda")
+    with torch.no_grad():
+        prod(x)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        prod(x)
+        torch.cuda.synchronize()
+    assert _lib.launch_count() - l0 == 5
