@@ -13,7 +13,7 @@
 //     directly (kind::tf32, M=128, N=block_n, K=8 per instruction), accumulators live in TMEM,
 //     double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-//     warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias -> global).
+//     warp 2 = TMEM allocator, warps 4-11 = epilogue (tcgen05.ld -> smem transpose -> bias/BN/ReLU -> global).
 //   * fp32 parity: tf32 has a 10-bit mantissa, the north-star tolerance is 1e-5.  npass=3 runs the
 //     error-compensated split  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  Measured on B200
 //     (tests/test_igemm_gpu.py::test_hw_rounding_probe): kind::tf32 TRUNCATES fp32 operands, so the
@@ -35,10 +35,10 @@ using namespace umma;
 
 constexpr int IG_BLOCK_M = 128;
 constexpr int IG_KC = 32;  // channels per k-block = 128 bytes = one swizzle row
-constexpr int IG_THREADS = 256;
+constexpr int IG_THREADS = 384;   // warps 0-3: TMA, MMA issue, TMEM allocator, idle; warps 4-11: epilogue
 constexpr int IG_MAX_STAGES = 8;
-constexpr int IG_EPI_LD = 36;   // floats per row of an epilogue warp's 32 x 32 staging tile (16-byte aligned, conflict-free)
-constexpr int IG_EPI_BYTES = 4 * 32 * IG_EPI_LD * 4;
+constexpr uint32_t IG_EPI_WARP_BYTES = 32 * 16 * 4;   // an epilogue warp's 32 x 16 staging tile
+constexpr int IG_EPI_BYTES = 8 * IG_EPI_WARP_BYTES;
 constexpr int IG_MAX_CHAIN = 72;  // MMAs accumulated into one TMEM accumulator
 constexpr uint32_t IG_A_TILE_BYTES = IG_BLOCK_M * IG_KC * 4;  // 16 KB
 
@@ -59,6 +59,7 @@ struct IgemmParams {
   float *out;
   int *err;
   IgemmEpilogue ep;
+  int dbg;            // bring-up switches (PVCNN_IGEMM_DBG): 1 = no global stores, 4 = no MMAs
 };
 
 __global__ void __launch_bounds__(IG_THREADS, 1)
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], 256);
     }
     fence_barrier_init();
   }
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
           const uint32_t fresh_corr = kb != 0;
 #pragma unroll
           for (int k = 0; k < IG_KC / 8; ++k) {
+            if (p.dbg & 4) break;
             const uint32_t ko = (uint32_t)k * 2u;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
             mma_tf32_lo32(d_tmem, a_hi + ko, b_hi + ko, dhi, idesc, (k == 0) ? (fresh ? 0u : 1u) : 1u);
             if (p.npass > 1) {
@@ -177,18 +179,22 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    // Eight warps: warp w reads TMEM lanes 32*(w%4).. (the hardware's lane-quarter rule) and, of the tile's 32-column
+    // chunks, the even ones (warps 4-7) or the odd ones (warps 8-11).
     // TMEM -> registers (thread = one output row, 32 columns at a time; partial accumulators are combined here in
     // round-to-nearest fp32: the tensor core's own accumulation truncates, so its chains are kept short, see DESIGN.md
-    // "accumulation") -> a warp-private shared-memory tile -> registers in the transposed role (8 lanes x float4 = 128
-    // contiguous bytes of one row, 4 rows per instruction) -> global.  Every store instruction writes whole 128-byte
-    // lines; storing straight from the row-per-thread layout (16 bytes per lane at a row stride of ldo floats) ran the
-    // wide layers of the network heads at < 1 TB/s.  Bias, the optional per-cloud bias, BatchNorm + (Leaky)ReLU and the
-    // tf32 lo split are applied in the transposed role, where a lane owns the same 4 columns for all of its rows.
-    const int we = warp - 4;  // TMEM lane quarter this warp may access
+    // "accumulation") -> a warp-private, XOR-swizzled shared-memory tile of 32 rows x 16 columns -> registers in the
+    // transposed role (4 lanes x float4 = 64 contiguous bytes of one row, 8 rows per instruction) -> global.  Storing
+    // straight from the row-per-thread layout (16 bytes per lane at a row stride of ldo floats) ran the wide layers of the
+    // network heads at < 1 TB/s.  Bias, the optional per-cloud bias, BatchNorm + (Leaky)ReLU and the tf32 lo split are
+    // applied in the transposed role, where a lane owns the same 4 columns of every 16-column group for all of its rows;
+    // their coefficients are fetched before the wait for the accumulator.
+    const int we = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;   // 0: even chunks, 1: odd chunks
     const int m = we * 32 + lane;
     const int lz = m % p.bz, ly = (m / p.bz) % p.by, lx = m / (p.bz * p.by);
-    const uint32_t stage_tile = smem_u32(smem + (size_t)p.stages * p.stage_bytes) + (uint32_t)we * (32u * IG_EPI_LD * 4u);
-    const int rsub = lane >> 3, cq = (lane & 7) * 4;
+    const uint32_t stage_tile = smem_u32(smem + (size_t)p.stages * p.stage_bytes) + (uint32_t)(warp - 4) * IG_EPI_WARP_BYTES;
+    const int rsub = lane >> 2, cq = (lane & 3) * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_bufs;
@@ -204,18 +210,42 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
                                                     (size_t)n_tile * p.block_n)
                                       : -1;
       const int grp = p.ep.group_bias ? z / p.ep.group_rows : 0;   // rows are flat along z whenever an epilogue is given
-      long long roff[8];
-      int rgrp[8];
+      long long roff[4];
+      int rgrp[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        roff[i] = __shfl_sync(0xffffffffu, row_off, i * 4 + rsub);
-        rgrp[i] = __shfl_sync(0xffffffffu, grp, i * 4 + rsub);
+      for (int i = 0; i < 4; ++i) {
+        roff[i] = __shfl_sync(0xffffffffu, row_off, i * 8 + rsub);
+        rgrp[i] = __shfl_sync(0xffffffffu, grp, i * 8 + rsub);
       }
+      const int ncols = min(p.block_n, p.cout - n_tile * p.block_n);
+      const int nchunks = (ncols + 31) >> 5;
+      // coefficients of this lane's columns: chunk slot cs (this warp's cs-th chunk), 16-column group g, 4 columns
+      float bs[2][2][4], sc[2][2][4], sh[2][2][4];
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs)
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cl = (2 * cs + half) * 32 + g * 16 + cq + k;
+            const int cg = n_tile * p.block_n + cl;
+            const bool ok = cl < ncols;
+            bs[cs][g][k] = (ok && p.bias) ? __ldg(p.bias + cg) : 0.0f;
+            sc[cs][g][k] = (ok && p.ep.scale) ? __ldg(p.ep.scale + cg) : 1.0f;
+            sh[cs][g][k] = (ok && p.ep.scale) ? __ldg(p.ep.shift + cg) : 0.0f;
+          }
       mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(we * 32) << 16) + (uint32_t)(acc * p.acc_slots * p.block_n);
-      const int ncols = min(p.block_n, p.cout - n_tile * p.block_n);
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      if (half >= nchunks) {   // nothing to read for this warp: hand the accumulator back at once
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+      }
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs) {
+        const int ch = 2 * cs + half;
+        if (ch >= nchunks) break;
+        const int c0 = ch * 32;
         float v[32];
         const bool wide = c0 + 32 <= p.block_n;   // block_n is a multiple of 16: the last chunk may hold 16 columns
         {
@@ -244,75 +274,73 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
             }
           }
         }
-        if (c0 + 32 >= ncols) {   // last chunk of this tile: the accumulator can be handed back before the stores
+        if (ch + 2 >= nchunks) {   // this warp's last chunk: the accumulator can be handed back before the stores
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[acc]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_tile + (uint32_t)(lane * IG_EPI_LD + 4 * j) * 4u),
-                       "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                       : "memory");
-        __syncwarp();
-        const int cl = c0 + cq;               // this lane's first column inside the n-tile
-        const int cg = n_tile * p.block_n + cl;   // ... and inside the output row
-        const int nv = ncols - cl;            // valid columns among the lane's 4 (<= 0: none)
-        if (nv > 0) {
-          float bs[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int g = 0; g < 2; ++g) {
+          // stage 32 rows x 16 columns; the 16-byte column group j of row r sits at slot j ^ ((r >> 1) & 3)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k < nv) {
-              if (p.bias) bs[k] = __ldg(p.bias + cg + k);
-              if (p.ep.scale) { sc[k] = __ldg(p.ep.scale + cg + k); sh[k] = __ldg(p.ep.shift + cg + k); }
-            }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (roff[i] < 0) continue;
-            float o[4];
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                         : "r"(stage_tile + (uint32_t)((i * 4 + rsub) * IG_EPI_LD + cq) * 4u)
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(
+                             stage_tile + (uint32_t)(lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) * 4u),
+                         "f"(v[g * 16 + 4 * j]), "f"(v[g * 16 + 4 * j + 1]), "f"(v[g * 16 + 4 * j + 2]),
+                         "f"(v[g * 16 + 4 * j + 3])
                          : "memory");
-            if (p.bias) {
+          __syncwarp();
+          const int cl = c0 + g * 16 + cq;      // this lane's first column inside the n-tile
+          const int nv = ncols - cl;            // valid columns among the lane's 4 (<= 0: none)
+          if (nv > 0) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) o[k] += bs[k];
-            }
-            if (p.ep.group_bias) {
-              const float *gb = p.ep.group_bias + (size_t)rgrp[i] * p.ep.group_ld + cg;
+            for (int i = 0; i < 4; ++i) {
+              if (roff[i] < 0) continue;
+              const int rr = i * 8 + rsub;
+              float o[4];
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                           : "r"(stage_tile + (uint32_t)(rr * 16 + 4 * ((lane & 3) ^ ((rr >> 1) & 3))) * 4u)
+                           : "memory");
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < nv) o[k] += __ldg(gb + k);
-            }
-            if (p.ep.scale) {
+              for (int k = 0; k < 4; ++k) o[k] += bs[cs][g][k];
+              if (p.ep.group_bias) {
+                const float *gb = p.ep.group_bias + (size_t)rgrp[i] * p.ep.group_ld + n_tile * p.block_n + cl;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float t = fmaf(o[k], sc[k], sh[k]);
-                o[k] = t > 0.0f ? t : t * p.ep.slope;
+                for (int k = 0; k < 4; ++k)
+                  if (k < nv) o[k] += __ldg(gb + k);
               }
-            }
-            float *dst = p.out + roff[i] + cl;
-            if (nv >= 4) {
-              *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
+              if (p.ep.scale) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < nv) dst[k] = o[k];
-            }
-            if (p.ep.out_lo) {
-              float *dlo = p.ep.out_lo + roff[i] + cl;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) o[k] = __fsub_rn(o[k], __uint_as_float(__float_as_uint(o[k]) & 0xFFFFE000u));
+                for (int k = 0; k < 4; ++k) {
+                  const float t = fmaf(o[k], sc[cs][g][k], sh[cs][g][k]);
+                  o[k] = t > 0.0f ? t : t * p.ep.slope;
+                }
+              }
+              if (p.dbg & 1) continue;
+              float *dst = p.out + roff[i] + cl;
               if (nv >= 4) {
-                *reinterpret_cast<float4 *>(dlo) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (k < nv) dlo[k] = o[k];
+                  if (k < nv) dst[k] = o[k];
+              }
+              if (p.ep.out_lo) {
+                float *dlo = p.ep.out_lo + roff[i] + cl;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = __fsub_rn(o[k], __uint_as_float(__float_as_uint(o[k]) & 0xFFFFE000u));
+                if (nv >= 4) {
+                  *reinterpret_cast<float4 *>(dlo) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (k < nv) dlo[k] = o[k];
+                }
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -586,6 +614,7 @@ int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, 
   p.tmem_cols = cols;
   p.bias = bias; p.out = out; p.err = g_err_flag;
   if (ep) p.ep = *ep;
+  { const char *e = getenv("PVCNN_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   // B tiles must start 1024-aligned inside the stage: a_bytes is a multiple of 16 KB, b_hi = bn*128 bytes;
   // b_lo starts at b_bytes/2 = bn*128 which is a multiple of 1024 only when bn % 8 == 0 (true: bn % 16 == 0).
 
