@@ -269,13 +269,16 @@ PVCNN_API int pvcnn_mlp_pool_segments(long long groups, int u);
 /* one layer forward: y = x W^T + bias (saved), BatchNorm (batch statistics + running update when training, running
  * statistics otherwise; coef[4*pad4(cout)] = mean, invstd, scale, shift), then either z (+ z_lo) = relu(bn(y)) or, with
  * pool_u > 0, pooled/argmax [rows/pool_u, pad4(cout)] = max over groups of pool_u consecutive rows
- * (modules/pointnet.py:87 `.max(dim=-1).values`); pool_tmp: 2*segments*(rows/pool_u)*pad4(cout) floats if segments > 1 */
+ * (modules/pointnet.py:87 `.max(dim=-1).values`); pool_tmp: 2*segments*(rows/pool_u)*pad4(cout) floats if segments > 1.
+ * group_bias [rows / group_rows, group_ld] (NULL: none) is added to y before the BatchNorm: see
+ * pvcnn_mlp_layer_forward_eval */
 PVCNN_API int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int npass, float bn_eps,
                                       float momentum, const float *x, const float *x_lo, const float *w,
                                       const float *bias, const float *gamma, const float *beta, float *running_mean,
                                       float *running_var, long long *num_batches_tracked, float *wprep, float *partials,
                                       float *coef, float *y, float *z, float *z_lo, int pool_u, float *pooled, int *argmax,
-                                      float *pool_tmp, void *stream);
+                                      float *pool_tmp, long long group_rows, const float *group_bias, int group_ld,
+                                      void *stream);
 /* Inference form of one SharedMLP layer (modules/shared_mlp.py:6-33 under model.eval()): prepare once per parameter
  * version, then one fused GEMM per forward (bias + BatchNorm(running stats) + ReLU in the epilogue; y never written).
  * group_bias [rows / group_rows, group_ld]: per-cloud additive term for input channels that are constant over a cloud
@@ -292,11 +295,13 @@ PVCNN_API int pvcnn_mlp_layer_forward_eval(long long rows, int cin, int cout, in
 PVCNN_API int pvcnn_mlp_pool_backward(long long groups, int u, int cout, const float *gpool, const int *argmax,
                                       float *gz, void *stream);
 /* one layer backward: gz = d relu(bn(y)); writes dgamma/dbeta/dbias [cout], dw [cout,cin], gx [rows,pad4(cin)] (NULL to
- * skip); gy (+gy_lo) [rows,pad4(cout)] and sums [4*pad4(cout)] are scratch */
+ * skip); gy (+gy_lo) [rows,pad4(cout)] and sums [4*pad4(cout)] are scratch; d_group_bias [rows / group_rows, pad4(cout)]
+ * (NULL unless the forward had a group_bias) = per-cloud column sums of the conv-output gradient */
 PVCNN_API int pvcnn_mlp_layer_backward(long long rows, int cin, int cout, int npass, const float *gz, const float *x,
                                        const float *x_lo, const float *w, const float *y, const float *coef,
                                        float *wprep, float *partials, float *sums, float *gy, float *gy_lo, float *gx,
-                                       float *dw, float *dbias, float *dgamma, float *dbeta, void *stream);
+                                       float *dw, float *dbias, float *dgamma, float *dbeta, long long group_rows,
+                                       float *d_group_bias, void *stream);
 /* model-level glue: channel concatenation written straight into channels-last rows (the 1472-channel
  * torch.cat + repeat of models/s3dis/pvcnn.py:44-46 never exists in [B,C,N] form); src_n == 1 broadcasts a per-cloud
  * vector over the points.  pvcnn_cl_slice_to_points is its gradient (and the generic [rows] -> [B,C,N] slice reader). */

@@ -100,6 +100,44 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_kernel(long long rows, int
   });
 }
 
+// per-cloud column sums: out[(b * segs + s), cp] = sum of rows [b*n + s*per, min(n, (s+1)*per)) of g  (gradient of a per-cloud
+// bias); thread -> (channel quad, row lane) as in column_reduce
+__global__ void __launch_bounds__(RED_THREADS) group_colsum_kernel(long long n, int segs, int cp,
+                                                                   const float *__restrict__ g, float *__restrict__ out) {
+  __shared__ float4 red[RED_THREADS];
+  const int cp4 = cp >> 2, rl = RED_THREADS / cp4;
+  const int c4 = threadIdx.x % cp4, lane_r = threadIdx.x / cp4;
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const long long per = (n + segs - 1) / segs;
+  const long long r0 = seg * per, r1 = min(n, r0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane_r < rl)
+    for (long long r = r0 + lane_r; r < r1; r += rl) {
+      const float4 v = ldg_stream4(g + ((size_t)b * n + r) * cp + c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < cp4) {
+    float4 t = red[threadIdx.x];
+    for (int j = 1; j < rl; ++j) {
+      const float4 v = red[threadIdx.x + j * cp4];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    st4(out + ((size_t)b * segs + seg) * cp + threadIdx.x * 4, t);
+  }
+}
+__global__ void __launch_bounds__(256) group_colsum_finish_kernel(long long total, int segs, int cp,
+                                                                  const float *__restrict__ part, float *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / cp;
+    const int c = (int)(i % cp);
+    float t = 0.f;
+    for (int k = 0; k < segs; ++k) t += part[((size_t)b * segs + k) * cp + c];
+    out[i] = t;
+  }
+}
+
 // relu(bn(y)) followed by max over groups of U consecutive rows; one CTA per (group, row segment).
 // thread -> (channel quad c4 = t % cp4, row lane = t / cp4); partial (max, argmax) per segment, combined below.
 constexpr int PL_THREADS = 256;
@@ -392,9 +430,11 @@ int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int
                             const float *x, const float *x_lo, const float *w, const float *bias, const float *gamma,
                             const float *beta, float *running_mean, float *running_var, long long *num_batches_tracked,
                             float *wprep, float *partials, float *coef, float *y, float *z, float *z_lo, int pool_u,
-                            float *pooled, int *argmax, float *pool_tmp, void *stream) {
+                            float *pooled, int *argmax, float *pool_tmp, long long group_rows, const float *group_bias,
+                            int group_ld, void *stream) {
   PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3));
   PVB_CHECK_ARG(x && w && gamma && beta && wprep && partials && coef && y && (npass == 1 || x_lo));
+  PVB_CHECK_ARG(group_bias == nullptr || (group_rows > 0 && group_rows < (1LL << 31) && rows % group_rows == 0));
   PVB_CHECK_ARG(pool_u > 0 ? (pooled && argmax && rows % pool_u == 0) : (z != nullptr));
   cudaStream_t s = (cudaStream_t)stream;
   const int ci = mp_pad4(cin), co = mp_pad4(cout);
@@ -402,7 +442,12 @@ int pvcnn_mlp_layer_forward(long long rows, int cin, int cout, int training, int
   const long long nf = (long long)cout * mp_ld32(cin);
   MLP_TRY(pvcnn_conv_weight_prep(cout, cin, 1, 0, mp_ld32(cin), w, wprep, wprep + nf, stream));
   if (co != cout) MLP_TRY(launch_memset_f32(y, rows * co, s));  // pad columns feed the BN passes: keep them finite
-  MLP_TRY(igemm_launch(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, wprep, wprep + nf, mp_ld32(cin), bias, y, co, npass, s));
+  IgemmEpilogue ep;
+  ep.group_bias = group_bias;
+  ep.group_rows = (int)group_rows;
+  ep.group_ld = group_ld;
+  MLP_TRY(igemm_launch_ep(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, wprep, wprep + nf, mp_ld32(cin), bias, y, co, npass,
+                          s, group_bias ? &ep : nullptr));
   BnCoef bn = mlp_coef(coef, co);
   if (training) {
     int nblk = 0;
@@ -521,8 +566,9 @@ int pvcnn_mlp_pool_backward(long long groups, int u, int cout, const float *gpoo
 int pvcnn_mlp_layer_backward(long long rows, int cin, int cout, int npass, const float *gz, const float *x,
                              const float *x_lo, const float *w, const float *y, const float *coef, float *wprep,
                              float *partials, float *sums, float *gy, float *gy_lo, float *gx, float *dw, float *dbias,
-                             float *dgamma, float *dbeta, void *stream) {
+                             float *dgamma, float *dbeta, long long group_rows, float *d_group_bias, void *stream) {
   PVB_CHECK_ARG(rows > 0 && rows < (1LL << 31) && cin > 0 && cout > 0 && (npass == 1 || npass == 3));
+  PVB_CHECK_ARG(d_group_bias == nullptr || (group_rows > 0 && rows % group_rows == 0));
   PVB_CHECK_ARG(gz && x && w && y && coef && wprep && partials && sums && gy && dw && dbias && dgamma && dbeta);
   PVB_CHECK_ARG(npass == 1 || (x_lo && gy_lo));
   cudaStream_t s = (cudaStream_t)stream;
@@ -539,6 +585,22 @@ int pvcnn_mlp_layer_backward(long long rows, int cin, int cout, int npass, const
   MLP_TRY(launch_bn_bwd_apply(rows, co, 1, 0.0f, gz, y, bn, sums, sums + co, gy, npass > 1 ? gy_lo : nullptr, partials, &nblk, s));
   MLP_TRY(launch_reduce_partials(nblk, co, partials, sums + 2 * co, s));
   PVB_CUDA(cudaMemcpyAsync(dbias, sums + 2 * co, cb, cudaMemcpyDeviceToDevice, s));
+  if (d_group_bias) {   // gradient of the per-cloud bias [rows / group_rows, co]: column sums of gy over each cloud
+    const long long groups = rows / group_rows;
+    PVB_CHECK_ARG(groups < 65536 && co / 4 <= RED_THREADS);
+    const long long cap = (pvcnn_mlp_partials_floats(cout) - 64) / co;   // rows of `partials` available
+    long long segs = (group_rows + 511) / 512;
+    if (segs * groups > cap) segs = cap / groups;
+    if (segs <= 1) {
+      PVB_LAUNCH(group_colsum_kernel, dim3(1, (unsigned)groups), RED_THREADS, 0, s, group_rows, 1, co, gy, d_group_bias);
+    } else {
+      PVB_LAUNCH(group_colsum_kernel, dim3((unsigned)segs, (unsigned)groups), RED_THREADS, 0, s, group_rows, (int)segs, co,
+                 gy, partials);
+      const long long total = groups * co;
+      PVB_LAUNCH(group_colsum_finish_kernel, (int)min((total + 255) / 256, (long long)kNumSMs * 4), 256, 0, s, total,
+                 (int)segs, co, partials, d_group_bias);
+    }
+  }
   // weight gradient, then the data gradient
   MLP_TRY(wgrad_launch(1, 1, 1, (int)rows, cin, cout, 1, x, x_lo, ci, gy, gy_lo, co, dw, npass, s, nullptr, nullptr, nullptr, nullptr));
   if (gx) {

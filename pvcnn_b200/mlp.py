@@ -91,17 +91,25 @@ class _FromCL(Function):
         return gcl, None, None, None
 
 
-def _eval_prepared(conv, bn, cin, cout, dev, lib):
+def _select_cols(w, cols):
+    """Columns `cols` = ((start, end), ...) of a k=1 conv weight [cout, cin, 1(,1)] as a contiguous [cout, sum] matrix."""
+    w2 = w.reshape(w.shape[0], w.shape[1])
+    return torch.cat([w2[:, a:b] for a, b in cols], dim=1).contiguous()
+
+
+def _eval_prepared(conv, bn, cin, cout, dev, lib, cols=None):
     """(wprep, coef) of a frozen layer, rebuilt only when a parameter or running statistic changed (in-place updates bump
-    torch's version counter; re-assignment changes the storage pointer)."""
+    torch's version counter; re-assignment changes the storage pointer).  `cols`: the input-channel ranges the GEMM keeps
+    (the rest of the weight acts through a per-cloud bias)."""
     tensors = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
-    key = tuple((t.data_ptr(), t._version) for t in tensors) + (float(bn.eps), str(dev))
+    key = tuple((t.data_ptr(), t._version) for t in tensors) + (float(bn.eps), str(dev), cols)
     cache = getattr(bn, "_pvcnn_eval_cache", None)
     if cache is not None and cache[0] == key:
         return cache[1], cache[2]
     wprep = torch.empty(lib.pvcnn_mlp_wprep_floats(cin, cout), dtype=torch.float32, device=dev)
     coef = torch.empty(4 * _pad4(cout), dtype=torch.float32, device=dev)
-    _lib.call("pvcnn_mlp_layer_prepare", cin, cout, float(bn.eps), conv.weight.detach(), bn.weight.detach(),
+    weight = conv.weight.detach() if cols is None else _select_cols(conv.weight.detach(), cols)
+    _lib.call("pvcnn_mlp_layer_prepare", cin, cout, float(bn.eps), weight, bn.weight.detach(),
               bn.bias.detach(), bn.running_mean, bn.running_var, wprep, coef, device=dev)
     bn._pvcnn_eval_cache = (key, wprep, coef)
     return wprep, coef
@@ -123,7 +131,7 @@ def _mlp_eval(x_cl, x_lo, meta, group_bias=None, group_rows=0):
         co = _pad4(cout)
         last = li == nl - 1
         pool = pool_u if (last and pool_u) else 0
-        wprep, coef = _eval_prepared(conv, bn, cin, cout, dev, lib)
+        wprep, coef = _eval_prepared(conv, bn, cin, cout, dev, lib, meta.get("point_cols") if li == 0 else None)
         y = z = zl = pooled = argmax = tmp = None
         if pool:
             groups = rows // pool
@@ -149,7 +157,7 @@ class _MLP(Function):
     """x_cl [rows, pad4(cin)] -> relu(bn(conv(.))) stack -> [rows, pad4(cout)]  (or [rows/pool_u, pad4(cout)])."""
 
     @staticmethod
-    def forward(ctx, x_cl, x_lo, meta, *params):
+    def forward(ctx, x_cl, x_lo, group_bias, meta, *params):
         lib = _lib_sizes()
         dev = x_cl.device
         rows = x_cl.shape[0]
@@ -190,12 +198,15 @@ class _MLP(Function):
                       bn.running_var if (bn.track_running_stats and bn.running_var is not None) else None,
                       bn.num_batches_tracked if (training and bn.num_batches_tracked is not None
                                                  and bn.num_batches_tracked.dtype == torch.int64) else None,
-                      wprep, partials, coef, y, z, zl, pool, pooled, argmax, tmp, device=dev)
+                      wprep, partials, coef, y, z, zl, pool, pooled, argmax, tmp,
+                      _LL(meta["group_rows"] if (li == 0 and group_bias is not None) else 0),
+                      group_bias if li == 0 else None, 0 if group_bias is None else group_bias.shape[1], device=dev)
             if keep:
                 saved.append((x, xl, y, coef, argmax))
             out = pooled if pool else z
             x, xl, cin = z, zl, cout
         ctx.saved = saved
+        ctx.has_group_bias = group_bias is not None
         ctx.meta = dict(meta, rows=rows)
         ctx.params = [None if p is None else p.detach() for p in params]
         return out
@@ -212,6 +223,7 @@ class _MLP(Function):
         grads = [None] * len(ctx.params)
         g = g.contiguous().float()
         nl = len(widths)
+        d_gb = None
         for li in range(nl - 1, -1, -1):
             cin, cout = cins[li], widths[li]
             ci, co = _pad4(cin), _pad4(cout)
@@ -232,14 +244,17 @@ class _MLP(Function):
             wprep = _scratch("mlp_wprep", lib.pvcnn_mlp_wprep_floats(cin, cout), dev)
             partials = _scratch("mlp_partials", lib.pvcnn_mlp_partials_floats(cout), dev)
             sums = _scratch("mlp_sums", 4 * co, dev)
+            if li == 0 and ctx.has_group_bias and ctx.needs_input_grad[2]:
+                d_gb = torch.empty((rows // meta["group_rows"], co), dtype=torch.float32, device=dev)
             _lib.call("pvcnn_mlp_layer_backward", _LL(rows), cin, cout, npass, g, x, xl, w, y, coef, wprep, partials,
-                      sums, gy, gyl, gx, dw, dbias, dgamma, dbeta, device=dev)
+                      sums, gy, gyl, gx, dw, dbias, dgamma, dbeta, _LL(meta["group_rows"] if li == 0 else 0),
+                      d_gb if li == 0 else None, device=dev)
             grads[4 * li] = dw
             grads[4 * li + 1] = dbias if ctx.params[4 * li + 1] is not None else None
             grads[4 * li + 2] = dgamma
             grads[4 * li + 3] = dbeta
             g = gx
-        return (g, None, None, *grads)
+        return (g, None, d_gb, None, *grads)
 
 
 def native_supported(layers):
@@ -262,23 +277,36 @@ def native_supported(layers):
     return True
 
 
-def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True):
-    """Run the (conv, bn, relu)* stack `layers` on channels-last rows.  Returns [rows, pad4(cout)] (or pooled)."""
+def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True, point_cols=None, group_bias=None, group_rows=0):
+    """Run the (conv, bn, relu)* stack `layers` on channels-last rows.  Returns [rows, pad4(cout)] (or pooled).
+
+    point_cols / group_bias / group_rows: the first layer's input is the reference's concatenation restricted to the
+    channel ranges `point_cols`; the remaining channels are constant over each cloud of `group_rows` rows and enter as
+    group_bias [clouds, pad4(cout)] = their part of the weight applied once per cloud (see head_cl)."""
     mods = list(layers)
     convs, bns = mods[0::3], mods[1::3]
-    params = []
-    for conv, bn in zip(convs, bns):
-        params += [conv.weight, conv.bias, bn.weight, bn.bias]
     training = bool(bns[0].training)
+    fused_eval = (not training and not torch.is_grad_enabled()
+                  and os.environ.get("PVCNN_B200_MLP_EVAL", "fused") != "layers")
+    params = []
+    for i, (conv, bn) in enumerate(zip(convs, bns)):
+        w = conv.weight
+        if i == 0 and point_cols is not None and not fused_eval:
+            w = _select_cols(w, point_cols)          # autograd: the gradient flows back into the full weight
+        params += [w, conv.bias, bn.weight, bn.bias]
     need_bwd = training and torch.is_grad_enabled() and (
-        (input_needs_grad and x_cl.requires_grad) or any(p is not None and p.requires_grad for p in params))
+        (input_needs_grad and x_cl.requires_grad) or any(p is not None and p.requires_grad for p in params)
+        or (group_bias is not None and group_bias.requires_grad))
+    cin = convs[0].in_channels if point_cols is None else sum(b - a for a, b in point_cols)
     meta = dict(npass=precision_passes(), training=training, pool_u=int(pool_u), widths=[c.out_channels for c in convs],
-                bns=bns, convs=convs, cin=convs[0].in_channels, need_bwd=bool(need_bwd),
+                bns=bns, convs=convs, cin=cin, need_bwd=bool(need_bwd), group_rows=int(group_rows),
+                point_cols=None if point_cols is None else tuple(point_cols),
                 need_input_grad=bool(input_needs_grad and x_cl.requires_grad))
-    if not training and not torch.is_grad_enabled() and os.environ.get("PVCNN_B200_MLP_EVAL", "fused") != "layers":
+    if fused_eval:
         # inference: frozen-layer path (cached weight operands / BatchNorm coefficients, activation fused into the GEMM)
-        return _mlp_eval(x_cl.detach(), None if x_lo is None else x_lo.detach(), meta)
-    return _run(_MLP, x_cl, x_lo, meta, *params)
+        return _mlp_eval(x_cl.detach(), None if x_lo is None else x_lo.detach(), meta,
+                         None if group_bias is None else group_bias.detach(), group_rows)
+    return _run(_MLP, x_cl, x_lo, group_bias, meta, *params)
 
 
 def shared_mlp_forward(layers, x):
@@ -436,9 +464,31 @@ class _LinearCL(Function):
         return gx, None, dw, db
 
 
-def head_cl(seq, rows, lo, b, n):
+def head_supported(seq):
+    from .nn.shared_mlp import SharedMLP
+    for m in seq:
+        ok = isinstance(m, torch.nn.Dropout) or (isinstance(m, SharedMLP) and native_supported(m.layers)) or (
+            isinstance(m, torch.nn.Conv1d) and m.kernel_size == (1,) and m.groups == 1 and m.stride == (1,))
+        if not ok:
+            return False
+    return True
+
+
+def cloud_bias(conv, cloud_taps, cloud_cols):
+    """The first head layer's response to the channels that are constant over a cloud: [B, pad4(cout)] =
+    W[:, cloud_cols] @ cat(cloud_taps), one small GEMM per forward instead of K_cloud extra columns on every point row."""
+    g = torch.cat([t.reshape(t.shape[0], t.shape[1]) for t in cloud_taps], dim=1).float()
+    kb = g.shape[1]
+    if _pad4(kb) != kb:
+        g = torch.nn.functional.pad(g, (0, _pad4(kb) - kb))
+    w_b = _select_cols(conv.weight, cloud_cols)
+    return _run(_LinearCL, g.contiguous(), None, w_b, None)
+
+
+def head_cl(seq, rows, lo, b, n, point_cols=None, group_bias=None):
     """Run a per-point head -- nn.Sequential of SharedMLP | nn.Dropout | nn.Conv1d(k=1) (models/utils.py:15-45) -- on
-    channels-last rows and return [B, Cout, N].  Returns None if the head holds anything else (caller falls back)."""
+    channels-last rows and return [B, Cout, N].  Returns None if the head holds anything else (caller falls back).
+    point_cols / group_bias: see mlp_cl (they apply to the first module, which must then be a SharedMLP)."""
     from .nn.shared_mlp import SharedMLP
     mods = list(seq)
     for m in mods:
@@ -455,7 +505,10 @@ def head_cl(seq, rows, lo, b, n):
             if xl is None and precision_passes() > 1:
                 from . import dense
                 xl = dense.split_tf32(x.contiguous(), want_hi=False)[1]
-            x = mlp_cl(m.layers, x, xl)
+            if m is mods[0] and group_bias is not None:
+                x = mlp_cl(m.layers, x, xl, point_cols=point_cols, group_bias=group_bias, group_rows=n)
+            else:
+                x = mlp_cl(m.layers, x, xl)
             xl = None
             cout = list(m.layers)[-3].out_channels
         else:

@@ -7,6 +7,7 @@ tests/test_abi_cpu.py checks key by key against the unmodified reference models,
 Only the network wiring lives here; every layer is a pvcnn_b200.nn module (PVConv / SharedMLP / PointNet*Module).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -22,10 +23,23 @@ def _classify(head, taps, n):
     neither the [B, sum C, N] concat nor the repeated cloud feature is materialised."""
     if taps[0].is_cuda and native_mlp_enabled():
         from . import mlp
-        rows, lo = mlp.cat_cl(taps, n)
-        out = mlp.head_cl(head, rows, lo, taps[0].shape[0], n)
-        if out is not None:
-            return out
+        if mlp.head_supported(head):
+            first = list(head)[0]
+            cloud = [t.shape[2] == 1 and n > 1 for t in taps]
+            if any(cloud) and not all(cloud) and isinstance(first, SharedMLP) and os.environ.get("PVCNN_B200_HEAD_SPLIT", "1") != "0":
+                # Channels that are constant over a cloud (one-hot class vector, max-pooled cloud feature:
+                # models/shapenet/pvcnn.py:40-42, models/kitti/frustum/pvcnne.py) never become columns of the point rows: their
+                # part of the first layer's weight is applied once per cloud and enters the GEMM epilogue as a per-cloud bias.
+                col, pcols, ccols = 0, [], []
+                for t, c in zip(taps, cloud):
+                    (ccols if c else pcols).append((col, col + t.shape[1]))
+                    col += t.shape[1]
+                conv0 = list(first.layers)[0]
+                gb = mlp.cloud_bias(conv0, [t for t, c in zip(taps, cloud) if c], tuple(ccols))
+                rows, lo = mlp.cat_cl([t for t, c in zip(taps, cloud) if not c], n)
+                return mlp.head_cl(head, rows, lo, taps[0].shape[0], n, point_cols=tuple(pcols), group_bias=gb)
+            rows, lo = mlp.cat_cl(taps, n)
+            return mlp.head_cl(head, rows, lo, taps[0].shape[0], n)
     return head(torch.cat([t.expand(-1, -1, n) for t in taps], dim=1))
 
 

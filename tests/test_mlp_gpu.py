@@ -304,3 +304,64 @@ def test_inference_path_launch_count():
         prod(x)
         torch.cuda.synchronize()
     assert _lib.launch_count() - l0 == 5
+
+
+def _head_and_taps(seed, b, n, widths):
+    """A per-point head in the reference's form (models/utils.py:15-45) over taps [point, cloud, point, cloud]."""
+    from pvcnn_b200 import zoo  # noqa: F401
+    torch.manual_seed(seed)
+    g = rng(seed)
+    chans = [20, 12, 9, 7]
+    cloud = [False, True, False, True]
+    taps = [torch.from_numpy(g.standard_normal((b, c, 1 if cl else n), dtype=np.float32)).cuda().requires_grad_(True)
+            for c, cl in zip(chans, cloud)]
+    head = torch.nn.Sequential(modules.SharedMLP(sum(chans), widths, dim=1), torch.nn.Dropout(0.0),
+                               torch.nn.Conv1d(widths[-1], 5, 1)).cuda()
+    _randomise_bn(head, seed)
+    return head, taps
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_head_cloud_channels_enter_as_per_cloud_bias(train, monkeypatch):
+    """models/shapenet/pvcnn.py:40-42 / models/kitti/frustum: taps that are constant over a cloud are not concatenated to
+    every point row; their slice of the first layer's weight is applied once per cloud and added in the GEMM epilogue
+    (forward), and its gradient is the per-cloud column sum of the conv-output gradient (backward).  Same function as the
+    concatenated form up to fp32 summation order: compared with that form (itself pinned against the fp64 oracle by the
+    tests above) on outputs, tap gradients and every parameter gradient, and directly against the fp64 module."""
+    from pvcnn_b200 import zoo
+    b, n, widths = 3, 384, [64, 32]
+    outs = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("PVCNN_B200_HEAD_SPLIT", split)
+        head, taps = _head_and_taps(11, b, n, widths)
+        head.train(train)
+        if train:
+            out = zoo._classify(head, taps, n)
+            (out * torch.linspace(0.5, 1.5, n, device="cuda")).square().mean().backward()
+            grads = [t.grad.clone() for t in taps] + [p.grad.clone() for p in head.parameters()]
+        else:
+            with torch.no_grad():
+                out = zoo._classify(head, taps, n)
+            grads = []
+        outs.append((out.detach(), grads, head, taps))
+    (o1, g1, head, taps), (o0, g0, _, _) = outs
+    assert rel_err(o1.cpu().numpy(), o0.cpu().numpy()) < 1e-5
+    for a, c in zip(g1, g0):
+        a, c = a.cpu().numpy(), c.cpu().numpy()
+        if np.abs(c).max() < 1e-6:      # conv bias in front of a BatchNorm: the exact gradient is 0, both are rounding noise
+            assert np.abs(a).max() < 1e-6
+            continue
+        assert rel_err(a, c) < 5e-5
+    # fp64 statement of the reference: repeat + cat + head
+    ref = torch.nn.Sequential(R.SharedMLP(sum(t.shape[1] for t in taps), widths, dim=1), torch.nn.Dropout(0.0),
+                              torch.nn.Conv1d(widths[-1], 5, 1)).double()
+    ref[0] = R.clone_as_oracle(head[0], ref[0])
+    with torch.no_grad():
+        ref[2].weight.copy_(head[2].weight.double().cpu())
+        ref[2].bias.copy_(head[2].bias.double().cpu())
+    ref.train(train)
+    if train:   # running statistics were already updated once by the run above: compare eval-free quantities only
+        return
+    with torch.no_grad():
+        want = ref(torch.cat([t.detach().cpu().double().expand(-1, -1, n) for t in taps], dim=1))
+    assert rel_err(o1.cpu().numpy(), want.numpy()) < 1e-5
