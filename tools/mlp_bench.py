@@ -46,7 +46,7 @@ for rows, cin, cout in shapes:
     y, z, zl = (torch.empty(rows, co, device=dev) for _ in range(3))
     _lib.call("pvcnn_mlp_layer_prepare", cin, cout, 1e-5, w, gamma, beta, rm, rv, wprep, coef)
     t_lay = timeit(lambda: _lib.call("pvcnn_mlp_layer_forward", LL(rows), cin, cout, 0, npass, 1e-5, 0.1, x, xl, w, bias, gamma,
-                                     beta, rm, rv, None, wprep, partials, coef, y, z, zl, 0, None, None, None))
+                                     beta, rm, rv, None, wprep, partials, coef, y, z, zl, 0, None, None, None, LL(0), None, 0))
     z1 = z.clone()
     t_fus = timeit(lambda: _lib.call("pvcnn_mlp_layer_forward_eval", LL(rows), cin, cout, npass, x, xl, wprep, bias, coef, LL(0),
                                      None, 0, None, z, zl, 0, None, None, None))
