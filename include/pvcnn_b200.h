@@ -190,6 +190,8 @@ typedef struct {
   int with_se;        /* SE3d after the second conv block (modules/se.py), hidden = cout / 8 */
   int vox_stats;      /* 0: fused fp64-mean normalisation; 1: ws->vox_mean given (reference-exact), denom computed;
                          2: ws->vox_mean and ws->vox_denom given */
+  int prepared;       /* inference with ws->prep: 1 = ws->prep already holds this block's GEMM operands, BatchNorm
+                         coefficients and conv2 constants for the current parameters (skip rebuilding them) */
 } pvcnn_pvconv_desc;
 
 typedef struct { /* parameters in torch layouts; running stats are updated in training mode */
@@ -229,6 +231,8 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
   float *se;                /* with_se: b*(7*co + cout/8)  (pooled sums, mean, hidden, gate, d gate, dense term) */
   float *vox_mean;          /* b*3   per-cloud coordinate mean (desc.vox_stats >= 1) */
   float *vox_denom;         /* b     per-cloud normalisation denominator (desc.vox_stats >= 1, normalize) */
+  float *prep;              /* pvcnn_pvconv_prep_floats(desc), or NULL: per-block buffer that survives between inference
+                               calls (training == 0); see desc.prepared */
 } pvcnn_pvconv_ws;
 
 /* 1 when the grid-sized `lo` buffers (g0_lo, z1_lo, gy2_lo, gy1_lo) must be provided (3xTF32 mode: the weight-
@@ -236,6 +240,7 @@ typedef struct { /* caller-allocated device buffers (element counts in comments)
 PVCNN_API int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_sparse_ints(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d);
+PVCNN_API long long pvcnn_pvconv_prep_floats(const pvcnn_pvconv_desc *d);
 PVCNN_API long long pvcnn_pvconv_partials_floats(const pvcnn_pvconv_desc *d);
 /* features [b,cin,n], coords [b,3,n] -> out [b,cout,n] */
 PVCNN_API int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, const float *coords,

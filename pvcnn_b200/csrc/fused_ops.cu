@@ -1104,9 +1104,12 @@ __global__ void __launch_bounds__(256) fill_class_rows_kernel(int r, int cp, con
 }
 
 int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
-                           const float *bias1, BnCoef bn1, float *classsum, float *tapsum, float *out, cudaStream_t s) {
-  PVB_LAUNCH(conv_const_taps_kernel, 27, 128, cin * sizeof(float), s, cin, cout, slope, w, bias1, bn1, tapsum);
-  PVB_LAUNCH(conv_const_classes_kernel, 27, 128, 0, s, cout, cp_out, bias2, tapsum, classsum);
+                           const float *bias1, BnCoef bn1, float *classsum, float *tapsum, float *out, cudaStream_t s,
+                           int tables_ready) {
+  if (!tables_ready) {   // the 27 class constants depend on the parameters only
+    PVB_LAUNCH(conv_const_taps_kernel, 27, 128, cin * sizeof(float), s, cin, cout, slope, w, bias1, bn1, tapsum);
+    PVB_LAUNCH(conv_const_classes_kernel, 27, 128, 0, s, cout, cp_out, bias2, tapsum, classsum);
+  }
   PVB_LAUNCH(fill_class_rows_kernel, nb * r * r, 256, 0, s, r, cp_out, classsum, out);
   return 0;
 }

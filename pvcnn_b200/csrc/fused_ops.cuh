@@ -103,7 +103,7 @@ int launch_bn_bwd_units(int max_units, int r, int ty, int c, int cp, float slope
 int launch_fill_bias_rows(long long rows, int c, int cp, const float *bias, float *out, cudaStream_t s);
 int launch_fill_const_conv(int nb, int r, int cin, int cout, int cp_out, float slope, const float *w, const float *bias2,
                            const float *bias1, BnCoef bn1, float *classsum /*[27][cp_out]*/, float *tapsum /*[27][cout]*/, float *out,
-                           cudaStream_t s);
+                           cudaStream_t s, int tables_ready = 0);
 
 // small helpers
 int launch_memset_f32(float *p, long long n, cudaStream_t s);

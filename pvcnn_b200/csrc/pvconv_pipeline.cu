@@ -147,6 +147,13 @@ extern "C" {
 
 long long pvcnn_pvconv_wprep_floats(const pvcnn_pvconv_desc *d) { return wprep_layout(d).total; }
 
+/* ws->prep (inference): [3 BatchNorm coefficient sets: 12*co][conv2 class constants 27*co][tap sums 27*co][forward GEMM
+ * operands of conv1, conv2 and the point branch] */
+long long pvcnn_pvconv_prep_floats(const pvcnn_pvconv_desc *d) {
+  const long long co = (d->cout + 3) / 4 * 4;
+  return 66 * co + wprep_layout(d).w1d;
+}
+
 int pvcnn_pvconv_needs_grid_lo(const pvcnn_pvconv_desc *d) { return needs_grid_lo(d) ? 1 : 0; }
 
 long long pvcnn_pvconv_sparse_ints(const pvcnn_pvconv_desc *d) {
@@ -203,12 +210,21 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
     PVB_TRY(launch_memset_f32(ws->g0_lo, Mv * ci, s));
     PVB_TRY(launch_grid_lo_at_points(b, n, r3, ci, ws->ind, ws->g0, ws->g0_lo, s));
   }
-  // 3. weights -> GEMM operands
-  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 27, 0, ld32(d->cin), prm->w1, wp + W.w1f, wp + W.w1f + W.n1f, stream));
-  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cout, 27, 0, ld32(d->cout), prm->w2, wp + W.w2f, wp + W.w2f + W.n2f, stream));
-  PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 1, 0, ld32(d->cin), prm->wp, wp + W.wpf, wp + W.wpf + W.npf, stream));
+  // 3. weights -> GEMM operands.  Inference with ws->prep: operands, BatchNorm coefficients and the conv2 constant tables
+  //    live in the caller's per-block buffer and are rebuilt only when desc.prepared == 0 (parameters changed).
+  const bool frozen = !d->training && ws->prep != nullptr;
+  const bool have_prep = frozen && d->prepared;
+  float *coef_base = frozen ? ws->prep : ws->coef;
+  float *cls_tab = frozen ? ws->prep + 12 * (size_t)co : sp.classsum;
+  float *tap_tab = frozen ? ws->prep + 39 * (size_t)co : sp.tapsum;
+  if (frozen) wp = ws->prep + 66 * (size_t)co;
+  if (!have_prep) {
+    PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 27, 0, ld32(d->cin), prm->w1, wp + W.w1f, wp + W.w1f + W.n1f, stream));
+    PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cout, 27, 0, ld32(d->cout), prm->w2, wp + W.w2f, wp + W.w2f + W.n2f, stream));
+    PVB_TRY(pvcnn_conv_weight_prep(d->cout, d->cin, 1, 0, ld32(d->cin), prm->wp, wp + W.wpf, wp + W.wpf + W.npf, stream));
+  }
 
-  BnCoef bn1 = coef_at(ws->coef, 0, co), bn2 = coef_at(ws->coef, 1, co), bnp = coef_at(ws->coef, 2, co);
+  BnCoef bn1 = coef_at(coef_base, 0, co), bn2 = coef_at(coef_base, 1, co), bnp = coef_at(coef_base, 2, co);
   // 4. conv1 -> BN1 -> LeakyReLU                                   (modules/pvconv.py:21-23)
   if (sparse) {  // zero neighbourhood -> conv1 = bias; only the listed units run on the tensor cores
     PVB_TRY(launch_fill_bias_rows(Mv, d->cout, co, prm->b1, ws->y1, s));
@@ -222,13 +238,14 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
     PVB_TRY(launch_bn_stats(Mv, co, ws->y1, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g1, prm->be1,
                                prm->rm1, prm->rv1, bn1, s, prm->nbt1));
-  } else {
+  } else if (!have_prep) {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g1, prm->be1, prm->rm1, prm->rv1, bn1, s));
   }
   PVB_TRY(launch_bn_apply_leaky(Mv, co, d->slope, ws->y1, bn1, ws->z1, glo ? ws->z1_lo : nullptr, s));
   // 5. conv2 -> BN2 statistics (BN2-apply + LeakyReLU are folded into the devoxelize gather)
   if (sparse) {  // constant neighbourhood -> conv2 = one of 27 boundary-class constants
-    PVB_TRY(launch_fill_const_conv(b, r, d->cout, d->cout, co, d->slope, prm->w2, prm->b2, prm->b1, bn1, sp.classsum, sp.tapsum, ws->y2, s));
+    PVB_TRY(launch_fill_const_conv(b, r, d->cout, d->cout, co, d->slope, prm->w2, prm->b2, prm->b1, bn1, cls_tab, tap_tab,
+                                   ws->y2, s, have_prep ? 1 : 0));
     PVB_TRY(conv_halo_launch(b, r, r, r, d->cout, d->cout, ws->z1, co, wp + W.w2f, wp + W.w2f + W.n2f, ld32(d->cout),
                              prm->b2, ws->y2, co, d->npass, s, sp.fwd2, sp.counts + 2));
   } else {
@@ -239,7 +256,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
     PVB_TRY(launch_bn_stats(Mv, co, ws->y2, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mv, d->bn_eps_vox, d->momentum, ws->partials, prm->g2, prm->be2,
                                prm->rm2, prm->rv2, bn2, s, prm->nbt2));
-  } else {
+  } else if (!have_prep) {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_vox, prm->g2, prm->be2, prm->rm2, prm->rv2, bn2, s));
   }
   // 6. point branch: 1x1 conv as a GEMM over all points             (modules/shared_mlp.py:10-12)
@@ -249,7 +266,7 @@ int pvcnn_pvconv_forward(const pvcnn_pvconv_desc *d, const float *features, cons
     PVB_TRY(launch_bn_stats(Mp, co, ws->p, ws->partials, &nblk, s));
     PVB_TRY(launch_bn_finalize(nblk, d->cout, co, Mp, d->bn_eps_pt, d->momentum, ws->partials, prm->gp, prm->bep,
                                prm->rmp, prm->rvp, bnp, s, prm->nbtp));
-  } else {
+  } else if (!have_prep) {
     PVB_TRY(launch_bn_coef_from_running(d->cout, d->bn_eps_pt, prm->gp, prm->bep, prm->rmp, prm->rvp, bnp, s));
   }
   // 6b. SE3d gate from the pooled (post BN2 + LeakyReLU) grid                  (modules/se.py:16-17)

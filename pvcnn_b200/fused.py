@@ -22,7 +22,7 @@ class Desc(ctypes.Structure):
                 ("r", ctypes.c_int), ("normalize", ctypes.c_int), ("eps", ctypes.c_float),
                 ("training", ctypes.c_int), ("npass", ctypes.c_int), ("bn_eps_vox", ctypes.c_float),
                 ("bn_eps_pt", ctypes.c_float), ("momentum", ctypes.c_float), ("slope", ctypes.c_float),
-                ("with_se", ctypes.c_int), ("vox_stats", ctypes.c_int)]
+                ("with_se", ctypes.c_int), ("vox_stats", ctypes.c_int), ("prepared", ctypes.c_int)]
 
 
 _PARAM_FIELDS = ["w1", "b1", "g1", "be1", "rm1", "rv1", "w2", "b2", "g2", "be2", "rm2", "rv2",
@@ -32,7 +32,7 @@ _WS_FIELDS = [("nc", _F), ("vc", _I), ("ind", _I), ("cnt", _I), ("fcl", _F), ("f
               ("g0_lo", _F), ("y1", _F), ("z1", _F), ("z1_lo", _F), ("y2", _F), ("p", _F), ("coef", _F),
               ("wprep", _F), ("partials", _F), ("sums", _F), ("ga", _F), ("gpp", _F), ("gpp_lo", _F),
               ("gfpt", _F), ("d2", _F), ("gy2", _F), ("gy2_lo", _F), ("gy1", _F), ("gy1_lo", _F), ("sparse", _I), ("se", _F),
-              ("vox_mean", _F), ("vox_denom", _F)]
+              ("vox_mean", _F), ("vox_denom", _F), ("prep", _F)]
 
 
 class Params(ctypes.Structure):
@@ -167,7 +167,7 @@ class _PVConvFused(Function):
         training = bool(module.training)
         vox = module.voxelization
         desc = Desc(b, n, cin, module.out_channels, int(module.resolution), int(bool(vox.normalize)), float(vox.eps),
-                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1, int(se_w1 is not None), 0)
+                    int(training), precision_passes(), 1e-4, 1e-5, 0.1, 0.1, int(se_w1 is not None), 0, 0)
         bns = [module.voxel_layers[1], module.voxel_layers[4], module.point_features.layers[1]]
         desc.bn_eps_vox = float(bns[0].eps)
         desc.bn_eps_pt = float(bns[2].eps)
@@ -201,6 +201,23 @@ class _PVConvFused(Function):
                 t += 1
         out = torch.empty((b, module.out_channels, n), dtype=torch.float32, device=dev)
         _poison([out])
+        if not training and not torch.is_grad_enabled() and os.environ.get("PVCNN_B200_PVCONV_EVAL", "cached") != "rebuild":
+            # frozen block: GEMM operands, BatchNorm coefficients and the conv2 constants are rebuilt only when a parameter
+            # or running statistic changed (in-place updates bump the version counter, re-assignment changes the pointer)
+            tensors = [t for t in keep[:18] if t is not None]
+            key = tuple((t.data_ptr(), t._version) for t in tensors) + (str(dev), float(desc.bn_eps_vox),
+                                                                       float(desc.bn_eps_pt), float(desc.slope))
+            cache = getattr(module, "_pvcnn_eval_prep", None)
+            if cache is None or cache[0] != key:
+                lib = _lib.load()
+                lib.pvcnn_pvconv_prep_floats.restype = ctypes.c_longlong
+                prep = torch.empty(lib.pvcnn_pvconv_prep_floats(ctypes.byref(desc)), dtype=torch.float32, device=dev)
+                module._pvcnn_eval_prep = (key, prep)
+                desc.prepared = 0
+            else:
+                prep = cache[1]
+                desc.prepared = 1
+            plan.t["prep"] = prep
         ws = plan.struct()
         _lib.call("pvcnn_pvconv_forward", ctypes.byref(desc), features, coords, ctypes.byref(prm), ctypes.byref(ws),
                   out, device=dev)

@@ -143,6 +143,56 @@ def test_pvconv_running_stats_and_eval_mode(monkeypatch):
     assert rel_err(out.cpu().numpy(), refe["out"]) < 1e-5
 
 
+@pytest.mark.parametrize("c,r,se", [(16, 8, False), (32, 16, True), (64, 12, False)])
+def test_pvconv_inference_cache_of_frozen_operands(c, r, se, monkeypatch):
+    """Inference keeps a block's GEMM operands, BatchNorm coefficients and conv2 class constants between calls
+    (desc.prepared / ws->prep).  Cached calls equal rebuilding them every time (to the run-to-run noise of the scatter-mean's
+    atomic adds, ~1e-7), also with another batch, and an in-place parameter / running-statistic update invalidates the
+    cache."""
+    from pvcnn_b200 import _lib
+    monkeypatch.setenv("PVCNN_B200_PVCONV", "fused_strict")
+    g = rng(34)
+    b, n = 2, 1024
+    m = make_block(c, c, r, with_se=se).cuda()
+    with torch.no_grad():
+        for bn in (m.voxel_layers[1], m.voxel_layers[4], m.point_features.layers[1]):
+            bn.running_mean.normal_(0, 0.1)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.2)
+    m.eval()
+    f = torch.from_numpy(g.standard_normal((b, c, n), dtype=np.float32)).cuda()
+    co = torch.from_numpy(s3dis_like_coords(g, b, n)).cuda()
+    f2 = torch.from_numpy(g.standard_normal((3, c, 700), dtype=np.float32)).cuda()
+    co2 = torch.from_numpy(s3dis_like_coords(g, 3, 700)).cuda()
+    with torch.no_grad():
+        first, _ = m((f, co))                 # builds the cache
+        l0 = _lib.launch_count()
+        cached, _ = m((f, co))
+        l1 = _lib.launch_count()
+        cached2, _ = m((f2, co2))             # other batch shape, same cache
+        monkeypatch.setenv("PVCNN_B200_PVCONV_EVAL", "rebuild")
+        l2 = _lib.launch_count()
+        rebuilt, _ = m((f, co))
+        l3 = _lib.launch_count()
+        rebuilt2, _ = m((f2, co2))
+        monkeypatch.delenv("PVCNN_B200_PVCONV_EVAL")
+    err = lambda a, c: rel_err(a.cpu().numpy(), c.cpu().numpy())
+    same = lambda a, c: err(a, c) < 1e-5
+    assert same(first, cached) and same(cached, rebuilt) and same(cached2, rebuilt2), (
+        err(first, cached), err(cached, rebuilt), err(cached2, rebuilt2))
+    assert (l3 - l2) - (l1 - l0) >= 6, (l1 - l0, l3 - l2)   # 3 weight preps + 3 coefficient kernels (+ 2 constant tables) skipped
+    refe = run_oracle(m, f.cpu().numpy(), co.cpu().numpy(), None, r, training=False, dtype="float64", with_se=se)
+    assert rel_err(cached.cpu().numpy(), refe["out"]) < 1e-5
+    with torch.no_grad():
+        m.voxel_layers[3].weight.mul_(0.7)
+        m.point_features.layers[1].running_mean.add_(0.1)
+        changed, _ = m((f, co))
+        monkeypatch.setenv("PVCNN_B200_PVCONV_EVAL", "rebuild")
+        want, _ = m((f, co))
+    assert same(changed, want) and not same(changed, cached)
+
+
 def test_precision_modes(monkeypatch):
     """tf32 mode = one tensor-core pass (the reference's cuDNN default precision): ~1e-3, not 1e-5."""
     g = rng(33)
