@@ -59,9 +59,9 @@ struct IgemmParams {
   float *out;
   int *err;
   IgemmEpilogue ep;
-  int dbg;            // bring-up switches (PVCNN_IGEMM_DBG): 1 = no global stores, 4 = no MMAs
 };
 
+template <bool THREE>
 __global__ void __launch_bounds__(IG_THREADS, 1)
     igemm_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_a_hi);
     prefetch_tensormap(&map_w_hi);
-    if (p.npass > 1) {
+    if (THREE) {
       prefetch_tensormap(&map_a_lo);
       prefetch_tensormap(&map_w_lo);
     }
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
           mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
           tma_load_5d(st, &map_a_hi, &full_bar[stage], cc * IG_KC, z0 + dz, y0 + dy, x0 + dx, b);
           tma_load_3d(st + p.a_bytes, &map_w_hi, &full_bar[stage], cc * IG_KC, n_tile * p.block_n, tap);
-          if (p.npass > 1) {
+          if (THREE) {
             tma_load_5d(st + IG_A_TILE_BYTES, &map_a_lo, &full_bar[stage], cc * IG_KC, z0 + dz, y0 + dy, x0 + dx, b);
             tma_load_3d(st + p.a_bytes + p.b_bytes / 2, &map_w_lo, &full_bar[stage], cc * IG_KC, n_tile * p.block_n,
                         tap);
@@ -146,31 +146,37 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
         tc_fence_after();
         const uint32_t tile_tmem = tmem_base + (uint32_t)(acc * p.acc_slots * p.block_n);
         const uint32_t corr_tmem = tile_tmem + (uint32_t)(p.acc_split * p.block_n);
-        int prev_slot = -1;
+        // k-blocks are dealt to the main accumulators in contiguous ranges: slot = floor(kb * acc_split / num_kb), tracked
+        // incrementally (this thread's instruction stream is the issue path of every MMA: no divisions in the loop)
+        int slot = 0, slot_rem = 0;
+        bool fresh = true;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, p.err, 3);
           tc_fence_after();
-          // k-blocks are dealt to the main accumulators in contiguous ranges
-          const int slot = (int)(((long long)kb * p.acc_split) / num_kb);
           const uint32_t d_tmem = tile_tmem + (uint32_t)(slot * p.block_n);
-          const bool fresh = slot != prev_slot;
-          prev_slot = slot;
           constexpr uint32_t dhi = desc_hi32(1024, kLayoutSW128);
           const uint32_t a_hi = desc_lo32(smem_u32(smem + (size_t)stage * p.stage_bytes), 0);
-          const uint32_t a_lo = a_hi + (IG_A_TILE_BYTES >> 4);
           const uint32_t b_hi = a_hi + (p.a_bytes >> 4);
-          const uint32_t b_lo = b_hi + (p.b_bytes >> 5);
-          const uint32_t fresh_corr = kb != 0;
+          if (THREE) {
+            const uint32_t a_lo = a_hi + (IG_A_TILE_BYTES >> 4);
+            const uint32_t b_lo = b_hi + (p.b_bytes >> 5);
+            const uint32_t fresh_corr = kb != 0;
 #pragma unroll
-          for (int k = 0; k < IG_KC / 8; ++k) {
-            if (p.dbg & 4) break;
-            const uint32_t ko = (uint32_t)k * 2u;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
-            mma_tf32_lo32(d_tmem, a_hi + ko, b_hi + ko, dhi, idesc, (k == 0) ? (fresh ? 0u : 1u) : 1u);
-            if (p.npass > 1) {
+            for (int k = 0; k < IG_KC / 8; ++k) {
+              const uint32_t ko = (uint32_t)k * 2u;  // advance 8 tf32 = 32 bytes inside the 128B swizzle row
+              mma_tf32_lo32(d_tmem, a_hi + ko, b_hi + ko, dhi, idesc, (k == 0) ? (fresh ? 0u : 1u) : 1u);
               mma_tf32_lo32(corr_tmem, a_hi + ko, b_lo + ko, dhi, idesc, (k == 0) ? fresh_corr : 1u);
               mma_tf32_lo32(corr_tmem, a_lo + ko, b_hi + ko, dhi, idesc, 1u);
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < IG_KC / 8; ++k)
+              mma_tf32_lo32(d_tmem, a_hi + (uint32_t)k * 2u, b_hi + (uint32_t)k * 2u, dhi, idesc,
+                            (k == 0) ? (fresh ? 0u : 1u) : 1u);
           }
+          fresh = false;
+          slot_rem += p.acc_split;
+          if (slot_rem >= num_kb) { slot_rem -= num_kb; ++slot; fresh = true; }
           mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -316,7 +322,6 @@ __global__ void __launch_bounds__(IG_THREADS, 1)
                   o[k] = t > 0.0f ? t : t * p.ep.slope;
                 }
               }
-              if (p.dbg & 1) continue;
               float *dst = p.out + roff[i] + cl;
               if (nv >= 4) {
                 *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -614,7 +619,6 @@ int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, 
   p.tmem_cols = cols;
   p.bias = bias; p.out = out; p.err = g_err_flag;
   if (ep) p.ep = *ep;
-  { const char *e = getenv("PVCNN_IGEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   // B tiles must start 1024-aligned inside the stage: a_bytes is a multiple of 16 KB, b_hi = bn*128 bytes;
   // b_lo starts at b_bytes/2 = bn*128 which is a multiple of 1024 only when bn % 8 == 0 (true: bn % 16 == 0).
 
@@ -639,9 +643,14 @@ int igemm_launch_ep(int nb, int sx, int sy, int sz, int k, int cout, int ntaps, 
     if (rc) return rc;
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + IG_EPI_BYTES;
-  PVB_CUDA(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(kNumSMs, p.num_m_tiles * p.n_tiles);
-  PVB_LAUNCH(igemm_conv_kernel, grid, IG_THREADS, smem, stream, ma_hi, ma_lo, mw_hi, mw_lo, p);
+  if (npass > 1) {
+    PVB_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(igemm_conv_kernel<true>, grid, IG_THREADS, smem, stream, ma_hi, ma_lo, mw_hi, mw_lo, p);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PVB_LAUNCH(igemm_conv_kernel<false>, grid, IG_THREADS, smem, stream, ma_hi, ma_lo, mw_hi, mw_lo, p);
+  }
   return 0;
 }
 

@@ -115,7 +115,7 @@ def _eval_prepared(conv, bn, cin, cout, dev, lib, cols=None):
     return wprep, coef
 
 
-def _mlp_eval(x_cl, x_lo, meta, group_bias=None, group_rows=0):
+def _mlp_eval(x_cl, x_lo, meta, group_bias=None, group_rows=0, want_lo=False):
     """Frozen (eval-mode) stack: per layer one GEMM with bias + BatchNorm + ReLU (+ lo split) in its epilogue."""
     lib = _lib_sizes()
     dev = x_cl.device
@@ -143,14 +143,14 @@ def _mlp_eval(x_cl, x_lo, meta, group_bias=None, group_rows=0):
                 tmp = _scratch("mlp_pooltmp", 2 * groups * segs * co, dev)
         else:
             z = torch.empty((rows, co), dtype=torch.float32, device=dev)
-            zl = torch.empty((rows, co), dtype=torch.float32, device=dev) if (npass > 1 and not last) else None
+            zl = torch.empty((rows, co), dtype=torch.float32, device=dev) if (npass > 1 and (not last or want_lo)) else None
         gb = group_bias if li == 0 else None
         _lib.call("pvcnn_mlp_layer_forward_eval", _LL(rows), cin, cout, npass, x, xl, wprep,
                   None if conv.bias is None else conv.bias.detach(), coef, _LL(group_rows if gb is not None else 0), gb,
                   0 if gb is None else gb.shape[1], y, z, zl, pool, pooled, argmax, tmp, device=dev)
         out = pooled if pool else z
         x, xl, cin = z, zl, cout
-    return out
+    return (out, xl) if want_lo else out
 
 
 class _MLP(Function):
@@ -277,12 +277,14 @@ def native_supported(layers):
     return True
 
 
-def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True, point_cols=None, group_bias=None, group_rows=0):
+def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True, point_cols=None, group_bias=None, group_rows=0,
+           want_lo=False):
     """Run the (conv, bn, relu)* stack `layers` on channels-last rows.  Returns [rows, pad4(cout)] (or pooled).
 
     point_cols / group_bias / group_rows: the first layer's input is the reference's concatenation restricted to the
     channel ranges `point_cols`; the remaining channels are constant over each cloud of `group_rows` rows and enter as
-    group_bias [clouds, pad4(cout)] = their part of the weight applied once per cloud (see head_cl)."""
+    group_bias [clouds, pad4(cout)] = their part of the weight applied once per cloud (see head_cl).
+    want_lo: return (out, out_lo | None); the lo operand of the next 3xTF32 GEMM comes for free from the inference epilogue."""
     mods = list(layers)
     convs, bns = mods[0::3], mods[1::3]
     training = bool(bns[0].training)
@@ -305,8 +307,9 @@ def mlp_cl(layers, x_cl, x_lo, pool_u=0, input_needs_grad=True, point_cols=None,
     if fused_eval:
         # inference: frozen-layer path (cached weight operands / BatchNorm coefficients, activation fused into the GEMM)
         return _mlp_eval(x_cl.detach(), None if x_lo is None else x_lo.detach(), meta,
-                         None if group_bias is None else group_bias.detach(), group_rows)
-    return _run(_MLP, x_cl, x_lo, group_bias, meta, *params)
+                         None if group_bias is None else group_bias.detach(), group_rows, want_lo=want_lo)
+    out = _run(_MLP, x_cl, x_lo, group_bias, meta, *params)
+    return (out, None) if want_lo else out
 
 
 def shared_mlp_forward(layers, x):
@@ -499,17 +502,17 @@ def head_cl(seq, rows, lo, b, n, point_cols=None, group_bias=None):
     x, xl, cout = rows, lo, None
     for m in mods:
         if isinstance(m, torch.nn.Dropout):
-            x = torch.nn.functional.dropout(x, m.p, m.training)   # element-wise i.i.d.: layout-agnostic
-            xl = None
+            if m.training and m.p > 0:
+                x = torch.nn.functional.dropout(x, m.p, True)   # element-wise i.i.d.: layout-agnostic
+                xl = None
         elif isinstance(m, SharedMLP):
             if xl is None and precision_passes() > 1:
                 from . import dense
                 xl = dense.split_tf32(x.contiguous(), want_hi=False)[1]
             if m is mods[0] and group_bias is not None:
-                x = mlp_cl(m.layers, x, xl, point_cols=point_cols, group_bias=group_bias, group_rows=n)
+                x, xl = mlp_cl(m.layers, x, xl, point_cols=point_cols, group_bias=group_bias, group_rows=n, want_lo=True)
             else:
-                x = mlp_cl(m.layers, x, xl)
-            xl = None
+                x, xl = mlp_cl(m.layers, x, xl, want_lo=True)
             cout = list(m.layers)[-3].out_channels
         else:
             x = _run(_LinearCL, x, xl, m.weight, m.bias)
