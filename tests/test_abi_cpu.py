@@ -103,6 +103,7 @@ def test_invalid_arguments_are_rejected_before_any_gpu_work():
     null = ctypes.c_void_p(0)
     i = ctypes.c_int
     f = ctypes.c_float
+    ll, ull = ctypes.c_longlong, ctypes.c_ulonglong
     cases = {
         "pvcnn_avg_voxelize": [i(0), i(4), i(8), i(2), i(4), i(8), null, null, null, null, null, null],
         "pvcnn_avg_voxelize_grad": [i(1), i(4), i(8), i(8), null, null, null, null, null],
@@ -118,10 +119,31 @@ def test_invalid_arguments_are_rejected_before_any_gpu_work():
         "pvcnn_furthest_point_sampling": [i(1), i(8), i(2), null, null, null, null],
         "pvcnn_pvconv_forward": [null, null, null, null, null, null, null],
         "pvcnn_pvconv_backward": [null, null, null, null, null, null, null],
+        # test-time voting (csrc/eval_voting.cu): (b, nv, seed, first_window, num_points, indices, stream) ...
+        "pvcnn_vote_indices": [i(0), i(8), ull(1), i(0), null, null, null],
+        "pvcnn_window_indices": [i(1), i(0), ull(1), i(0), null, null, null],
+        "pvcnn_vote_gather": [i(1), i(3), i(8), i(1), i(8), i(1), null, null, null, null, null, null],
+        "pvcnn_softmax_max": [i(1), i(4), i(8), i(2), i(2), null, null, null, null],
+        "pvcnn_vote_reset": [ll(0), null, null, null],
+        "pvcnn_vote_merge": [i(1), i(8), i(1), ll(10), ctypes.c_uint(0), null, null, null, null, null, null, null],
+        "pvcnn_vote_confidences": [ll(5), null, null, null],
+        "pvcnn_vote_stats": [ll(5), i(5000), i(1), null, null, null, null],
     }
     bad_arg = 100001   # PVCNN_E_BADARG (include/pvcnn_b200.h:38); a CUDA failure would surface as a cudaError_t (< 1000)
     for name, args in cases.items():
         assert getattr(lib, name)(*args) == bad_arg, name
+
+
+def test_voting_host_api_has_no_cpu_path():
+    """pvcnn_b200.evaluate mirrors the reference's evaluation loops on the device only: host tensors raise"""
+    import torch
+    from pvcnn_b200 import _lib, evaluate
+    with pytest.raises(_lib.PvcnnError):
+        evaluate.softmax_max(torch.zeros(1, 3, 8))
+    with pytest.raises(RuntimeError):
+        evaluate.softmax_max(torch.zeros(3, 8))
+    with pytest.raises(RuntimeError):
+        evaluate.vote_inputs(torch.zeros(1, 8, 3), torch.zeros(1, 6, dtype=torch.int32), 4)   # nv % num_points != 0
 
 
 def test_workspace_size_queries_are_host_only_and_consistent():
