@@ -457,49 +457,94 @@ def run_config(args):
     point ops around torch's cuDNN/cuBLAS dense layers (TF32 allowed, the reference's default precision)."""
     import numpy as np
     import torch
+    import torch.distributed as dist
     from pvcnn_b200 import zoo, _lib
+    from pvcnn_b200.parallel import GradBucket, broadcast_parameters, pin_process_to_gpu_numa_node
     os.environ["PVCNN_B200_PRECISION"] = args.precision
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
+    if world > 1:
+        # weak scaling, one process per GPU: the train config (3) is data parallel -- every rank a replica on its own
+        # batch of the configured size, ONE NCCL all-reduce of the flat gradient bucket per step; the inference configs
+        # (2, 4, 5) are replicas only, no collective (SURVEY.md 8e)
+        dist.init_process_group("nccl", device_id=dev)
+        pin_process_to_gpu_numa_node(dev.index)
     torch.manual_seed(SEED)
     model, spec = zoo.build(args.config)
     train = spec["mode"] == "train"
     model = model.to(dev).train(train)
-    g = torch.Generator().manual_seed(SEED)
+    if world > 1:
+        broadcast_parameters(model)
+    g = torch.Generator().manual_seed(SEED + rank)
     x = zoo.synthetic_input(spec, g)
     x = {k: v.to(dev) for k, v in x.items()} if isinstance(x, dict) else x.to(dev)
     bsz, npts = spec["batch"], spec["points"]
     target = torch.randint(0, 50, (bsz, npts), generator=g).to(dev) if train else None
     opt = torch.optim.Adam(model.parameters(), lr=1e-3) if train else None   # configs/shapenet/__init__.py:43-44
+    # data parallel: p.grad of every parameter is a view of one flat buffer (fused PVConv blocks write there directly,
+    # the other layers accumulate through autograd), averaged by a single all-reduce in bucket.finish()
+    bucket = GradBucket(list(model.parameters()), dev).attach(model) if (train and world > 1) else None
 
     def step():
         if train:
-            opt.zero_grad(set_to_none=True)
+            if bucket is not None:
+                bucket.zero()
+            else:
+                opt.zero_grad(set_to_none=True)
             loss = torch.nn.functional.cross_entropy(model(x), target)
             loss.backward()
+            if bucket is not None:
+                bucket.finish()
             opt.step()
             return loss
         with torch.no_grad():
             return model(x)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     def timed(nsteps, nwarm):
         np.random.seed(0)
         for _ in range(nwarm):
             step()
-        torch.cuda.synchronize()
+        barrier()
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(nsteps):
             step()
         e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / nsteps, (_lib.launch_count() - l0) // nsteps
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / nsteps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # the slowest rank defines the step
+        return float(t[0]), (_lib.launch_count() - l0) // nsteps
 
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    if sampler:
+        sampler.start()
     ms, launches = timed(args.steps, args.warmup)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
+    what = {"s3dis_pvcnn": "S3DIS PVCNN (1xC) forward", "shapenet_c0p25_train": "ShapeNet PVCNN (0.25xC) train step (Adam)",
+            "pvcnn2": "S3DIS PVCNN++ forward", "frustum_pvcnne": "KITTI Frustum-PVCNN(E) end-to-end inference"}[args.config]
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({
+                "metric": "%s points/sec (B=%d/GPU,N=%d)" % (what, bsz, npts), "value": world * bsz * npts / ms * 1e3,
+                "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+                "dtype": "f32 (3xTF32)" if args.precision == "fp32" else "tf32",
+                "config": {"workload": "%s, random-init weights, B=%d per GPU N=%d, pvcnn_b200/zoo.py:%s" % (
+                               what, bsz, npts, args.config),
+                           "precision": args.precision,
+                           "parallelism": ("dp%d: one NCCL all-reduce (AVG) of the flat gradient bucket per step" % world)
+                                          if train else ("%d independent replicas, no collective" % world)},
+                "clocks": clocks, "gpu_launches": int(launches)}))
+        dist.destroy_process_group()
+        return
     graphed = None
     if not train:
         try:   # the same forward as one CUDA-graph replay (eager runs are bound by the host's launch rate)
@@ -526,8 +571,6 @@ def run_config(args):
     torch.backends.cudnn.benchmark = True
     ms_cmp, _ = timed(max(3, args.steps // 2), args.warmup)
     os.environ.pop("PVCNN_B200_PVCONV"); os.environ.pop("PVCNN_B200_MLP")
-    what = {"s3dis_pvcnn": "S3DIS PVCNN (1xC) forward", "shapenet_c0p25_train": "ShapeNet PVCNN (0.25xC) train step (Adam)",
-            "pvcnn2": "S3DIS PVCNN++ forward", "frustum_pvcnne": "KITTI Frustum-PVCNN(E) end-to-end inference"}[args.config]
     print(json.dumps({
         "metric": "%s points/sec (B=%d,N=%d)" % (what, bsz, npts), "value": bsz * npts / ms * 1e3, "unit": "points/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
