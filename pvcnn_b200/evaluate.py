@@ -109,7 +109,7 @@ class SceneVotes:
         """confidences fp32 / predictions int32 / indices int32, all [b, nv]; window_to_scene_mapping int [b, P] = the rows
         of `indices_split_to_full` of these windows (None: shapenet, the index is the point)."""
         b, nv = indices.shape
-        confidences = confidences.reshape(b, nv).contiguous()
+        confidences = confidences.reshape(b, nv).to(torch.float32).contiguous()
         predictions = predictions.reshape(b, nv).to(torch.int32).contiguous()
         indices = indices.to(torch.int32).contiguous()
         p = 1
