@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["vote_indices", "window_indices", "vote_inputs", "softmax_max", "SceneVotes", "evaluate_scene_file",
-           "evaluate_shape", "sample_windows"]
+           "evaluate_shape", "sample_windows", "scenes_of_rank", "all_reduce_stats"]
 
 
 _DEFAULT_DEVICE = "cuda"   # every kernel of this module needs a CUDA device; the tensors decide which one
@@ -194,3 +194,24 @@ def sample_windows(window_data, window_labels, window_num_points, num_points, se
     idx = window_indices(window_num_points, num_points, seed, first_window, window_data.device)
     data, labels = vote_inputs(window_data, idx, num_points, labels=window_labels)
     return data, labels.long()
+
+
+# ---- multi-GPU: scenes (shapes) are independent units ------------------------------------------------
+def scenes_of_rank(num_scenes, rank=None, world=None):
+    """Scene indices evaluated by this rank: round-robin over the ranks (scene sizes vary by an order of magnitude, so
+    interleaving balances better than contiguous blocks).  No data-path collective: every rank runs whole scenes."""
+    import torch.distributed as dist
+    if rank is None or world is None:
+        on = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank() if on else 0
+        world = dist.get_world_size() if on else 1
+    return list(range(rank, int(num_scenes), world))
+
+
+def all_reduce_stats(stats, group=None):
+    """The one exchange step of a sharded evaluation: `stats` [3, classes, scenes] (eval.py:130) holds this rank's scenes'
+    columns and zeros elsewhere; a SUM all-reduce gives every rank the full table.  int64 counters, NCCL or gloo."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats

@@ -80,3 +80,41 @@ def test_shard_batch_covers_everything():
         parts = [shard_batch(x, r, world) for r in range(world)]
         assert torch.equal(torch.cat(parts), x)
     assert shard_batch(torch.arange(5).view(5, 1), 2, 4).numel() == 1  # ragged tail
+
+
+def _eval_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pvcnn_b200 import evaluate as E
+    num_scenes, classes = 7, 13
+    mine = E.scenes_of_rank(num_scenes)
+    stats = torch.zeros(3, classes, num_scenes, dtype=torch.int64)
+    for s in mine:   # stand-in for SceneVotes.stats of scene s (the kernels need a GPU; the exchange step does not)
+        g = torch.Generator().manual_seed(1000 + s)
+        stats[:, :, s] = torch.randint(0, 10_000, (3, classes), generator=g)
+    E.all_reduce_stats(stats)
+    if rank == 0:
+        out.put((mine, stats))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_scenes_and_stats_exchange_gloo_world2():
+    """evaluation shards over whole scenes (round-robin), one SUM all-reduce of the [3, classes, scenes] counters"""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    mine, stats = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert mine == [0, 2, 4, 6]
+    for s in range(7):
+        g = torch.Generator().manual_seed(1000 + s)
+        assert torch.equal(stats[:, :, s], torch.randint(0, 10_000, (3, 13), generator=g))
+    from pvcnn_b200 import evaluate as E
+    assert E.scenes_of_rank(5, 1, 3) == [1, 4] and E.scenes_of_rank(2, 0, 1) == [0, 1]
