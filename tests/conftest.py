@@ -7,10 +7,25 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from util import host_threads  # noqa: E402
+
+# The CPU references (torch fp64 conv3d / matmul, the OpenMP C oracle) default to one thread per HARDWARE thread of the
+# node; inside a container with a smaller CPU quota that oversubscription is catastrophic for torch's CPU conv3d (measured
+# by bench.py's cpu_baseline on a GPU box: 4.2 s/step with 128 threads vs 0.16 s with 8-32).  Cap them once, before torch
+# and libgomp read the environment; results do not depend on it (fp64 references, 1e-5 tolerances).
+os.environ.setdefault("OMP_NUM_THREADS", str(host_threads()))
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    try:
+        import torch
+        torch.set_num_threads(host_threads())
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def _has_gpu():

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle
-from util import rng, s3dis_like_coords, rel_err, device_mean
+from util import rng, s3dis_like_coords, rel_err, device_mean, host_threads
 
 pytestmark = pytest.mark.gpu
 
@@ -386,7 +386,7 @@ def test_pvconv_metric_config_vs_fp64_oracle(monkeypatch):
     m = make_block(c, c, r).cuda().train()
     params = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()
               if "running" not in k and "num_batches" not in k}
-    ref = oracle.pvconv_forward_backward(params, f, co, go, r, training=True, dtype="float64", threads=os.cpu_count(),
+    ref = oracle.pvconv_forward_backward(params, f, co, go, r, training=True, dtype="float64", threads=host_threads(),
                                          vox_mean=device_mean(co))
     out, gin, pg = _step(m, torch.from_numpy(f).cuda(), torch.from_numpy(co).cuda(), torch.from_numpy(go).cuda())
     assert rel_err(out.cpu().numpy(), ref["out"]) < 1e-5

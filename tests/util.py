@@ -1,4 +1,6 @@
 """Shared input generators for the parity tests (seeded, config-by-config)."""
+import os
+
 import numpy as np
 
 SEED = 1588147245  # the reference's own seed (configs/__init__.py:3)
@@ -61,3 +63,20 @@ def reference_voxelization(coords_t, r, normalize=True, eps=0.0):
         norm_coords = (norm_coords + 1) / 2.0
     norm_coords = torch.clamp(norm_coords * r, 0, r - 1)
     return norm_coords, torch.round(norm_coords).to(torch.int32)
+
+
+def host_threads(cap=32):
+    """Threads for the CPU references: the scheduler affinity and the cgroup CPU quota bound what this process can really
+    use (os.cpu_count() reports the whole node), and more than ~32 does not help the sizes tested here."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, cap))
