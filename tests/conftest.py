@@ -39,9 +39,6 @@ def _has_gpu():
         return False
 
 
-# GPU run order: the hot path's own parity tests first, wider rows after them
-_GPU_ORDER = ["test_pvconv_gpu", "test_ops_gpu", "test_igemm_gpu", "test_mlp_gpu", "test_modules_gpu", "test_network_gpu",
-              "test_models_gpu", "test_voting_gpu", "test_parallel_gpu"]
 # Safety net, not a feature: the round-end driver kills `pytest -m gpu` at 1200 s (GPUTEST_r01.json: step timeout_s 1200;
 # round 1 took 820 s for 107 tests, this suite has 222).  A killed run reports nothing, so past this many seconds since
 # start-up the REMAINING gpu tests are skipped with an explicit reason (visible in the summary as skips, never as passes).
@@ -51,10 +48,6 @@ _GPU_BUDGET_S = float(os.environ.get("PVCNN_TEST_BUDGET_S", "960"))
 
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
-        def rank(item):
-            name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
-            return _GPU_ORDER.index(name) if name in _GPU_ORDER else -1   # CPU tests (if selected) keep their place up front
-        items.sort(key=rank)   # stable: the order inside a file is unchanged
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
