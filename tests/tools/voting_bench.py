@@ -11,7 +11,7 @@ points per window, 13 classes; scene of 1 M points.
               time of that step is printed for information and is not part of `ms_total`.)
   device arm  pvcnn_b200.evaluate: vote_indices + vote_inputs + softmax_max + SceneVotes.update, CUDA events.
 
-  python tools/voting_bench.py [--host-only] [--iters 20]
+  python tests/tools/voting_bench.py [--host-only] [--iters 20]
 """
 import argparse
 import importlib.util
@@ -23,7 +23,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 BATCH, P, CH, NPO, VOTES, CLASSES, SCENE = 10, 8192, 9, 4096, 1, 13, 1_000_000
