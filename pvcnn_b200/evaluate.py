@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["vote_indices", "window_indices", "vote_inputs", "softmax_max", "SceneVotes", "evaluate_scene_file",
-           "evaluate_shape", "sample_windows", "scenes_of_rank", "all_reduce_stats"]
+           "evaluate_shape", "shape_iou", "sample_windows", "scenes_of_rank", "all_reduce_stats"]
 
 
 _DEFAULT_DEVICE = "cuda"   # every kernel of this module needs a CUDA device; the tensors decide which one
@@ -186,6 +186,16 @@ def evaluate_shape(model, point_set, *, num_points, num_votes, start_class, end_
         conf, pred = softmax_max(model(inputs), start_class, end_class)                    # shapenet eval.py:158-162
     votes.update(conf.view(1, -1), pred.view(1, -1), idx, None)
     return votes
+
+
+def shape_iou(counts, start_class, end_class):
+    """update_stats of evaluate/shapenet/eval.py:184-197 from the [3, classes] counters of `SceneVotes.stats(...,
+    wrap_unvoted=False)`: mean over the shape's part classes of intersection / union, 1 where the union is empty
+    (union = |gt == i| + |pred == i| - |both|).  Host arithmetic on <= 50 numbers."""
+    c = torch.as_tensor(counts).to("cpu", torch.float64)[:, int(start_class):int(end_class)]
+    union = c[0] + c[1] - c[2]
+    iou = torch.where(union == 0, torch.ones_like(union), c[2] / union.clamp(min=1))
+    return float(iou.mean())
 
 
 def sample_windows(window_data, window_labels, window_num_points, num_points, seed=0, first_window=0):

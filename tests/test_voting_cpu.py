@@ -66,6 +66,8 @@ def test_shape_merge_and_iou_equal_reference_numba(gold, name):
     np.add.at(counts[1], pred[pred >= 0], 1)
     np.add.at(counts[2], c["gt"][c["gt"] == pred], 1)
     assert abs(ev.shape_iou_from_counts(counts, c0, c1) - float(c["iou"])) < 1e-12
+    from pvcnn_b200 import evaluate                       # the product's host-side reduction of the same counters
+    assert abs(evaluate.shape_iou(counts, c0, c1) - float(c["iou"])) < 1e-12
 
 
 def test_sequential_rule_first_vote_wins_ties():

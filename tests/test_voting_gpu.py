@@ -138,6 +138,7 @@ def test_shape_merge_and_iou_equal_reference_numba_outputs(gold, name):
     num_classes, c0, c1 = (int(v) for v in c["classes"])
     counts = votes.stats(c["gt"], num_classes, wrap_unvoted=False).cpu().numpy()
     assert abs(ev.shape_iou_from_counts(counts, c0, c1) - float(c["iou"])) < 1e-12       # shapenet eval.py:184-197
+    assert abs(E.shape_iou(counts, c0, c1) - float(c["iou"])) < 1e-12
 
 
 @pytest.mark.parametrize("n,num_classes", [(1, 13), (1000, 13), (1 << 20, 50), (3_000_001, 2048)])
