@@ -358,6 +358,15 @@ def single_gpu_extras(torch, dev, m, args):
                                        "(allow_tf32=True, what the reference runs), [1] allow_tf32=False (fp32-strict)")
     except Exception as e:  # noqa: BLE001
         extra["reference_gpu"] = {"unavailable": repr(e)[:200]}
+    # test-time voting around the network (pvcnn_b200/evaluate.py): device arm with CUDA events next to
+    # the reference's own host steps (numpy tiling / shuffle / gather + merge) on this box's cores; informational
+    try:
+        import voting_bench   # tests/tools: its host arm is a CPU baseline leg (reference numba function or oracle restatement)
+        extra["voting"] = {"workload": "one S3DIS evaluation batch: 10 windows x 8192 points x 9 channels, num_points 4096, "
+                                       "81920 voted points, 13 classes (evaluate/s3dis/eval.py:149-183 without the network)",
+                           "device": voting_bench.device_arm(20), "host": voting_bench.host_arm(3)}
+    except Exception as e:  # noqa: BLE001
+        extra["voting"] = {"unavailable": repr(e)[:200]}
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
     return extra
 

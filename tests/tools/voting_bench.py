@@ -81,9 +81,13 @@ def host_arm(iters):
             t_soft += t2 - t1
             t_merge += t3 - t2
         del inputs
-    return {"arm": "host", "merge": kind, "threads_torch": torch.get_num_threads(), "cores": os.cpu_count(),
+    # the numpy restatement of the merge is a checker (a lexsort), not a stand-in for the reference's compiled numba loop:
+    # where the reference tree is absent (the GPU box) the total counts the tiling only (97 % of the reference's host time)
+    counted = (t_tile + t_merge) if kind == "reference numba function" else t_tile
+    return {"arm": "host", "merge": kind, "merge_counted_in_total": kind == "reference numba function",
+            "threads_torch": torch.get_num_threads(), "cores": os.cpu_count(),
             "ms_tile_shuffle_gather": t_tile / iters * 1e3, "ms_softmax_max_torch_cpu_info_only": t_soft / iters * 1e3,
-            "ms_merge": t_merge / iters * 1e3, "ms_total": (t_tile + t_merge) / iters * 1e3,
+            "ms_merge": t_merge / iters * 1e3, "ms_total": counted / iters * 1e3,
             "voted_points_per_batch": BATCH * nv}
 
 
