@@ -367,8 +367,42 @@ def single_gpu_extras(torch, dev, m, args):
                            "device": voting_bench.device_arm(20), "host": voting_bench.host_arm(3)}
     except Exception as e:  # noqa: BLE001
         extra["voting"] = {"unavailable": repr(e)[:200]}
+    if os.environ.get("PVCNN_BENCH_CONFIGS", "1") != "0":
+        extra["configs"] = configs_subresults(args)
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
     return extra
+
+
+def configs_subresults(args, per_config_timeout=240):
+    """BASELINE.json configs 2-5 (whole networks, pvcnn_b200/zoo.py) as sub-results of the default line, so that the
+    driver's own run records them: each is `bench.py --config <name>` in a child process (a failure or a hang there
+    cannot touch this line), reduced to the numbers profiles/r02_configs.md tabulates.  PVCNN_BENCH_CONFIGS=0 skips it."""
+    out = {}
+    for name in ("s3dis_pvcnn", "shapenet_c0p25_train", "pvcnn2", "frustum_pvcnne"):
+        t0 = time.perf_counter()
+        try:
+            env = dict(os.environ)
+            for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", name, "--steps", "10", "--warmup", "3",
+                                "--precision", args.precision], capture_output=True, text=True, timeout=per_config_timeout,
+                               env=env, cwd=ROOT)
+            lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            if p.returncode != 0 or not lines:
+                out[name] = {"unavailable": "rc=%d %s" % (p.returncode, (p.stderr or "")[-160:])}
+                continue
+            d = json.loads(lines[-1])
+            g, c = d.get("cuda_graph") or {}, d.get("comparison_arm") or {}
+            out[name] = {"metric": d["metric"], "ms_per_step": d["ms_per_step"], "value": d["value"], "unit": d["unit"],
+                         "gpu_launches": d.get("gpu_launches"), "cuda_graph_ms": g.get("ms_per_step"),
+                         "comparison_arm_ms": c.get("ms_per_step"), "wall_s": round(time.perf_counter() - t0, 1)}
+        except subprocess.TimeoutExpired:
+            out[name] = {"unavailable": "timeout after %d s" % per_config_timeout}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"unavailable": repr(e)[:200]}
+    out["note"] = ("10 timed steps after 3 warm-up each, same precision mode as this line; comparison_arm = same network and "
+                   "weights on the stand-alone sm_100a point ops + torch cuDNN/cuBLAS dense layers with TF32 allowed")
+    return out
 
 
 def _host_thread_candidates():
