@@ -369,8 +369,29 @@ def single_gpu_extras(torch, dev, m, args):
         extra["voting"] = {"unavailable": repr(e)[:200]}
     if os.environ.get("PVCNN_BENCH_CONFIGS", "1") != "0":
         extra["configs"] = configs_subresults(args)
+        extra["ops_vs_reference"] = ops_subresults()
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
     return extra
+
+
+def ops_subresults(timeout=240):
+    """The stand-alone ("classic") ops through the C ABI next to the reference's own CUDA kernels (oracle/_ref, built from
+    the unmodified reference sources) on this GPU: tests/tools/ops_bench.py in a child process; median of 20 launches each,
+    algorithmic GB/s where SURVEY.md 8d defines the bytes (profiles/r02_ops_vs_reference.md is the builder-run copy)."""
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "ops_bench.py")], capture_output=True,
+                           text=True, timeout=timeout, env=env, cwd=ROOT)
+        rows = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 and not rows:
+            return {"unavailable": "rc=%d %s" % (p.returncode, (p.stderr or "")[-160:])}
+        return rows
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timeout after %d s" % timeout}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
 
 
 def configs_subresults(args, per_config_timeout=240):
