@@ -362,67 +362,78 @@ def single_gpu_extras(torch, dev, m, args):
     # the reference's own host steps (numpy tiling / shuffle / gather + merge) on this box's cores; informational
     try:
         import voting_bench   # tests/tools: its host arm is a CPU baseline leg (reference numba function or oracle restatement)
-        extra["voting"] = {"workload": "one S3DIS evaluation batch: 10 windows x 8192 points x 9 channels, num_points 4096, "
-                                       "81920 voted points, 13 classes (evaluate/s3dis/eval.py:149-183 without the network)",
-                           "device": voting_bench.device_arm(20), "host": voting_bench.host_arm(3)}
+        dv, hs = voting_bench.device_arm(20), voting_bench.host_arm(3)
+        extra["voting"] = {"workload": "one S3DIS evaluation batch around the network (eval.py:149-183): 10 windows x 8192 "
+                                       "points x 9 ch, 81920 voted points, 13 classes",
+                           "device_ms": round(dv["ms_total"], 4), "device_GBps_algorithmic": round(dv["achieved_gbs"], 1),
+                           "host_ms": round(hs["ms_total"], 2), "host_merge": hs["merge"],
+                           "host_merge_counted": hs["merge_counted_in_total"]}
     except Exception as e:  # noqa: BLE001
         extra["voting"] = {"unavailable": repr(e)[:200]}
     if os.environ.get("PVCNN_BENCH_CONFIGS", "1") != "0":
-        extra["configs"] = configs_subresults(args)
-        extra["ops_vs_reference"] = ops_subresults()
+        # whole networks and the classic-op table run in child processes under ONE time budget (the driver's scaling run
+        # gives each N 870 s; these are informational and must never cost the line)
+        deadline = time.perf_counter() + float(os.environ.get("PVCNN_BENCH_EXTRAS_S", "300"))
+        extra["configs"] = configs_subresults(args, deadline)
+        extra["ops_vs_reference"] = ops_subresults(deadline)
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
     return extra
 
 
-def ops_subresults(timeout=240):
+def _child(cmd, timeout):
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    return p.returncode, [ln for ln in p.stdout.splitlines() if ln.startswith("{")], (p.stderr or "")[-120:]
+
+
+def ops_subresults(deadline):
     """The stand-alone ("classic") ops through the C ABI next to the reference's own CUDA kernels (oracle/_ref, built from
     the unmodified reference sources) on this GPU: tests/tools/ops_bench.py in a child process; median of 20 launches each,
     algorithmic GB/s where SURVEY.md 8d defines the bytes (profiles/r02_ops_vs_reference.md is the builder-run copy)."""
+    left = deadline - time.perf_counter()
+    if left < 30:
+        return {"unavailable": "sub-result time budget spent"}
     try:
-        env = dict(os.environ)
-        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
-            env.pop(k, None)
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "ops_bench.py")], capture_output=True,
-                           text=True, timeout=timeout, env=env, cwd=ROOT)
-        rows = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith("{")]
-        if p.returncode != 0 and not rows:
-            return {"unavailable": "rc=%d %s" % (p.returncode, (p.stderr or "")[-160:])}
-        return rows
+        rc, lines, err = _child([sys.executable, os.path.join(ROOT, "tests", "tools", "ops_bench.py")], min(150, left))
+        rows = [json.loads(ln) for ln in lines]
+        if not rows:
+            return {"unavailable": "rc=%d %s" % (rc, err)}
+        return {"columns": ["op", "ours_us", "reference_us", "ours_GBps_algorithmic"],
+                "rows": [[r["op"], r["ours_us"], r["reference_us"], r.get("ours_GBps_algorithmic")] for r in rows]}
     except subprocess.TimeoutExpired:
-        return {"unavailable": "timeout after %d s" % timeout}
+        return {"unavailable": "timeout"}
     except Exception as e:  # noqa: BLE001
-        return {"unavailable": repr(e)[:200]}
+        return {"unavailable": repr(e)[:120]}
 
 
-def configs_subresults(args, per_config_timeout=240):
+def configs_subresults(args, deadline):
     """BASELINE.json configs 2-5 (whole networks, pvcnn_b200/zoo.py) as sub-results of the default line, so that the
     driver's own run records them: each is `bench.py --config <name>` in a child process (a failure or a hang there
-    cannot touch this line), reduced to the numbers profiles/r02_configs.md tabulates.  PVCNN_BENCH_CONFIGS=0 skips it."""
-    out = {}
+    cannot touch this line), reduced to the numbers profiles/r02_configs.md tabulates: ms per step eager / as one CUDA
+    graph / comparison arm (same network and weights on the stand-alone sm_100a point ops + torch cuDNN/cuBLAS dense layers
+    with TF32 allowed).  10 timed steps after 3 warm-up, same precision mode as the line."""
+    out = {"columns": ["ms_per_step", "cuda_graph_ms", "comparison_arm_ms", "gpu_launches"]}
     for name in ("s3dis_pvcnn", "shapenet_c0p25_train", "pvcnn2", "frustum_pvcnne"):
-        t0 = time.perf_counter()
+        left = deadline - time.perf_counter()
+        if left < 30:
+            out[name] = "time budget spent"
+            continue
         try:
-            env = dict(os.environ)
-            for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
-                env.pop(k, None)
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", name, "--steps", "10", "--warmup", "3",
-                                "--precision", args.precision], capture_output=True, text=True, timeout=per_config_timeout,
-                               env=env, cwd=ROOT)
-            lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
-            if p.returncode != 0 or not lines:
-                out[name] = {"unavailable": "rc=%d %s" % (p.returncode, (p.stderr or "")[-160:])}
+            rc, lines, err = _child([sys.executable, os.path.abspath(__file__), "--config", name, "--steps", "10",
+                                     "--warmup", "3", "--precision", args.precision], min(150, left))
+            if rc != 0 or not lines:
+                out[name] = "unavailable: rc=%d %s" % (rc, err)
                 continue
             d = json.loads(lines[-1])
             g, c = d.get("cuda_graph") or {}, d.get("comparison_arm") or {}
-            out[name] = {"metric": d["metric"], "ms_per_step": d["ms_per_step"], "value": d["value"], "unit": d["unit"],
-                         "gpu_launches": d.get("gpu_launches"), "cuda_graph_ms": g.get("ms_per_step"),
-                         "comparison_arm_ms": c.get("ms_per_step"), "wall_s": round(time.perf_counter() - t0, 1)}
+            rnd = lambda v: None if v is None else round(v, 4)   # noqa: E731
+            out[name] = [rnd(d["ms_per_step"]), rnd(g.get("ms_per_step")), rnd(c.get("ms_per_step")), d.get("gpu_launches")]
         except subprocess.TimeoutExpired:
-            out[name] = {"unavailable": "timeout after %d s" % per_config_timeout}
+            out[name] = "unavailable: timeout"
         except Exception as e:  # noqa: BLE001
-            out[name] = {"unavailable": repr(e)[:200]}
-    out["note"] = ("10 timed steps after 3 warm-up each, same precision mode as this line; comparison_arm = same network and "
-                   "weights on the stand-alone sm_100a point ops + torch cuDNN/cuBLAS dense layers with TF32 allowed")
+            out[name] = "unavailable: " + repr(e)[:120]
     return out
 
 
