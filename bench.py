@@ -294,8 +294,11 @@ def run_ours(args):
             "modes": modes,
             "peaks": pk,
         }
+        ops_table = extra.pop("ops_vs_reference", None)
         line.update(extra)
         print(json.dumps(line))
+        if ops_table is not None:   # bulky and informational: kept off the ONE stdout line (stderr)
+            sys.stderr.write("[bench ops_vs_reference] " + json.dumps(ops_table) + "\n")
     if world > 1:
         dist.destroy_process_group()
 
@@ -329,13 +332,11 @@ def single_gpu_extras(torch, dev, m, args):
     except Exception:  # noqa: BLE001
         pass
     extra["roofline"] = {
-        "kernel": "conv_halo_kernel (3x3x3 conv forward / dgrad, tcgen05 kind::tf32, one smem halo per channel chunk, "
-                  "z shift in the epilogue)", "bound": "tensor",
+        "kernel": "conv_halo_kernel (3x3x3 conv fwd / dgrad, tcgen05 kind::tf32)", "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
         "traffic": traffic, "kernel_ms": k_ms, "traffic_source": traffic_src,
-        "note": "achieved = algorithmic FLOPs (2*B*R^3*Cout*Cin*27 = %.2f GFLOP) / CUDA-event time of a dense launch "
-                "run alone (random dense input); executed tensor FLOPs are %dx that. peak = %s bf16_tflops (burst) / 2: "
-                "MEASURED_PEAKS.json holds no direct tf32 measurement" % (CONV_FLOPS / 1e9, npass, pk["source"]),
+        "note": "achieved = algorithmic FLOPs (%.2f GFLOP) / CUDA-event time of a dense launch run alone; executed tensor "
+                "FLOPs are %dx that; peak = %s bf16 burst / 2 (no tf32 peak measured)" % (CONV_FLOPS / 1e9, npass, pk["source"]),
     }
     # the same kernel in the other precision (sub-result)
     npass2 = 1 if npass == 3 else 3
@@ -354,8 +355,7 @@ def single_gpu_extras(torch, dev, m, args):
         sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))  # checker-side tool: runs oracle/_ref (reference .so)
         import ref_gpu_time
         extra["reference_gpu"] = [ref_gpu_time.run(True, steps=10, warmup=5), ref_gpu_time.run(False, steps=5, warmup=2)]
-        extra["reference_gpu_note"] = ("the reference's own CUDA ops + cuDNN on this GPU, same inputs: [0] cuDNN default "
-                                       "(allow_tf32=True, what the reference runs), [1] allow_tf32=False (fp32-strict)")
+        extra["reference_gpu_note"] = "reference CUDA ops + cuDNN, same GPU and inputs: [0] its default (TF32), [1] fp32-strict"
     except Exception as e:  # noqa: BLE001
         extra["reference_gpu"] = {"unavailable": repr(e)[:200]}
     # test-time voting around the network (pvcnn_b200/evaluate.py): device arm with CUDA events next to
@@ -496,9 +496,8 @@ def cpu_baseline(sample_batch=2, iters=2):
     dt = (time.perf_counter() - t0) / iters
     return {"value": sample_batch * N / dt, "unit": "points/s", "cores": threads, "kind": "port",
             "ms_per_step": dt * 1e3, "iterations": iters, "warmup_passes": warm,
-            "sample": "B=%d of the 16 clouds (N=4096, C=64, R=32), fwd+bwd, %d timed iterations after %d untimed passes "
-                      "(1 warm-up + one per thread-count candidate); the reference has no CPU path, this is the oracle "
-                      "port (C kernels + torch CPU conv/BN)" % (sample_batch, iters, warm)}
+            "sample": "B=%d of the 16 clouds, fwd+bwd, %d timed iterations after %d untimed passes (warm-up + thread-count "
+                      "tuning); oracle port: the reference has no CPU path" % (sample_batch, iters, warm)}
 
 
 def run_reference(args):
