@@ -32,3 +32,19 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     """Under torchrun only rank 0 measures and prints; the other ranks exit 0 without work."""
     assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_informational_subresults_never_raise_and_respect_their_time_budget():
+    """configs / classic-op sub-results run in child processes under one deadline; without a GPU every child fails, which
+    must surface as an 'unavailable' entry (never an exception, never past the budget): the driver-read line survives."""
+    import time
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    t0 = time.perf_counter()
+    out = bench.configs_subresults(types.SimpleNamespace(precision="fp32"), t0 + 75)
+    assert set(out) == {"columns", "s3dis_pvcnn", "shapenet_c0p25_train", "pvcnn2", "frustum_pvcnne"}
+    assert all(isinstance(out[k], str) for k in out if k != "columns")          # 'unavailable: ...' / 'time budget spent'
+    ops = bench.ops_subresults(time.perf_counter() + 5)                          # < 30 s left: not even started
+    assert ops == {"unavailable": "sub-result time budget spent"}
+    assert time.perf_counter() - t0 < 150
