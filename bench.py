@@ -374,6 +374,7 @@ def single_gpu_extras(torch, dev, m, args):
         # whole networks and the classic-op table run in child processes under ONE time budget (the driver's scaling run
         # gives each N 870 s; these are informational and must never cost the line)
         deadline = time.perf_counter() + float(os.environ.get("PVCNN_BENCH_EXTRAS_S", "300"))
+        extra["cuda_graph"] = graph_subresult(args, deadline)
         extra["configs"] = configs_subresults(args, deadline)
         extra["ops_vs_reference"] = ops_subresults(deadline)
     extra["cpu_baseline"] = cpu_baseline(sample_batch=2, iters=2)
@@ -386,6 +387,27 @@ def _child(cmd, timeout):
         env.pop(k, None)
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
     return p.returncode, [ln for ln in p.stdout.splitlines() if ln.startswith("{")], (p.stderr or "")[-120:]
+
+
+def graph_subresult(args, deadline):
+    """the metric step replayed as one CUDA graph (run_graph_probe in a child process): device-timed and end to end"""
+    left = deadline - time.perf_counter()
+    if left < 30:
+        return {"unavailable": "sub-result time budget spent"}
+    try:
+        rc, lines, err = _child([sys.executable, os.path.abspath(__file__), "--graph-probe", "--steps", str(args.steps),
+                                 "--warmup", str(args.warmup), "--precision", args.precision], min(120, left))
+        if rc != 0 or not lines:
+            return {"unavailable": "rc=%d %s" % (rc, err)}
+        d = json.loads(lines[-1])
+        return {"ms_per_step": round(d["ms_per_step"], 4), "e2e_ms_per_step": round(d["e2e_ms_per_step"], 4),
+                "matches_eager": bool(d["matches_eager"] and d["e2e_host_output_matches"]),
+                "max_rel_diff": float("%.2e" % max(d["rel_diff_vs_eager"].values())),
+                "what": "same step as one CUDA-graph replay (graphs.GraphedTrainStep, child process); headline stays eager"}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timeout"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:120]}
 
 
 def ops_subresults(deadline):
@@ -523,6 +545,97 @@ def run_reference(args):
             "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def run_graph_probe(args):
+    """Child process of the default run (`modes.cuda_graph`): the SAME fwd+bwd step replayed as one CUDA graph
+    (pvcnn_b200/graphs.py::GraphedTrainStep), checked against an eager step on the same inputs, timed on the device, and
+    timed end to end with host buffers (two captured instances, double-buffered like the eager e2e loop).  Informational:
+    the headline numbers of the line stay the eager ones."""
+    import torch
+    import modules
+    from pvcnn_b200.graphs import GraphedTrainStep
+    from pvcnn_b200.parallel import GradBucket, pin_process_to_gpu_numa_node
+    os.environ["PVCNN_B200_PRECISION"] = args.precision
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    pin_process_to_gpu_numa_node(0)
+    torch.manual_seed(SEED)
+    m = modules.PVConv(C, C, 3, R).to(dev).train()
+    feats_h, coords_h, gout_h = [t.contiguous().pin_memory() for t in make_inputs(torch, dev)]
+    feats = feats_h.to(dev).requires_grad_(True)
+    coords, gout = coords_h.to(dev), gout_h.to(dev)
+    bucket = GradBucket(list(m.parameters()), dev).attach(m)
+    for _ in range(3):   # eager reference step (also the warm-up of every lazily created buffer)
+        bucket.zero()
+        feats.grad = None
+        out, _ = m((feats, coords))
+        out.backward(gout)
+    torch.cuda.synchronize()
+    o0, g0, p0 = out.detach().clone(), feats.grad.detach().clone(), bucket.flat.clone()
+    gts = [GraphedTrainStep(m, feats, coords, gout, bucket=bucket) for _ in range(2)]
+    o1, g1 = gts[0]()
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max())
+    diffs = {"out": rel(o1, o0), "grad_features": rel(g1, g0), "param_grads": rel(bucket.flat, p0)}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(max(3, args.warmup)):
+        gts[0].graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        gts[0].graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # end to end: pinned host buffers in and out every step, copies on a second stream, two captured instances
+    out_h = [torch.empty(B, C, N).pin_memory() for _ in range(2)]
+    gfe_h = [torch.empty(B, C, N).pin_memory() for _ in range(2)]
+    copy_stream, main_stream = torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+    up_done, comp_done, down_done = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(comp_done[k])
+            gts[k].f.copy_(feats_h, non_blocking=True)
+            gts[k].c.copy_(coords_h, non_blocking=True)
+            gts[k].go.copy_(gout_h, non_blocking=True)
+            up_done[k].record(copy_stream)
+
+    def e2e_loop(nsteps):
+        upload(0)
+        for i in range(nsteps):
+            k = i % 2
+            if i + 1 < nsteps:
+                upload((i + 1) % 2)
+            main_stream.wait_event(up_done[k])
+            main_stream.wait_event(down_done[k])
+            gts[k].graph.replay()
+            comp_done[k].record(main_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(comp_done[k])
+                out_h[k].copy_(gts[k].out, non_blocking=True)
+                gfe_h[k].copy_(gts[k].f.grad, non_blocking=True)
+                down_done[k].record(copy_stream)
+        copy_stream.synchronize()
+
+    for ev in comp_done + down_done:
+        ev.record(main_stream)
+    e2e_loop(4)
+    torch.cuda.synchronize()
+    e0.record()
+    e2e_loop(args.steps)
+    main_stream.wait_stream(copy_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ok = max(diffs.values()) < 1e-4
+    print(json.dumps({"ms_per_step": ms, "value": B * N / ms * 1e3, "e2e_ms_per_step": ms_e2e,
+                      "e2e_value": B * N / ms_e2e * 1e3, "unit": "points/s", "steps": args.steps,
+                      "precision": args.precision, "rel_diff_vs_eager": diffs, "matches_eager": ok,
+                      "e2e_host_output_matches": rel(out_h[(args.steps - 1) % 2].to(dev), o0) < 1e-4}))
 
 
 def run_config(args):
@@ -672,10 +785,13 @@ def main():
                                                             "frustum_pvcnne"],
                     help="metric (default): BASELINE.json's single-PVConv metric; the others: BASELINE configs 2-5 "
                          "(whole networks, 1 GPU)")
+    ap.add_argument("--graph-probe", action="store_true", help=argparse.SUPPRESS)   # child of the default run
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.graph_probe:
+        run_graph_probe(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.config != "metric":
         run_config(args)
