@@ -172,7 +172,7 @@ def run_ours(args):
     minimal = os.environ.get("PVCNN_BENCH_MINIMAL") == "1"  # profiling runs: timed loop only
     # ---- end-to-end: host buffers in, host buffers out, copies inside the timed region.
     # Every step copies ITS inputs from pinned host memory and returns ITS outputs (fused features + input gradient) to
-    # pinned host memory; the copies run on a second stream with two buffer sets, so step i+1's upload and step i's
+    # pinned host memory; the copies run on two side streams (one per direction) with two buffer sets, so step i+1's upload and step i's
     # download overlap step i+1's compute (ordering by CUDA events; nothing is skipped or reused across steps).
     nbuf = 2
     out_h = [torch.empty(bl, C, N).pin_memory() for _ in range(nbuf)]
@@ -182,19 +182,23 @@ def run_ours(args):
     g_d = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
     res_o = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
     res_g = [torch.empty(bl, C, N, device=dev) for _ in range(nbuf)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    # one stream per PCIe direction: uploads and downloads use different copy engines and the link is full duplex, so
+    # step i+1's inputs and step i's results travel at the same time (a single copy stream serialises them: 68 MB per
+    # step at ~29 GB/s took longer than the 2.07 ms of compute it was meant to hide behind)
+    up_stream = torch.cuda.Stream(device=dev)
+    down_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     up_done = [torch.cuda.Event() for _ in range(nbuf)]
     comp_done = [torch.cuda.Event() for _ in range(nbuf)]
     down_done = [torch.cuda.Event() for _ in range(nbuf)]
 
     def upload(k):
-        with torch.cuda.stream(copy_stream), torch.no_grad():
-            copy_stream.wait_event(comp_done[k])      # the previous user of this buffer set has finished computing
+        with torch.cuda.stream(up_stream), torch.no_grad():
+            up_stream.wait_event(comp_done[k])        # the previous user of this buffer set has finished computing
             f_d[k].copy_(feats_h, non_blocking=True)
             c_d[k].copy_(coords_h, non_blocking=True)
             g_d[k].copy_(gout_h, non_blocking=True)
-            up_done[k].record(copy_stream)
+            up_done[k].record(up_stream)
 
     def e2e_loop(nsteps):
         upload(0)
@@ -209,12 +213,13 @@ def run_ours(args):
                 res_o[k].copy_(out.detach())
                 res_g[k].copy_(f_d[k].grad)
             comp_done[k].record(main_stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(comp_done[k])
+            with torch.cuda.stream(down_stream):
+                down_stream.wait_event(comp_done[k])
                 out_h[k].copy_(res_o[k], non_blocking=True)
                 gfe_h[k].copy_(res_g[k], non_blocking=True)
-                down_done[k].record(copy_stream)
-        copy_stream.synchronize()
+                down_done[k].record(down_stream)
+        up_stream.synchronize()
+        down_stream.synchronize()
 
     for ev in comp_done + down_done:
         ev.record(main_stream)
@@ -224,7 +229,8 @@ def run_ours(args):
         barrier()
         e0.record()
         e2e_loop(args.steps)
-        main_stream.wait_stream(copy_stream)
+        main_stream.wait_stream(up_stream)
+        main_stream.wait_stream(down_stream)   # the timed region ends after the last result has reached host memory
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1) / args.steps
@@ -590,19 +596,20 @@ def run_graph_probe(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    # end to end: pinned host buffers in and out every step, copies on a second stream, two captured instances
+    # end to end: pinned host buffers in and out every step, copies on two side streams (one per direction), two captured instances
     out_h = [torch.empty(B, C, N).pin_memory() for _ in range(2)]
     gfe_h = [torch.empty(B, C, N).pin_memory() for _ in range(2)]
-    copy_stream, main_stream = torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
+    up_stream, down_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
     up_done, comp_done, down_done = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
 
     def upload(k):
-        with torch.cuda.stream(copy_stream), torch.no_grad():
-            copy_stream.wait_event(comp_done[k])
+        with torch.cuda.stream(up_stream), torch.no_grad():
+            up_stream.wait_event(comp_done[k])
             gts[k].f.copy_(feats_h, non_blocking=True)
             gts[k].c.copy_(coords_h, non_blocking=True)
             gts[k].go.copy_(gout_h, non_blocking=True)
-            up_done[k].record(copy_stream)
+            up_done[k].record(up_stream)
 
     def e2e_loop(nsteps):
         upload(0)
@@ -614,12 +621,13 @@ def run_graph_probe(args):
             main_stream.wait_event(down_done[k])
             gts[k].graph.replay()
             comp_done[k].record(main_stream)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(comp_done[k])
+            with torch.cuda.stream(down_stream):
+                down_stream.wait_event(comp_done[k])
                 out_h[k].copy_(gts[k].out, non_blocking=True)
                 gfe_h[k].copy_(gts[k].f.grad, non_blocking=True)
-                down_done[k].record(copy_stream)
-        copy_stream.synchronize()
+                down_done[k].record(down_stream)
+        up_stream.synchronize()
+        down_stream.synchronize()
 
     for ev in comp_done + down_done:
         ev.record(main_stream)
@@ -627,7 +635,8 @@ def run_graph_probe(args):
     torch.cuda.synchronize()
     e0.record()
     e2e_loop(args.steps)
-    main_stream.wait_stream(copy_stream)
+    main_stream.wait_stream(up_stream)
+    main_stream.wait_stream(down_stream)
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1) / args.steps
