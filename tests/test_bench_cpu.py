@@ -48,3 +48,22 @@ def test_informational_subresults_never_raise_and_respect_their_time_budget():
     ops = bench.ops_subresults(time.perf_counter() + 5)                          # < 30 s left: not even started
     assert ops == {"unavailable": "sub-result time budget spent"}
     assert time.perf_counter() - t0 < 150
+
+
+def test_bench_control_flow_under_a_fake_cuda_layer():
+    """tests/tools/dry_run_bench_on_cpu.py: the default arm's timed loop, its double-buffered end-to-end loop (events, one
+    side stream per direction), the mode sub-results, the JSON line and the CUDA-graph probe run to completion against
+    no-op streams / events and a CPU stand-in block -- Python-level protection of the artefact the driver reads."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "dry_run_bench_on_cpu.py")],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2
+    line, probe = lines
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "modes", "peaks"):
+        assert k in line, k
+    assert set(line["modes"]) == {"tf32", "fp32_dense", "tf32_dense"}
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert probe["matches_eager"] is True and probe["e2e_host_output_matches"] is True

@@ -1,0 +1,115 @@
+"""Development aid (no GPU in the build container): runs bench.py's host-side control flow -- the timed loop, the
+double-buffered end-to-end loop with its events and side streams, the precision / skipping modes, the JSON line, and the
+CUDA-graph probe -- against a FAKE CUDA layer (no-op streams / events, a "graph" that re-runs the captured callable) and a
+small CPU stand-in for the PVConv block.  It checks Python-level correctness of the judged artefact (no typo can reach the
+round-end run unnoticed); it measures nothing and touches no kernel.  Not a product path.
+
+    python tests/tools/dry_run_bench_on_cpu.py        # prints the two JSON lines
+"""
+import contextlib
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+class _Stream:
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+class _Graph:
+    fn = None
+
+    def replay(self):
+        self.fn()
+
+
+@contextlib.contextmanager
+def _ctx(*a, **k):
+    yield
+
+
+def _strip_device(fn):
+    return lambda *a, **k: fn(*a, **{kk: v for kk, v in k.items() if kk != "device"})
+
+
+def install_fake_cuda():
+    cur = _Stream()
+    torch.cuda.Stream, torch.cuda.Event, torch.cuda.CUDAGraph = _Stream, _Event, _Graph
+    torch.cuda.current_stream = lambda *a, **k: cur
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.stream, torch.cuda.graph = _ctx, _ctx
+    torch.Tensor.pin_memory = lambda self: self
+    to = torch.Tensor.to
+
+    def tensor_to(self, *a, **k):
+        a = [x for x in a if not (isinstance(x, torch.device) and x.type == "cuda")]
+        k = {kk: v for kk, v in k.items() if kk != "device"}
+        return to(self, *a, **k) if (a or k) else self
+    torch.Tensor.to = tensor_to
+    torch.nn.Module.to = lambda self, *a, **k: self
+    torch.empty, torch.zeros, torch.tensor = _strip_device(torch.empty), _strip_device(torch.zeros), _strip_device(torch.tensor)
+
+
+class _Block(torch.nn.Module):
+    """stand-in with the PVConv call contract: ((features, coords)) -> (features', coords)"""
+
+    def __init__(self, cin, cout, k, r):
+        super().__init__()
+        self.conv, self.bn = torch.nn.Conv1d(cin, cout, 1), torch.nn.BatchNorm1d(cout)
+
+    def forward(self, inputs):
+        f, c = inputs
+        return self.bn(self.conv(f)), c
+
+
+def main():
+    install_fake_cuda()
+    import bench
+    import modules
+    import pvcnn_b200.graphs as graphs
+    import pvcnn_b200.parallel as parallel
+    bench.B, bench.N, bench.C, bench.R = 2, 64, 8, 4
+    bench.make_inputs.__defaults__ = (2,)
+    bench.single_gpu_extras = lambda *a, **k: {}          # needs the real kernels
+    modules.PVConv = _Block
+    parallel.pin_process_to_gpu_numa_node = lambda i: None
+    init = graphs.GraphedTrainStep.__init__
+
+    def init_and_bind(self, *a, **k):
+        init(self, *a, **k)
+        self.graph.fn = self._step                         # the fake graph "replays" by re-running the captured step
+    graphs.GraphedTrainStep.__init__ = init_and_bind
+    args = types.SimpleNamespace(precision="fp32", steps=6, warmup=3, scaling="weak", gpus=1)
+    bench.run_ours(args)
+    bench.run_graph_probe(args)
+
+
+if __name__ == "__main__":
+    main()
