@@ -58,8 +58,11 @@ def test_bench_control_flow_under_a_fake_cuda_layer():
                        capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 2
-    line, probe = lines
+    assert len(lines) == 4
+    line, probe, cfg_eval, cfg_train = lines
+    for cfg in (cfg_eval, cfg_train):      # the children behind the `configs` sub-result (bench.configs_subresults reads these)
+        assert cfg["ms_per_step"] > 0 and "comparison_arm" in cfg and "gpu_launches" in cfg and "metric" in cfg
+    assert cfg_eval["cuda_graph"]["ms_per_step"] > 0 and cfg_train["cuda_graph"] is None
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "modes", "peaks"):
         assert k in line, k
