@@ -70,3 +70,20 @@ def test_bench_control_flow_under_a_fake_cuda_layer():
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
     assert probe["matches_eager"] is True and probe["e2e_host_output_matches"] is True
+
+
+def test_bench_control_flow_two_ranks_over_gloo():
+    """the same dry run as two processes (gloo standing in for NCCL): what the driver's scaling run exercises -- barrier /
+    max-over-ranks timing, the flat gradient bucket's all-reduce, the strong-scaling sub-result, rank 0 printing alone --
+    plus `--config` under torchrun (data-parallel train config, replica inference config)."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "dry_run_bench_on_cpu.py"), "--world", "2"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 3                                   # rank 0 only, one line per bench invocation
+    line, cfg_eval, cfg_train = lines
+    assert line["n_gpus"] == 2 and line["config"]["parallelism"] == "dp2" and line["scaling"] == "weak"
+    assert line["modes"]["strong_scaling"]["per_gpu_batch"] * 2 == line["modes"]["strong_scaling"]["global_batch"]
+    assert "roofline" not in line and "cpu_baseline" not in line          # rank 0 at N=1 only
+    assert cfg_eval["n_gpus"] == 2 and "replicas" in cfg_eval["config"]["parallelism"]
+    assert cfg_train["n_gpus"] == 2 and "all-reduce" in cfg_train["config"]["parallelism"]

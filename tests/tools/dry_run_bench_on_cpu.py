@@ -4,7 +4,8 @@ CUDA-graph probe -- against a FAKE CUDA layer (no-op streams / events, a "graph"
 small CPU stand-in for the PVConv block.  It checks Python-level correctness of the judged artefact (no typo can reach the
 round-end run unnoticed); it measures nothing and touches no kernel.  Not a product path.
 
-    python tests/tools/dry_run_bench_on_cpu.py        # prints the two JSON lines
+    python tests/tools/dry_run_bench_on_cpu.py             # N=1: default line, graph probe, two --config lines
+    python tests/tools/dry_run_bench_on_cpu.py --world 2   # N=2 over gloo: default line (+ strong scaling), --config lines
 """
 import contextlib
 import os
@@ -89,8 +90,34 @@ class _Block(torch.nn.Module):
         return self.bn(self.conv(f)), c
 
 
+def launch_world(world):
+    """N>1: the same dry run as `world` processes over gloo (what the driver's scaling run does with torchrun + NCCL)"""
+    import socket
+    import subprocess
+    rc = 0
+    for what in ("ours", "s3dis_pvcnn", "shapenet_c0p25_train"):       # one rendezvous (port) per bench invocation
+        sock = socket.socket()
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+        sock.close()
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                       MASTER_PORT=str(port), DRY_RUN_WHAT=what)
+            procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__)], env=env))
+        rc = max([rc] + [p.wait(timeout=300) for p in procs])
+    return rc
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--world":
+        sys.exit(launch_world(int(sys.argv[2])))
     install_fake_cuda()
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        import torch.distributed as dist
+        real_init = dist.init_process_group
+        dist.init_process_group = lambda backend=None, **k: real_init("gloo")     # CPU tensors: gloo stands in for NCCL
     import bench
     import modules
     import pvcnn_b200.graphs as graphs
@@ -106,9 +133,12 @@ def main():
         init(self, *a, **k)
         self.graph.fn = self._step                         # the fake graph "replays" by re-running the captured step
     graphs.GraphedTrainStep.__init__ = init_and_bind
-    args = types.SimpleNamespace(precision="fp32", steps=6, warmup=3, scaling="weak", gpus=1)
-    bench.run_ours(args)
-    bench.run_graph_probe(args)
+    what = os.environ.get("DRY_RUN_WHAT", "all")
+    args = types.SimpleNamespace(precision="fp32", steps=6, warmup=3, scaling="weak", gpus=world)
+    if what in ("all", "ours"):
+        bench.run_ours(args)
+    if what == "all":
+        bench.run_graph_probe(args)
     # `bench.py --config <network>` (the children behind the `configs` sub-result): one inference and one training network
     from pvcnn_b200 import zoo
 
@@ -134,7 +164,8 @@ def main():
         self.graph.fn = again
     graphs.GraphedInference.__init__ = ginit_and_bind
     for name in specs:
-        bench.run_config(types.SimpleNamespace(precision="fp32", steps=4, warmup=3, config=name))
+        if what in ("all", name):
+            bench.run_config(types.SimpleNamespace(precision="fp32", steps=4, warmup=3, config=name))
 
 
 if __name__ == "__main__":
