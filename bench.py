@@ -369,7 +369,7 @@ def single_gpu_extras(torch, dev, m, args):
     try:
         import voting_bench   # tests/tools: its host arm is a CPU baseline leg (reference numba function or oracle restatement)
         dv, hs = voting_bench.device_arm(20), voting_bench.host_arm(3)
-        extra["voting"] = {"workload": "one S3DIS evaluation batch around the network (eval.py:149-183): 10 windows x 8192 "
+        extra["voting"] = {"workload": "one S3DIS evaluation batch around the network (eval.py:149-179): 10 windows x 8192 "
                                        "points x 9 ch, 81920 voted points, 13 classes",
                            "device_ms": round(dv["ms_total"], 4), "device_GBps_algorithmic": round(dv["achieved_gbs"], 1),
                            "host_ms": round(hs["ms_total"], 2), "host_merge": hs["merge"],

@@ -339,34 +339,34 @@ PVCNN_API int pvcnn_pvconv_backward_phase(const pvcnn_pvconv_desc *d, const floa
 
 /* =====================================================================================================
  * Test-time voting on the device: the host loops of evaluate/s3dis/eval.py:149-215,
- * evaluate/shapenet/eval.py:146-197 and the window sampling of datasets/s3dis.py:88-90.  The reference builds the
+ * evaluate/shapenet/eval.py:149-201 and the window sampling of datasets/s3dis.py:86-89.  The reference builds the
  * voted inputs with numpy (tile / np.random.shuffle / fancy indexing per window), copies confidences and predictions
  * of every batch back to the host and merges them with numba loops; here every step is a kernel
  * (pvcnn_b200/csrc/eval_voting.cu) and only the final [3, classes] counters are read back.  Random choices use a
  * counter-based pseudo-random permutation (balanced Feistel network + cycle walking) keyed by (seed, window): the
  * result does not depend on how windows are batched; oracle/eval_voting.py restates it bit for bit.
  * ===================================================================================================== */
-/* eval.py:160-165 (shapenet eval.py:148-151): indices[w, :] = tile(arange(num_points[w]))[:nv], shuffled; int32 [b, nv].
+/* eval.py:161-164 (shapenet eval.py:151-154): indices[w, :] = tile(arange(num_points[w]))[:nv], shuffled; int32 [b, nv].
  * Window w of the call is stream first_window + w of the generator.  num_points[w] <= 0 gives zeros. */
 PVCNN_API int pvcnn_vote_indices(int b, int nv, unsigned long long seed, int first_window, const int *num_points,
                                  int *indices, void *stream);
-/* datasets/s3dis.py:88-89: np.random.choice(num_points[w], k, replace=(num_points[w] < k)) -> int32 [b, k] */
+/* datasets/s3dis.py:86-87: np.random.choice(num_points[w], k, replace=(num_points[w] < k)) -> int32 [b, k] */
 PVCNN_API int pvcnn_window_indices(int b, int k, unsigned long long seed, int first_window, const int *num_points,
                                    int *indices, void *stream);
-/* eval.py:166-172: out[(w*extra + e), c, j] = src[w, indices[w, e*npo + j], c]; src is [b, p, ch] (channels_last = 1:
- * the h5 window layout) or [b, ch, p] (channels_last = 0: shapenet eval.py:154-156); out [b*extra, ch, npo] is the
- * network input.  labels [b, p] -> out_labels [b, extra*npo] (datasets/s3dis.py:90), both NULL or both given. */
+/* eval.py:166-171: out[(w*extra + e), c, j] = src[w, indices[w, e*npo + j], c]; src is [b, p, ch] (channels_last = 1:
+ * the h5 window layout) or [b, ch, p] (channels_last = 0: shapenet eval.py:158-160); out [b*extra, ch, npo] is the
+ * network input.  labels [b, p] -> out_labels [b, extra*npo] (datasets/s3dis.py:89), both NULL or both given. */
 PVCNN_API int pvcnn_vote_gather(int b, int ch, int p, int extra, int npo, int channels_last, const float *src,
                                 const int *indices, float *out, const int *labels, int *out_labels, void *stream);
-/* eval.py:176: F.softmax(logits, dim=1)[:, c0:c1].max(dim=1) (c0 = 0, c1 = c for S3DIS; the shape's part classes for
- * ShapeNet, eval.py:160-162).  logits [b, c, n] -> conf fp32 [b, n], pred int32 [b, n] = absolute class index, first
+/* eval.py:173: F.softmax(logits, dim=1)[:, c0:c1].max(dim=1) (c0 = 0, c1 = c for S3DIS; the shape's part classes for
+ * ShapeNet, eval.py:162-165).  logits [b, c, n] -> conf fp32 [b, n], pred int32 [b, n] = absolute class index, first
  * maximal class on ties. */
 PVCNN_API int pvcnn_softmax_max(int b, int c, int n, int c0, int c1, const float *logits, float *conf, int *pred,
                                 void *stream);
 /* scene state: keys uint64 [scene_points] (confidence bits << 32 | ~sequence number), scene_pred int32 [scene_points].
- * pvcnn_vote_reset = eval.py:134-135 (confidence 0, prediction -1). */
+ * pvcnn_vote_reset = eval.py:136-137 (confidence 0, prediction -1). */
 PVCNN_API int pvcnn_vote_reset(long long scene_points, unsigned long long *keys, int *scene_pred, void *stream);
-/* update_scene_predictions (eval.py:189-204) / update_shape_predictions (shapenet eval.py:173-181): vote (w, p) with
+/* update_scene_predictions (eval.py:189-204) / update_shape_predictions (shapenet eval.py:177-185): vote (w, p) with
  * confidence conf[w, p] and class pred[w, p] goes to scene point mapping[w, indices[w, p]] (mapping int32 [b, p], the
  * rows of `indices_split_to_full` for these windows; NULL: the point is indices[w, p] itself) and replaces the entry
  * iff its confidence is strictly larger -- among equal confidences the earliest vote in (call, w, p) order wins, as in
@@ -374,11 +374,11 @@ PVCNN_API int pvcnn_vote_reset(long long scene_points, unsigned long long *keys,
 PVCNN_API int pvcnn_vote_merge(int b, int nv, int p, long long scene_points, unsigned int order_base, const float *conf,
                                const int *pred, const int *indices, const int *mapping, unsigned long long *keys,
                                int *scene_pred, void *stream);
-/* the scene's confidences (eval.py:134 `confidences`) as fp32 [scene_points] */
+/* the scene's confidences (eval.py:136 `confidences`) as fp32 [scene_points] */
 PVCNN_API int pvcnn_vote_confidences(long long scene_points, const unsigned long long *keys, float *conf, void *stream);
 /* update_stats (eval.py:207-215): stats uint64 [3, num_classes] += (ground-truth count, prediction count, agreement).
  * wrap_unvoted = 1: a point without a vote (prediction -1) is counted in the last class of row 1, as numba's
- * wrap-around indexing does in the reference; 0: it is counted nowhere (shapenet eval.py:184-197 tests
+ * wrap-around indexing does in the reference; 0: it is counted nowhere (shapenet eval.py:188-201 tests
  * `predictions == i`; its IoU per class is stats[2] / (stats[0] + stats[1] - stats[2])).
  * num_classes <= 2048.  The caller zeroes `stats` once per scene. */
 PVCNN_API int pvcnn_vote_stats(long long n, int num_classes, int wrap_unvoted, const int *gt, const int *pred,

@@ -2,11 +2,11 @@
 
 Restates, in numpy, what the reference's evaluation loops compute on the host:
   evaluate/s3dis/eval.py:149-215      (tile / shuffle / gather, softmax-max, update_scene_predictions, update_stats)
-  evaluate/shapenet/eval.py:146-197   (same scheme per shape, class range of the shape, per-shape IoU)
-  datasets/s3dis.py:88-90             (np.random.choice window sampling)
+  evaluate/shapenet/eval.py:149-201   (same scheme per shape, class range of the shape, per-shape IoU)
+  datasets/s3dis.py:86-89             (np.random.choice window sampling)
 The merge / statistics functions are PINNED against the reference's own numba functions: tests/golden/
 make_voting_golden.py imports them from /root/reference, runs them on seeded inputs (ties, unvoted points, several
-batches) and the outputs are committed as tests/golden/ref_voting_golden.npz (tests/test_golden_cpu.py).
+batches) and the outputs are committed as tests/golden/ref_voting_golden.npz (tests/test_voting_cpu.py).
 The random choices of the reference come from numpy's global generator, which a device cannot reproduce; the product
 draws them from a counter-based pseudo-random permutation instead (pvcnn_b200/csrc/eval_voting.cu), restated here bit
 for bit (`feistel_perm`), and the tests check the distribution-free properties of the reference's scheme on top
@@ -63,7 +63,7 @@ def feistel_perm(n, seed, stream, x=None):
 
 
 def vote_indices(num_points, nv, seed, first_window=0):
-    """evaluate/s3dis/eval.py:160-165 with the device generator: tile(arange(n_w))[:nv] shuffled = perm_nv(p) mod n_w.
+    """evaluate/s3dis/eval.py:161-164 with the device generator: tile(arange(n_w))[:nv] shuffled = perm_nv(p) mod n_w.
     num_points [b] -> int32 [b, nv]"""
     num_points = np.asarray(num_points).reshape(-1)
     out = np.zeros((num_points.size, nv), np.int32)
@@ -74,7 +74,7 @@ def vote_indices(num_points, nv, seed, first_window=0):
 
 
 def window_indices(num_points, k, seed, first_window=0):
-    """datasets/s3dis.py:88-89 with the device generator: a uniform k-subset in random order when n_w >= k, k independent
+    """datasets/s3dis.py:86-87 with the device generator: a uniform k-subset in random order when n_w >= k, k independent
     uniform draws otherwise.  num_points [b] -> int32 [b, k]"""
     num_points = np.asarray(num_points).reshape(-1)
     out = np.zeros((num_points.size, k), np.int32)
@@ -90,7 +90,7 @@ def window_indices(num_points, k, seed, first_window=0):
 
 
 def vote_inputs(window_data, indices, num_points):
-    """evaluate/s3dis/eval.py:158-172, literally: window_data [b, P, ch] -> [b * extra, ch, num_points]"""
+    """evaluate/s3dis/eval.py:157-171, literally: window_data [b, P, ch] -> [b * extra, ch, num_points]"""
     b, nv = indices.shape
     ch = window_data.shape[-1]
     batched = np.zeros((b, nv, ch), np.float32)
@@ -101,13 +101,13 @@ def vote_inputs(window_data, indices, num_points):
 
 
 def shape_inputs(point_set, indices, num_points):
-    """evaluate/shapenet/eval.py:154-156, literally: point_set [ch, P] -> [extra, ch, num_points]"""
+    """evaluate/shapenet/eval.py:158-160, literally: point_set [ch, P] -> [extra, ch, num_points]"""
     extra = indices.size // num_points
     return np.ascontiguousarray(point_set[:, indices].reshape(-1, extra, num_points).transpose(1, 0, 2))
 
 
 def softmax_max(logits, c0=0, c1=None):
-    """evaluate/s3dis/eval.py:176 / shapenet eval.py:159-162 through the reference's own torch calls (CPU fp32)"""
+    """evaluate/s3dis/eval.py:173 / shapenet eval.py:162-165 through the reference's own torch calls (CPU fp32)"""
     import torch
     import torch.nn.functional as F
     t = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32))
@@ -122,7 +122,7 @@ def update_scene_predictions(batched_confidences, batched_predictions, batched_s
     """evaluate/s3dis/eval.py:189-204, same signature, in place.  The sequential rule (replace iff strictly larger) means:
     per scene point the winner of a call is its most confident vote, the earliest one among equals, and it replaces the
     stored entry iff it is strictly more confident.  window_to_scene_mapping=None: shapenet's update_shape_predictions
-    (shapenet eval.py:173-181, the shuffled index is the point)."""
+    (shapenet eval.py:177-185, the shuffled index is the point)."""
     conf = np.asarray(batched_confidences).reshape(batch_size, total_num_voted_points)
     pred = np.asarray(batched_predictions).reshape(batch_size, total_num_voted_points)
     idx = np.asarray(batched_shuffled_point_indices).reshape(batch_size, total_num_voted_points)
@@ -163,7 +163,7 @@ def scene_counts(ground_truth, predictions, num_classes):
 
 
 def shape_iou(ground_truth, predictions, start_class, end_class):
-    """evaluate/shapenet/eval.py:184-197: mean over the shape's part classes of intersection / union (1 when both empty)"""
+    """evaluate/shapenet/eval.py:188-201: mean over the shape's part classes of intersection / union (1 when both empty)"""
     iou = 0.0
     for i in range(start_class, end_class):
         igt, ipd = ground_truth == i, predictions == i

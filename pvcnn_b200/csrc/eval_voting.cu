@@ -1,11 +1,11 @@
 // eval_voting.cu -- the reference's test-time voting loops on the device.
 //
-// evaluate/s3dis/eval.py:149-178 and evaluate/shapenet/eval.py:146-166 do, per batch of windows / per shape, on the
+// evaluate/s3dis/eval.py:149-179 and evaluate/shapenet/eval.py:149-168 do, per batch of windows / per shape, on the
 // host: tile arange(num_points_in_window) up to `total_num_voted_points`, np.random.shuffle it, gather the points,
 // run the network, softmax -> max over the classes, copy confidences and predictions back, and merge them into the
-// scene with a numba loop (`update_scene_predictions` :189-204 / `update_shape_predictions` :173-181: a vote replaces
+// scene with a numba loop (`update_scene_predictions` :189-204 / `update_shape_predictions` :177-185: a vote replaces
 // the scene's entry iff its confidence is strictly larger, so among equal confidences the EARLIEST vote in (window,
-// position) order wins); `update_stats` (:207-215) is a confusion histogram.  datasets/s3dis.py:88-90 draws the
+// position) order wins); `update_stats` (:207-215) is a confusion histogram.  datasets/s3dis.py:86-89 draws the
 // training sample of a window with np.random.choice.  Here every one of those steps is a kernel and nothing but the
 // final [3, classes] counters goes back to the host:
 //   vote_indices / window_indices   counter-based pseudo-random permutation (balanced Feistel network + cycle walking)
@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t vt_perm(const VtPerm &p, uint32_t x) {
   return x;
 }
 
-// eval.py:160-165: indices[w, p] = shuffle(tile(arange(n_w)))[:nv][p] = perm_nv(p) mod n_w  (tile(...)[q] = q mod n_w)
+// eval.py:161-164: indices[w, p] = shuffle(tile(arange(n_w)))[:nv][p] = perm_nv(p) mod n_w  (tile(...)[q] = q mod n_w)
 __global__ void __launch_bounds__(256) vote_indices_kernel(int nv, unsigned long long seed, int first_window,
                                                            const int *__restrict__ num_points,
                                                            int *__restrict__ indices) {
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) vote_indices_kernel(int nv, unsigned long
   indices[(size_t)w * nv + p] = v;
 }
 
-// datasets/s3dis.py:88-89: np.random.choice(n_w, k, replace=(n_w < k)).  Without replacement: the first k entries of a
+// datasets/s3dis.py:86-87: np.random.choice(n_w, k, replace=(n_w < k)).  Without replacement: the first k entries of a
 // random permutation of [0, n_w); with replacement: k independent uniform draws (multiply-high of a 32-bit variate).
 __global__ void __launch_bounds__(256) window_indices_kernel(int k, unsigned long long seed, int first_window,
                                                              const int *__restrict__ num_points,
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) window_indices_kernel(int k, unsigned lon
   indices[(size_t)w * k + j] = v;
 }
 
-// eval.py:166-172 (channels_last = 1: src [b, P, ch], one row per point) / shapenet eval.py:154-156 (channels_last = 0:
+// eval.py:166-171 (channels_last = 1: src [b, P, ch], one row per point) / shapenet eval.py:158-160 (channels_last = 0:
 // src [b, ch, P]): out[(w*extra + e), c, j] = src[w, indices[w, e*npo + j], c].  One thread per voted point: the
 // writes of a warp are 128 contiguous bytes per channel; the reads are one short row per thread (L2 resident windows).
-// Optional labels [b, P] -> out_labels [b, extra*npo] (datasets/s3dis.py:90).
+// Optional labels [b, P] -> out_labels [b, extra*npo] (datasets/s3dis.py:89).
 __global__ void __launch_bounds__(256) vote_gather_kernel(int ch, int P, int extra, int npo, int channels_last,
                                                           const float *__restrict__ src,
                                                           const int *__restrict__ indices,
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) vote_gather_kernel(int ch, int P, int ext
   if (labels != nullptr) out_labels[(size_t)w * nv + p] = labels[(size_t)w * P + i];
 }
 
-// eval.py:176: F.softmax(model(inputs), dim=1).max(dim=1)  /  shapenet eval.py:159-160 with the class range of the
+// eval.py:173: F.softmax(model(inputs), dim=1).max(dim=1)  /  shapenet eval.py:162-165 with the class range of the
 // shape.  softmax as torch evaluates it: exp(x - max) / sum; the arg-max keeps the FIRST maximal class (torch.max).
 // logits [b, c, n] -> conf [b, n], pred [b, n] (class index in [c0, c1)).  One thread per point, coalesced over n.
 __global__ void __launch_bounds__(256) softmax_max_kernel(int c, int n, int c0, int c1,
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) vote_reset_kernel(long long n, unsigned l
                                                          int *__restrict__ pred) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  keys[i] = 0ull;   // confidence 0 (eval.py:134)
-  pred[i] = -1;     // eval.py:135
+  keys[i] = 0ull;   // confidence 0 (eval.py:136)
+  pred[i] = -1;     // eval.py:137
 }
 
 // key of a vote: positive floats order like their bit patterns; the complemented sequence number makes the earliest
@@ -182,10 +182,10 @@ __device__ __forceinline__ long long vt_scene_index(int w, int p, int nv, int P,
   const int i = indices[(size_t)w * nv + p];
   if (mapping == nullptr) return (long long)i;                 // shapenet: the shuffled index is the point
   if (i < 0 || i >= P) return -1;
-  return (long long)mapping[(size_t)w * P + i];                // eval.py:198
+  return (long long)mapping[(size_t)w * P + i];                // eval.py:199
 }
 
-// ASSIGN = false: eval.py:199-202 as an atomic max;  ASSIGN = true (launched after it): the vote whose key won the
+// ASSIGN = false: eval.py:200-202 as an atomic max;  ASSIGN = true (launched after it): the vote whose key won the
 // point writes its class (:203); keys are unique per vote, so there is exactly one writer per point and launch.
 template <bool ASSIGN>
 __global__ void __launch_bounds__(256) vote_merge_kernel(int nv, int P, long long scene_points, unsigned int order_base,
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) vote_confidences_kernel(long long n,
 
 // eval.py:207-215: stats[0, gt]++, stats[1, pd]++, stats[2, gt]++ iff gt == pd.  A point that never received a vote
 // keeps pd = -1, which numba's wrap-around indexing counts in the LAST class of row 1; reproduced when wrap_unvoted
-// is set (shapenet's update_stats, eval.py:184-197, tests `predictions == i` and so ignores it: wrap_unvoted = 0).
+// is set (shapenet's update_stats, eval.py:188-201, tests `predictions == i` and so ignores it: wrap_unvoted = 0).
 // Grid-stride CTAs with a shared-memory histogram, flushed once per CTA.
 __global__ void __launch_bounds__(256) vote_stats_kernel(long long n, int num_classes, int wrap_unvoted,
                                                          const int *__restrict__ gt,

@@ -1,7 +1,7 @@
 """Test-time voting on the device: the host loops of the reference's evaluation scripts as kernels.
 
-Mirrors evaluate/s3dis/eval.py:131-183 (`evaluate_scene_file`, `SceneVotes`) and evaluate/shapenet/eval.py:125-167
-(`evaluate_shape`) and the window sampling of datasets/s3dis.py:88-90 (`sample_windows`).  The reference tiles,
+Mirrors evaluate/s3dis/eval.py:131-182 (`evaluate_scene_file`, `SceneVotes`) and evaluate/shapenet/eval.py:125-169
+(`evaluate_shape`) and the window sampling of datasets/s3dis.py:86-89 (`sample_windows`).  The reference tiles,
 shuffles and gathers the voted inputs with numpy per window, copies every batch's confidences / predictions back to the
 host and merges them with numba loops; here the windows are uploaded once, every step is a kernel of
 csrc/eval_voting.cu behind the C ABI (include/pvcnn_b200.h, "Test-time voting"), and only the final [3, classes]
@@ -35,7 +35,7 @@ def _dev_i32(x, device):
 
 
 def vote_indices(num_points_in_window, total_num_voted_points, seed, first_window=0, device=None):
-    """eval.py:160-165 for a batch of windows: int32 [b, nv] = tile(arange(n_w))[:nv], shuffled."""
+    """eval.py:161-164 for a batch of windows: int32 [b, nv] = tile(arange(n_w))[:nv], shuffled."""
     device = _default_device() if device is None else torch.device(device)
     n = _dev_i32(num_points_in_window, device).reshape(-1)
     out = torch.empty((n.numel(), int(total_num_voted_points)), dtype=torch.int32, device=n.device)
@@ -45,7 +45,7 @@ def vote_indices(num_points_in_window, total_num_voted_points, seed, first_windo
 
 
 def window_indices(num_points_in_window, num_points, seed, first_window=0, device=None):
-    """datasets/s3dis.py:88-89: np.random.choice(n_w, num_points, replace=(n_w < num_points)) -> int32 [b, num_points]"""
+    """datasets/s3dis.py:86-87: np.random.choice(n_w, num_points, replace=(n_w < num_points)) -> int32 [b, num_points]"""
     device = _default_device() if device is None else torch.device(device)
     n = _dev_i32(num_points_in_window, device).reshape(-1)
     out = torch.empty((n.numel(), int(num_points)), dtype=torch.int32, device=n.device)
@@ -55,7 +55,7 @@ def window_indices(num_points_in_window, num_points, seed, first_window=0, devic
 
 
 def vote_inputs(window_data, indices, num_points, channels_last=True, labels=None):
-    """eval.py:166-172: window_data [b, P, ch] (channels_last, the h5 layout) or [b, ch, P] -> network input
+    """eval.py:166-171: window_data [b, P, ch] (channels_last, the h5 layout) or [b, ch, P] -> network input
     [b * extra, ch, num_points] with extra = nv / num_points; optionally labels [b, P] -> [b, nv]."""
     if window_data.dtype != torch.float32 or indices.dtype != torch.int32:
         raise RuntimeError("vote_inputs: window_data must be float32 and indices int32")
@@ -79,7 +79,7 @@ def vote_inputs(window_data, indices, num_points, channels_last=True, labels=Non
 
 
 def softmax_max(logits, start_class=0, end_class=None):
-    """F.softmax(logits, dim=1)[:, start:end].max(dim=1) (eval.py:176; shapenet eval.py:159-162, with the class offset
+    """F.softmax(logits, dim=1)[:, start:end].max(dim=1) (eval.py:173; shapenet eval.py:162-165, with the class offset
     already added): logits [b, c, n] -> (confidences fp32 [b, n], predictions int32 [b, n])."""
     if logits.dim() != 3 or logits.dtype != torch.float32:
         raise RuntimeError("softmax_max: logits must be float32 [b, c, n]")
@@ -93,7 +93,7 @@ def softmax_max(logits, start_class=0, end_class=None):
 
 
 class SceneVotes:
-    """The per-scene state of eval.py:132-135 (`confidences` zeros, `predictions` -1) on the device, and the merge of
+    """The per-scene state of eval.py:136-137 (`confidences` zeros, `predictions` -1) on the device, and the merge of
     `update_scene_predictions` (:189-204).  One 64-bit word per scene point holds (confidence bits, ~sequence number of
     the vote), so an atomic max realises "replace iff strictly more confident, earliest vote wins ties"."""
 
@@ -126,7 +126,7 @@ class SceneVotes:
 
     @property
     def predictions(self):
-        """int32 [total_num_points]; -1 where no vote with a positive confidence arrived (eval.py:135)"""
+        """int32 [total_num_points]; -1 where no vote with a positive confidence arrived (eval.py:137)"""
         return self._pred
 
     @property
@@ -150,7 +150,7 @@ class SceneVotes:
 
 def evaluate_scene_file(model, scene_data, scene_num_points, window_to_scene_mapping, votes, *, num_points, num_votes,
                         batch_size, seed=0, first_window=0):
-    """One h5 file of a scene, as eval.py:139-182: scene_data [num_windows, P, ch] fp32, scene_num_points [num_windows],
+    """One h5 file of a scene, as eval.py:139-179: scene_data [num_windows, P, ch] fp32, scene_num_points [num_windows],
     window_to_scene_mapping [num_windows, P] -> merged into `votes` (a SceneVotes).  The windows are uploaded once; per
     batch of windows: indices -> gathered inputs -> model -> softmax-max -> merge, all on the device."""
     device = votes.predictions.device
@@ -165,31 +165,31 @@ def evaluate_scene_file(model, scene_data, scene_num_points, window_to_scene_map
         idx = vote_indices(npts[lo:hi], total_num_voted_points, seed, first_window + lo, device)
         inputs = vote_inputs(scene_data[lo:hi], idx, num_points)
         with torch.no_grad():
-            conf, pred = softmax_max(model(inputs))                                        # eval.py:175-176
+            conf, pred = softmax_max(model(inputs))                                        # eval.py:172-173
         votes.update(conf.view(hi - lo, total_num_voted_points), pred.view(hi - lo, total_num_voted_points), idx,
                      mapping[lo:hi])
     return votes
 
 
 def evaluate_shape(model, point_set, *, num_points, num_votes, start_class, end_class, seed=0, shape_index=0):
-    """One ShapeNet shape, as shapenet eval.py:146-166: point_set [ch, n] fp32 -> SceneVotes over its n points."""
+    """One ShapeNet shape, as shapenet eval.py:149-168: point_set [ch, n] fp32 -> SceneVotes over its n points."""
     point_set = torch.as_tensor(point_set)
     device = point_set.device if point_set.is_cuda else _default_device()
     point_set = point_set.to(device=device, dtype=torch.float32).contiguous()
     n = point_set.shape[1]
-    extra_batch_size = num_votes * math.ceil(n / num_points)                               # shapenet eval.py:146
+    extra_batch_size = num_votes * math.ceil(n / num_points)                               # shapenet eval.py:149
     total_num_voted_points = extra_batch_size * num_points
     votes = SceneVotes(n, device)
     idx = vote_indices([n], total_num_voted_points, seed, shape_index, device)
     inputs = vote_inputs(point_set[None], idx, num_points, channels_last=False)
     with torch.no_grad():
-        conf, pred = softmax_max(model(inputs), start_class, end_class)                    # shapenet eval.py:158-162
+        conf, pred = softmax_max(model(inputs), start_class, end_class)                    # shapenet eval.py:161-165
     votes.update(conf.view(1, -1), pred.view(1, -1), idx, None)
     return votes
 
 
 def shape_iou(counts, start_class, end_class):
-    """update_stats of evaluate/shapenet/eval.py:184-197 from the [3, classes] counters of `SceneVotes.stats(...,
+    """update_stats of evaluate/shapenet/eval.py:188-201 from the [3, classes] counters of `SceneVotes.stats(...,
     wrap_unvoted=False)`: mean over the shape's part classes of intersection / union, 1 where the union is empty
     (union = |gt == i| + |pred == i| - |both|).  Host arithmetic on <= 50 numbers."""
     c = torch.as_tensor(counts).to("cpu", torch.float64)[:, int(start_class):int(end_class)]
@@ -199,7 +199,7 @@ def shape_iou(counts, start_class, end_class):
 
 
 def sample_windows(window_data, window_labels, window_num_points, num_points, seed=0, first_window=0):
-    """datasets/s3dis.py:88-92 for a batch of windows already on the device: window_data [b, P, ch], window_labels [b, P],
+    """datasets/s3dis.py:86-94 for a batch of windows already on the device: window_data [b, P, ch], window_labels [b, P],
     window_num_points [b] -> (data [b, ch, num_points] fp32, labels [b, num_points] int64)."""
     idx = window_indices(window_num_points, num_points, seed, first_window, window_data.device)
     data, labels = vote_inputs(window_data, idx, num_points, labels=window_labels)
@@ -219,7 +219,7 @@ def scenes_of_rank(num_scenes, rank=None, world=None):
 
 
 def all_reduce_stats(stats, group=None):
-    """The one exchange step of a sharded evaluation: `stats` [3, classes, scenes] (eval.py:130) holds this rank's scenes'
+    """The one exchange step of a sharded evaluation: `stats` [3, classes, scenes] (eval.py:131) holds this rank's scenes'
     columns and zeros elsewhere; a SUM all-reduce gives every rank the full table.  int64 counters, NCCL or gloo."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

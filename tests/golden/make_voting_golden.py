@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference and numba; no GPU): the merge / statistics functions of
 evaluate/s3dis/eval.py (`update_scene_predictions` :189-204, `update_stats` :207-215) and evaluate/shapenet/eval.py
-(`update_shape_predictions` :173-181, `update_stats` :184-197) are imported from the reference files where they lie and
+(`update_shape_predictions` :177-185, `update_stats` :188-201) are imported from the reference files where they lie and
 executed (numba-compiled, as the reference runs them) on seeded inputs that exercise what a parallel merge can get
 wrong: heavily tied confidences, several sequential batches into one scene, scene points that never receive a vote
 (prediction stays -1 and is counted in the last class by numba's wrap-around), confidences equal to the initial 0.
@@ -27,7 +27,7 @@ def _load(name, rel):
 
 
 def s3dis_case(ref, g, scene_points, num_windows, window_points, nv, batch_size, num_classes, quant):
-    """one scene merged batch by batch exactly like evaluate/s3dis/eval.py:149-183"""
+    """one scene merged batch by batch exactly like evaluate/s3dis/eval.py:149-182"""
     mapping = g.integers(0, scene_points, size=(num_windows, window_points)).astype(np.int64)
     num_pts = g.integers(max(1, window_points // 3), window_points + 1, size=num_windows).astype(np.int64)
     confidences = np.zeros(scene_points, np.float32)
@@ -53,7 +53,7 @@ def s3dis_case(ref, g, scene_points, num_windows, window_points, nv, batch_size,
 
 
 def shapenet_case(ref, g, n, nv, num_classes, start_class, end_class, quant):
-    """one shape as in evaluate/shapenet/eval.py:146-166"""
+    """one shape as in evaluate/shapenet/eval.py:149-169"""
     confidences = np.zeros(n, np.float32)
     predictions = np.full(n, -1, np.int64)
     conf = g.random(nv, dtype=np.float32)

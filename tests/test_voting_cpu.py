@@ -1,11 +1,11 @@
 """CPU tests of the test-time voting oracle (oracle/eval_voting.py).
 
 1. Pinned: the merge / statistics restatements equal the REFERENCE's own numba functions
-   (evaluate/s3dis/eval.py:189-215, evaluate/shapenet/eval.py:173-197) on tests/golden/ref_voting_golden.npz, which
+   (evaluate/s3dis/eval.py:189-215, evaluate/shapenet/eval.py:177-201) on tests/golden/ref_voting_golden.npz, which
    tests/golden/make_voting_golden.py produced by importing and running the unmodified reference files.
 2. Generator: the counter-based permutation is a permutation; the voted indices have the multiset the reference's
    tile + shuffle produces; window sampling is a subset without replacement / in range with replacement.
-3. The literal input tiling of eval.py:158-172 equals the index formula the device kernel uses.
+3. The literal input tiling of eval.py:157-171 equals the index formula the device kernel uses.
 """
 import os
 
@@ -116,7 +116,7 @@ def test_vote_indices_multiset_matches_tile_and_shuffle():
             assert not idx[w].any()
             continue
         counts = np.bincount(idx[w], minlength=n)
-        expect = np.bincount(np.tile(np.arange(n), -(-nv // n))[:nv], minlength=n)   # eval.py:161-163
+        expect = np.bincount(np.tile(np.arange(n), -(-nv // n))[:nv], minlength=n)   # eval.py:161-163 (num_repeats, np.tile, [:nv])
         assert np.array_equal(np.sort(counts), np.sort(expect))
         assert counts.size == n and counts.min() >= nv // n and counts.max() <= -(-nv // n)
     # batching invariance: window 12 alone equals row 2 of the batch that started at window 10

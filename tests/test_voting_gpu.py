@@ -3,7 +3,7 @@
 The merge / statistics kernels are compared with the REFERENCE's own outputs: tests/golden/ref_voting_golden.npz holds
 what the unmodified numba functions of evaluate/s3dis/eval.py and evaluate/shapenet/eval.py produced (tests/golden/
 make_voting_golden.py); integer results must be bit-exact.  Index generation is compared bit for bit with the oracle's
-restatement of the counter-based generator, the gather with the literal numpy tiling of eval.py:158-172, softmax-max
+restatement of the counter-based generator, the gather with the literal numpy tiling of eval.py:157-171, softmax-max
 with the reference's torch calls (1e-5 relative, the north-star tolerance for fp32)."""
 import os
 
@@ -66,9 +66,9 @@ def test_vote_gather_equals_literal_numpy_tiling():
     npts = np.array([777, 300, 1, 512, 700], np.int32)
     idx = ev.vote_indices(npts, extra * npo, 5)
     out, lab = E.vote_inputs(_cuda(data), _cuda(idx), npo, labels=_cuda(labels))
-    assert np.array_equal(out.cpu().numpy(), ev.vote_inputs(data, idx, npo))                  # eval.py:158-172
+    assert np.array_equal(out.cpu().numpy(), ev.vote_inputs(data, idx, npo))                  # eval.py:157-171
     assert np.array_equal(lab.cpu().numpy(), np.take_along_axis(labels, idx.astype(np.int64), 1))
-    # shapenet layout: point_set [ch, n] (shapenet eval.py:154-156)
+    # shapenet layout: point_set [ch, n] (shapenet eval.py:158-160)
     ps = g.standard_normal((ch, p)).astype(np.float32)
     so = E.vote_inputs(_cuda(ps)[None], _cuda(idx[:1]), npo, channels_last=False)
     assert np.array_equal(so.cpu().numpy(), ev.shape_inputs(ps, idx[0], npo))
@@ -137,7 +137,7 @@ def test_shape_merge_and_iou_equal_reference_numba_outputs(gold, name):
     assert np.array_equal(votes.confidences.cpu().numpy(), c["out_conf"])
     num_classes, c0, c1 = (int(v) for v in c["classes"])
     counts = votes.stats(c["gt"], num_classes, wrap_unvoted=False).cpu().numpy()
-    assert abs(ev.shape_iou_from_counts(counts, c0, c1) - float(c["iou"])) < 1e-12       # shapenet eval.py:184-197
+    assert abs(ev.shape_iou_from_counts(counts, c0, c1) - float(c["iou"])) < 1e-12       # shapenet eval.py:188-201
     assert abs(E.shape_iou(counts, c0, c1) - float(c["iou"])) < 1e-12
 
 
@@ -161,7 +161,7 @@ def test_vote_stats_vs_oracle_both_conventions(n, num_classes):
 
 
 class _PointwiseNet(torch.nn.Module):
-    """a fixed per-point classifier standing in for the network (eval.py:175 only needs [B, classes, N] logits)"""
+    """a fixed per-point classifier standing in for the network (eval.py:173 only needs [B, classes, N] logits)"""
 
     def __init__(self, ch, num_classes):
         super().__init__()
@@ -174,7 +174,7 @@ class _PointwiseNet(torch.nn.Module):
 
 @pytest.mark.parametrize("batch_size", [2, 5])
 def test_evaluate_scene_file_equals_the_reference_loop(batch_size):
-    """the whole loop of evaluate/s3dis/eval.py:139-183 on the device vs its restatement (oracle indices, literal numpy
+    """the whole loop of evaluate/s3dis/eval.py:139-182 on the device vs its restatement (oracle indices, literal numpy
     tiling, reference merge restatement pinned to numba) driven by the same per-vote confidences"""
     from pvcnn_b200 import evaluate as E
     g = np.random.default_rng(11)
@@ -222,7 +222,7 @@ def test_evaluate_shape_equals_the_reference_loop():
     ev.update_scene_predictions(conf.cpu().numpy().reshape(1, nv), pred.cpu().numpy().reshape(1, nv), idx, conf_s, pred_s,
                                 None, nv, 1, 0)
     assert np.array_equal(votes.predictions.cpu().numpy().astype(np.int64), pred_s)
-    assert (pred_s >= c0).all() and (pred_s < c1).all()       # nv >= n: every point is voted (shapenet eval.py:146-150)
+    assert (pred_s >= c0).all() and (pred_s < c1).all()       # nv >= n: every point is voted (shapenet eval.py:149-153)
 
 
 def test_sample_windows_matches_choice_semantics_and_oracle():
@@ -236,6 +236,6 @@ def test_sample_windows_matches_choice_semantics_and_oracle():
     idx = ev.window_indices(npts, k, 21, 3).astype(np.int64)
     assert out.shape == (b, ch, k) and lab.dtype == torch.int64
     for w in range(b):
-        assert np.array_equal(out[w].cpu().numpy(), data[w][idx[w]].T)        # datasets/s3dis.py:90
+        assert np.array_equal(out[w].cpu().numpy(), data[w][idx[w]].T)        # datasets/s3dis.py:88-89
         assert np.array_equal(lab[w].cpu().numpy(), labels[w][idx[w]])
         assert idx[w].max() < npts[w]

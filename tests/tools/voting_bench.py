@@ -1,13 +1,13 @@
-"""Times the test-time voting steps AROUND the network (evaluate/s3dis/eval.py:149-183 without :175): host arm vs device arm.
+"""Times the test-time voting steps AROUND the network (evaluate/s3dis/eval.py:149-179 without the model call of :173): host arm vs device arm.
 
 Workload = one batch of the reference's S3DIS evaluation: batch_size 10 windows (configs/s3dis/__init__.py:22) of up to
 8192 points x 9 channels (data/s3dis/prepare_data.py:88), num_points 4096, num_votes 1 -> extra_batch_size 2, 8192 voted
 points per window, 13 classes; scene of 1 M points.
 
   host arm    the reference's own steps on the host cores: np.tile / np.random.shuffle / fancy indexing per window
-              (:158-172) and the merge through the reference's numba function when /root/reference is importable
+              (:155-171) and the merge through the reference's numba function when /root/reference is importable
               (else the oracle restatement) -- what the reference pays on the HOST per batch next to the network, not
-              counting its H2D / D2H copies.  (softmax + max run on the device in the reference too, :176; the torch-CPU
+              counting its H2D / D2H copies.  (softmax + max run on the device in the reference too, :173; the torch-CPU
               time of that step is printed for information and is not part of `ms_total`.)
   device arm  pvcnn_b200.evaluate: vote_indices + vote_inputs + softmax_max + SceneVotes.update, CUDA events.
 
@@ -61,7 +61,7 @@ def host_arm(iters):
     t_tile = t_soft = t_merge = 0.0
     for it in range(iters + 1):
         t0 = time.perf_counter()
-        batched_inputs = np.zeros((BATCH, nv, CH), dtype=np.float32)                       # eval.py:158-166
+        batched_inputs = np.zeros((BATCH, nv, CH), dtype=np.float32)                       # eval.py:157-166
         batched_idx = np.zeros((BATCH, nv), dtype=np.int64)
         for w in range(BATCH):
             n = npts[w]
@@ -71,10 +71,10 @@ def host_arm(iters):
             batched_inputs[w] = data[w][idx]
         inputs = torch.from_numpy(batched_inputs.reshape((BATCH * extra, NPO, -1)).transpose(0, 2, 1)).float().contiguous()
         t1 = time.perf_counter()
-        conf, pred = F.softmax(torch.from_numpy(logits), dim=1).max(dim=1)                 # eval.py:176-178
+        conf, pred = F.softmax(torch.from_numpy(logits), dim=1).max(dim=1)                 # eval.py:173-175
         conf, pred = conf.view(BATCH, nv).numpy(), pred.view(BATCH, nv).numpy()
         t2 = time.perf_counter()
-        merge(conf, pred, batched_idx, conf_s, pred_s, mapping, nv, BATCH, 0)              # eval.py:180-182
+        merge(conf, pred, batched_idx, conf_s, pred_s, mapping, nv, BATCH, 0)              # eval.py:177-179
         t3 = time.perf_counter()
         if it:   # first pass = numba compilation / warm-up
             t_tile += t1 - t0
