@@ -169,7 +169,7 @@ class S3DISPVCNN2(nn.Module):
             cin = extra = stage[-1].out_channels
             sa_layers.append(stage[0] if len(stage) == 1 else nn.Sequential(*stage))
         self.sa_layers = nn.ModuleList(sa_layers)
-        # ---- feature propagation (models/utils.py:117-146); only the last FP module sees the raw extra features
+        # ---- feature propagation (models/utils.py:112-140); only the last FP module sees the raw extra features
         sa_in[0] = extra_feature_channels
         fp_layers = []
         for i, (fp_widths, conv_cfg) in enumerate(self.fp_table):
@@ -199,7 +199,7 @@ class S3DISPVCNN2(nn.Module):
 
 
 class _InstanceSegPVCNN(nn.Module):
-    """models/kitti/frustum/segmentation/pointnet.py:9-69 (InstanceSegmentationPVCNN)."""
+    """models/kitti/frustum/segmentation/pointnet.py:9-66 (InstanceSegmentationPVCNN)."""
     point_table = ((64, 2, 16), (64, 1, 12), (128, 1, 12), (1024, 1, None))
 
     def __init__(self, num_classes=3, extra_feature_channels=1, width_multiplier=1, voxel_resolution_multiplier=1):
@@ -225,7 +225,7 @@ class _InstanceSegPVCNN(nn.Module):
 
 
 class _CenterRegression(nn.Module):
-    """models/kitti/frustum/center_regression_net.py:9-34."""
+    """models/kitti/frustum/center_regression_net.py:9-32."""
 
     def __init__(self, num_classes=3, width_multiplier=1):
         super().__init__()
@@ -240,7 +240,7 @@ class _CenterRegression(nn.Module):
 
 
 class _BoxEstimationPointNet(nn.Module):
-    """models/kitti/frustum/box_estimation/pointnet.py:9-55."""
+    """models/kitti/frustum/box_estimation/pointnet.py:9-47."""
     table = ((128, 2, None), (256, 1, None), (512, 1, None))
 
     def __init__(self, num_classes=3, num_heading_angle_bins=12, num_size_templates=8, width_multiplier=1):
