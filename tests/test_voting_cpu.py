@@ -148,3 +148,18 @@ def test_vote_inputs_literal_tiling_equals_index_formula():
     so = ev.shape_inputs(ps, idx[0], npo)
     assert so.shape == (extra, ch, npo)
     assert np.array_equal(so[2, :, 5], ps[:, idx[0, 2 * npo + 5]])
+
+
+def test_kernel_source_under_cpu_emulation():
+    """tests/tools/emulate_voting_on_cpu.py compiles the UNMODIFIED csrc/eval_voting.cu with g++ behind a small CUDA shim
+    (thread-local blockIdx / threadIdx, atomics as GCC builtins, real threads where the kernel synchronises) and runs the
+    whole GPU test file against it: kernel logic, launch geometry and the ctypes argument order are checked without a GPU.
+    Test infrastructure only -- the product library has no CPU path (tests/test_abi_cpu.py::test_voting_host_api_has_no_cpu_path)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "emulate_voting_on_cpu.py")],
+                       capture_output=True, text=True, cwd=root, timeout=900,
+                       env=dict(os.environ, PVCNN_TEST_BUDGET_S="0"))
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-1500:])
+    assert "30 passed" in p.stdout
